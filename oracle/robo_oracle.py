@@ -1,0 +1,316 @@
+"""numpy/scipy restatement of RoBO's GP-posterior + acquisition hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity status: PINNED —
+oracle/make_golden.py executes the reference's own classes
+(/root/reference/robo/models/gaussian_process.py, robo/acquisition_functions/*)
+on top of oracle.george_oracle and asserts that every function below returns
+the same numbers; the resulting vectors are committed under tests/golden/.
+
+The restatement is *functional* (explicit state dict instead of a model object)
+so that it cannot be confused with, or imported as, the product classes.
+"""
+import numpy as np
+import scipy.linalg as spla
+from scipy.special import ndtr, log_ndtr
+
+from oracle import george_oracle as G
+
+EPS = np.finfo(np.float64).eps
+LOG_SQRT_2PI = 0.5 * np.log(2.0 * np.pi)
+
+
+# --------------------------------------------------------------------------- #
+# robo/util/normalization.py
+# --------------------------------------------------------------------------- #
+def zero_one_normalization(X, lower=None, upper=None):
+    """robo/util/normalization.py:4-13."""
+    if lower is None:
+        lower = np.min(X, axis=0)
+    if upper is None:
+        upper = np.max(X, axis=0)
+    return np.true_divide((X - lower), (upper - lower)), lower, upper
+
+
+def zero_one_unnormalization(Xn, lower, upper):
+    """robo/util/normalization.py:16-17."""
+    return lower + (upper - lower) * Xn
+
+
+def zero_mean_unit_var_normalization(y):
+    """robo/util/normalization.py:20-28 (population std, ddof=0)."""
+    mean = np.mean(y, axis=0)
+    std = np.std(y, axis=0)
+    return (y - mean) / std, mean, std
+
+
+# --------------------------------------------------------------------------- #
+# robo/models/gaussian_process.py
+# --------------------------------------------------------------------------- #
+def gp_fit(kernel, X, y, noise=1e-3, normalize_input=True, normalize_output=False,
+           lower=None, upper=None):
+    """GaussianProcess.train(..., do_optimize=False): gaussian_process.py:70-124.
+
+    Returns a state dict holding everything predict/nll need.  ``kernel`` is a
+    george_oracle kernel; it is used as is (hyper-parameters are NOT optimised
+    here, see gp_nll for the objective scipy minimises).
+    """
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    assert X.shape[0] == y.shape[0] and X.ndim == 2 and y.ndim == 1   # base_model.py:66-72
+    st = dict(kernel=kernel, normalize_input=normalize_input,
+              normalize_output=normalize_output, lower=lower, upper=upper)
+    if normalize_input:                                               # :89-93
+        st["X"], st["lower"], st["upper"] = zero_one_normalization(X, lower, upper)
+    else:
+        st["X"] = X
+    if normalize_output:                                              # :95-101
+        st["y"], st["y_mean"], st["y_std"] = zero_mean_unit_var_normalization(y)
+        if st["y_std"] == 0:
+            raise ValueError("Cannot normalize output. All targets have the same value")
+    else:
+        st["y"] = y
+    st["mean"] = np.mean(st["y"], axis=0)                             # :104
+    gp = G.GP(kernel, mean=st["mean"])                                # :106
+    st["hypers"] = np.append(kernel.get_parameter_vector(), np.log(noise))   # :113-114
+    try:                                                              # :118-122
+        gp.compute(st["X"], yerr=np.sqrt(noise))
+    except np.linalg.LinAlgError:
+        noise *= 10
+        gp.compute(st["X"], yerr=np.sqrt(noise))
+    st["noise"] = noise
+    st["gp"] = gp
+    return st
+
+
+def gp_nll(st, theta, prior=None):
+    """GaussianProcess.nll: gaussian_process.py:129-166 (mutates st['kernel'])."""
+    theta = np.asarray(theta, dtype=np.float64)
+    if np.any((-20 > theta) + (theta > 20)):                          # :147-148
+        return 1e25
+    gp = st["gp"]
+    gp.kernel.set_parameter_vector(theta[:-1])                        # :151
+    noise = np.exp(theta[-1])                                         # :152
+    try:
+        gp.compute(st["X"], yerr=np.sqrt(noise))                      # :155
+    except np.linalg.LinAlgError:
+        return 1e25
+    ll = gp.log_likelihood(st["y"], quiet=True)                       # :159
+    if prior is not None:
+        ll += prior.lnprob(theta)                                     # :162-163
+    return -ll if np.isfinite(ll) else 1e25                           # :166
+
+
+def gp_loglik_terms(st):
+    """(log-likelihood, log-determinant) of the current factorisation."""
+    gp = st["gp"]
+    return gp.log_likelihood(st["y"], quiet=True), gp.solver.log_determinant
+
+
+def gp_predict(st, X_test, full_cov=False):
+    """GaussianProcess.predict: gaussian_process.py:251-296.
+
+    Faithful to the reference: george returns the full M x M covariance
+    (:280), the diagonal is taken afterwards (:285-286), then the clip (:290-294).
+    """
+    X_test = np.asarray(X_test, dtype=np.float64)
+    assert X_test.ndim == 2                                           # base_model.py:74-79
+    if st["normalize_input"]:
+        Xs, _, _ = zero_one_normalization(X_test, st["lower"], st["upper"])   # :276
+    else:
+        Xs = X_test
+    mu, var = st["gp"].predict(st["y"], Xs)                           # :280
+    if st["normalize_output"]:                                        # :282-284
+        mu = mu * st["y_std"] + st["y_mean"]
+        var = var * st["y_std"] ** 2
+    if not full_cov:
+        var = np.diag(var)                                            # :286
+    var = np.clip(var, EPS, np.inf)                                   # :290-294 (the :294 zeroing is a no-op after the clip)
+    return mu, var
+
+
+def gp_predict_var_only(st, X_test):
+    """CPU-optimised variant (BASELINE.md section 3 row ii): variance through one
+    triangular solve, never forming the M x M covariance.  Same mean/variance as
+    gp_predict up to rounding; used only as a second CPU baseline."""
+    X_test = np.asarray(X_test, dtype=np.float64)
+    if st["normalize_input"]:
+        Xs, _, _ = zero_one_normalization(X_test, st["lower"], st["upper"])
+    else:
+        Xs = X_test
+    gp = st["gp"]
+    alpha = gp._compute_alpha(st["y"])
+    Ks = gp.kernel.get_value(Xs, gp._x)
+    mu = Ks @ alpha + st["mean"]
+    U = gp.solver._factor[0]
+    V = spla.solve_triangular(U, Ks.T, trans="T", lower=False, check_finite=False)
+    var = gp.kernel.get_value(Xs[:1], Xs[:1])[0, 0] - np.einsum("ij,ij->j", V, V)
+    if st["normalize_output"]:
+        mu = mu * st["y_std"] + st["y_mean"]
+        var = var * st["y_std"] ** 2
+    return mu, np.clip(var, EPS, np.inf)
+
+
+def gp_predict_variance(st, x1, X2):
+    """GaussianProcess.predict_variance: gaussian_process.py:221-248."""
+    x_ = np.concatenate((x1, X2))
+    _, var = gp_predict(st, x_, full_cov=True)
+    return var[-1, :-1, np.newaxis]
+
+
+def gp_get_incumbent(st):
+    """gaussian_process.py:334-352 + base_model.py:94-106."""
+    b = np.argmin(st["y"])
+    inc, val = st["X"][b], st["y"][b]
+    if st["normalize_input"]:
+        inc = zero_one_unnormalization(inc, st["lower"], st["upper"])
+    if st["normalize_output"]:
+        val = val * st["y_std"] + st["y_mean"]
+    return inc, val
+
+
+def gp_grad_nll_correct(st, theta):
+    """Mathematically correct gradient of -log-likelihood w.r.t. theta
+    (log kernel parameters ..., log sigma^2).  The reference's grad_nll
+    (gaussian_process.py:168-191) is dead code with a wrong noise slice
+    (identity instead of sigma^2 I, :179-182); this is the corrected form,
+    validated against finite differences of gp_nll in tests."""
+    gp = st["gp"]
+    gp.kernel.set_parameter_vector(theta[:-1])
+    noise = np.exp(theta[-1])
+    gp.compute(st["X"], yerr=np.sqrt(noise))
+    alpha = gp._compute_alpha(st["y"])
+    Kinv = gp.solver.get_inverse()
+    A = np.outer(alpha, alpha) - Kinv
+    Kg = gp.kernel.gradient(gp._x)
+    g = 0.5 * np.einsum("ijk,ij", Kg, A)
+    g_noise = 0.5 * noise * np.trace(A)
+    return -np.append(g, g_noise)
+
+
+def gp_grad_nll_reference_compat(st, theta):
+    """gaussian_process.py:168-191 exactly (identity noise slice, no prior)."""
+    gp = st["gp"]
+    gp.kernel.set_parameter_vector(theta[:-1])
+    noise = np.exp(theta[-1])
+    gp.compute(st["X"], yerr=np.sqrt(noise))
+    alpha = gp._compute_alpha(st["y"])
+    Kinv = gp.solver.get_inverse()
+    Kg = gp.kernel.gradient(gp._x)
+    Kg = np.concatenate((Kg, np.eye(Kg.shape[0])[:, :, None]), axis=2)
+    A = np.outer(alpha, alpha) - Kinv
+    return -0.5 * np.einsum("ijk,ij", Kg, A)
+
+
+# --------------------------------------------------------------------------- #
+# robo/acquisition_functions/{ei,log_ei,pi,lcb}.py  (closed forms on moments)
+# --------------------------------------------------------------------------- #
+def _pdf(z):
+    return np.exp(-0.5 * z * z) / np.sqrt(2.0 * np.pi)
+
+
+def _logpdf(z):
+    return -0.5 * z * z - LOG_SQRT_2PI
+
+
+def acq_ei(m, v, eta, par=0.0):
+    """EI.compute: ei.py:65-88 (whole-batch zero on any s==0; ValueError if f<0)."""
+    s = np.sqrt(v)
+    if (s == 0).any():
+        return np.array([[0]])
+    z = (eta - m - par) / s
+    f = s * (z * ndtr(z) + _pdf(z))
+    if (f < 0).any():
+        raise ValueError
+    return f
+
+
+def acq_pi(m, v, eta, par=0.0):
+    """PI.compute: pi.py:58-63."""
+    s = np.sqrt(v)
+    return ndtr((eta - m - par) / s)
+
+
+def acq_lcb(m, v, par=1.0):
+    """LCB.compute: lcb.py:62-65."""
+    return -(m - par * np.sqrt(v))
+
+
+def acq_log_ei(m, v, eta, par=0.0):
+    """LogEI.compute: log_ei.py:67-122, branch order preserved
+    (np.Infinity of the reference restated as np.inf: removed in numpy 2)."""
+    f_min = eta - par
+    s = np.sqrt(v)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = (f_min - m) / s
+    out = np.zeros([m.size])
+    for i in range(m.size):
+        mu, sigma = m[i], s[i]
+        if abs(f_min - mu) == 0:                                       # :85-89
+            out[i] = np.log(sigma) + _logpdf(z[i]) if sigma > 0 else -np.inf
+        elif sigma == 0:                                               # :92-96
+            out[i] = np.log(f_min - mu) if mu < f_min else -np.inf
+        else:
+            b = np.log(sigma) + _logpdf(z[i])                          # :99
+            if f_min > mu:                                             # :101-107
+                a = np.log(f_min - mu) + log_ndtr(z[i])
+                out[i] = max(a, b) + np.log(1 + np.exp(-abs(b - a)))
+            else:                                                      # :114-120
+                a = np.log(mu - f_min) + log_ndtr(z[i])
+                out[i] = -np.inf if a >= b else b + np.log(1 - np.exp(a - b))
+    return out
+
+
+ACQ = {"ei": acq_ei, "log_ei": acq_log_ei, "pi": acq_pi, "lcb": acq_lcb}
+
+
+def acquisition(st, X_test, kind, par=None, eta=None):
+    """acq.compute(X) on a fitted GP state: predict -> closed form."""
+    m, v = gp_predict(st, X_test)
+    if kind == "lcb":
+        return acq_lcb(m, v, 1.0 if par is None else par)
+    if eta is None:
+        eta = gp_get_incumbent(st)[1]
+    return ACQ[kind](m, v, eta, 0.0 if par is None else par)
+
+
+def argmax_first(values):
+    """numpy.argmax first-occurrence semantics (random_sampling.py:50)."""
+    return int(np.argmax(values))
+
+
+# --------------------------------------------------------------------------- #
+# robo/models/gaussian_process_mcmc.py:230-247 / marginalization.py:115-121
+# --------------------------------------------------------------------------- #
+def mcmc_mixture_moments(mus, vars_):
+    """GaussianProcessMCMC.predict: m = mean_i mu_i ; v = var_i(mu_i) + mean_i var_i,
+    clipped (gaussian_process_mcmc.py:235-247).  mus/vars_: (n_models, M)."""
+    m = mus.mean(axis=0)
+    v = np.var(mus, axis=0) + np.mean(vars_, axis=0)
+    return m, np.clip(v, EPS, np.inf)
+
+
+def marginalised_acquisition(per_model_values):
+    """MarginalizationGPMCMC.compute: marginalization.py:115-121."""
+    return np.asarray(per_model_values).mean(axis=0)
+
+
+# --------------------------------------------------------------------------- #
+# synthetic workloads, shared by tests and bench.py
+# --------------------------------------------------------------------------- #
+def synthetic_problem(N, D, M, seed_train=1234, seed_cand=4321):
+    """X ~ U[0,1]^(N x D), y = sum_d sinc(10 x_d - 5) + 0.01 N(0,1)
+    (mirrors test/test_models/test_gaussian_process.py:14-15); candidates
+    X* ~ U[0,1]^(M x D); theta: amplitude 1, metric_d = D/4, noise 1e-3."""
+    rng = np.random.RandomState(seed_train)
+    X = rng.rand(N, D)
+    y = np.sinc(X * 10 - 5).sum(axis=1) + 0.01 * rng.randn(N)
+    Xs = np.random.RandomState(seed_cand).rand(M, D)
+    theta = np.concatenate(([0.0], np.full(D, np.log(D / 4.0))))
+    return X, y, Xs, theta, 1e-3
+
+
+def make_kernel(kind, D, theta):
+    """kind in {'matern52','rbf'}: amp * ARD kernel with theta = [log amp, log metric_d...]."""
+    cls = {"matern52": G.Matern52Kernel, "rbf": G.ExpSquaredKernel}[kind]
+    k = G.Product(G.ConstantKernel(theta[0], ndim=D), cls(np.exp(theta[1:]), ndim=D))
+    return k

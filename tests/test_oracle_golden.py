@@ -1,0 +1,69 @@
+"""The restatement oracle/robo_oracle.py must reproduce the committed golden
+vectors, which were produced by the reference's own classes (oracle/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import george_oracle as G
+from oracle import robo_oracle as O
+from tests.golden_cases import load_case, GP_CASES
+
+
+@pytest.mark.parametrize("name", GP_CASES)
+def test_gp_case(name, golden_dir):
+    d, kernel_fn = load_case(name)
+    st = O.gp_fit(kernel_fn(), d["X"], d["y"], noise=float(d["noise"]),
+                  normalize_input=bool(d["normalize_input"]),
+                  normalize_output=bool(d["normalize_output"]),
+                  lower=d["lower_"], upper=d["upper_"])
+    mu, var = O.gp_predict(st, d["Xs"])
+    np.testing.assert_allclose(mu, d["mu"], rtol=1e-13)
+    np.testing.assert_allclose(var, d["var"], rtol=1e-13)
+    m = int(d["full_cov_m"])
+    _, cov = O.gp_predict(st, d["Xs"][:m], full_cov=True)
+    np.testing.assert_allclose(cov, d["cov"], rtol=1e-13)
+    ll, logdet = O.gp_loglik_terms(st)
+    np.testing.assert_allclose([ll, logdet], [d["ll"], d["logdet"]], rtol=1e-13)
+    for kind in ("ei", "log_ei", "pi", "lcb"):
+        np.testing.assert_allclose(O.acquisition(st, d["Xs"], kind), d["acq_" + kind], rtol=1e-13)
+    inc_x, inc_y = O.gp_get_incumbent(st)
+    np.testing.assert_allclose(inc_x, d["inc_x"], rtol=1e-15)
+    assert inc_y == d["inc_y"]
+
+
+def test_acq_moments(golden_dir):
+    d = np.load(os.path.join(golden_dir, "acq_moments.npz"))
+    m, v, eta = d["m"], d["v"], float(d["eta"])
+    with np.errstate(all="ignore"):
+        for par in (0.0, 0.3):
+            np.testing.assert_allclose(O.acq_log_ei(m, v, eta, par), d["log_ei_par%g" % par], rtol=1e-14)
+            np.testing.assert_allclose(O.acq_pi(m, v, eta, par), d["pi_par%g" % par], rtol=1e-14, equal_nan=True)
+            np.testing.assert_allclose(O.acq_lcb(m, v, 1 + par), d["lcb_par%g" % (1 + par)], rtol=1e-14)
+            pos = v > 0
+            np.testing.assert_allclose(O.acq_ei(m[pos], v[pos], eta, par), d["ei_pos_par%g" % par], rtol=1e-14)
+        assert O.acq_ei(m, v, eta).shape == (1, 1)        # ei.py:72-74 whole-batch zero
+
+
+def test_grad_nll_correct_vs_finite_differences():
+    X, y, _, theta, noise = O.synthetic_problem(40, 3, 1)
+    st = O.gp_fit(O.make_kernel("matern52", 3, theta), X, y, noise=noise, normalize_input=False)
+    th = np.append(theta, np.log(noise)) + 0.1
+    g = O.gp_grad_nll_correct(st, th)
+    h = 1e-6
+    for p in range(len(th)):
+        tp, tm = th.copy(), th.copy()
+        tp[p] += h
+        tm[p] -= h
+        fd = (O.gp_nll(st, tp) - O.gp_nll(st, tm)) / (2 * h)
+        assert abs(g[p] - fd) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_var_only_matches_full_cov_path():
+    X, y, Xs, theta, noise = O.synthetic_problem(128, 8, 64)
+    st = O.gp_fit(O.make_kernel("matern52", 8, theta), X, y, noise=noise, normalize_input=False)
+    m1, v1 = O.gp_predict(st, Xs)
+    m2, v2 = O.gp_predict_var_only(st, Xs)
+    np.testing.assert_allclose(m1, m2, rtol=1e-12)
+    np.testing.assert_allclose(v1, v2, rtol=1e-9)
