@@ -1,0 +1,151 @@
+/* gpk.h — C ABI of libgpk.so: B200-native (sm_100a) GP posterior + acquisition kernels.
+ *
+ * This is the drop-in boundary for RoBO's hot path.  Every entry
+ * point replaces a call the reference makes into george / scipy-LAPACK / scipy.stats from
+ *   robo/models/gaussian_process.py          (train / nll / predict)
+ *   robo/acquisition_functions/{ei,log_ei,pi,lcb}.py   (compute)
+ * The reference is pure Python; its "FFI" for this path is george's Cython bridge, so the
+ * binding a RoBO maintainer would add is a ctypes stub (see INTEGRATION.md and
+ * robo_b200/_lib.py, which is exactly that stub).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / numpy types.  All floating point is IEEE fp64.
+ *   - host pointers are caller-owned, C-contiguous, read/written only during the call.
+ *   - `*_dev` entry points take device pointers (e.g. torch.Tensor.data_ptr()) and are
+ *     asynchronous on the handle's stream.
+ *   - every function returns a gpk_status; nothing throws or aborts.  The Python side maps
+ *     GPK_NOT_PD -> numpy.linalg.LinAlgError (caught at gaussian_process.py:120,156 and by
+ *     the bare except at gaussian_process_mcmc.py:196), GPK_BAD_ARG -> ValueError,
+ *     GPK_CUDA_ERROR -> RuntimeError.
+ *   - one CUDA stream per handle; calls on one handle are not re-entrant.
+ */
+#ifndef GPK_H_
+#define GPK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpk_handle gpk_handle;
+
+typedef enum {
+    GPK_OK = 0,
+    GPK_NOT_PD = 1,        /* Cholesky pivot <= 0 or NaN: numpy.linalg.LinAlgError in the reference */
+    GPK_BAD_ARG = 2,
+    GPK_CUDA_ERROR = 3,
+    GPK_NOT_FITTED = 4
+} gpk_status;
+
+/* stationary radial families, george names (oracle/george_oracle.py) */
+typedef enum {
+    GPK_MATERN52 = 0,      /* george.kernels.Matern52Kernel   */
+    GPK_EXPSQUARED = 1,    /* george.kernels.ExpSquaredKernel */
+    GPK_MATERN32 = 2       /* george.kernels.Matern32Kernel   */
+} gpk_family;
+
+typedef enum {
+    GPK_ACQ_NONE = 0,      /* posterior moments only                              */
+    GPK_ACQ_EI = 1,        /* robo/acquisition_functions/ei.py:65-78              */
+    GPK_ACQ_LOG_EI = 2,    /* robo/acquisition_functions/log_ei.py:67-122         */
+    GPK_ACQ_PI = 3,        /* robo/acquisition_functions/pi.py:58-63              */
+    GPK_ACQ_LCB = 4        /* robo/acquisition_functions/lcb.py:62-65             */
+} gpk_acq_kind;
+
+#define GPK_MAX_TERMS 64   /* metric entries (input dims x product factors) per kernel */
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+int gpk_create(gpk_handle** h, int device);
+int gpk_destroy(gpk_handle* h);
+const char* gpk_last_error(gpk_handle* h);
+const char* gpk_version(void);
+/* key in {"loader" (0 = cp.async staging, 1 = TMA staging [default]), "chunk" (candidates per
+ * scoring pass, multiple of 128), "graph" (1 = replay the fit as a CUDA graph)} */
+int gpk_set_option(gpk_handle* h, const char* key, long value);
+/* run on an existing CUDA stream (cudaStream_t passed as void*); NULL = the handle's own */
+int gpk_set_stream(gpk_handle* h, void* cuda_stream);
+int gpk_synchronize(gpk_handle* h);
+
+/* ---- model state ------------------------------------------------------------------- */
+/* Training inputs as the reference hands them to george: X already scaled by
+ * zero_one_normalization (gaussian_process.py:89-93), y already standardised if
+ * normalize_output (:95-101).  X is (n, d) row-major. */
+int gpk_set_data(gpk_handle* h, const double* X, const double* y, int n, int d);
+
+/* Test-input scaling fused into the scoring kernels: x <- (x - lower) / (upper - lower)
+ * (robo/util/normalization.py:11, applied at gaussian_process.py:276).  NULL disables. */
+int gpk_set_input_bounds(gpk_handle* h, const double* lower, const double* upper, int d);
+
+/* Output un-normalisation fused into the scoring kernels (gaussian_process.py:282-284):
+ * mu <- mu * y_std + y_mean ; var <- var * y_std^2.  enabled = 0 disables. */
+int gpk_set_output_transform(gpk_handle* h, int enabled, double y_mean, double y_std);
+
+/* k(x, x') = exp(log_amp) * prod_g f( sum_{t in g} (x[axis_t] - x'[axis_t])^2 / exp(log_metric_t) )
+ * Terms are listed group by group (group[] non-decreasing from 0).  One group over all
+ * columns = george's axis-aligned (ARD) kernel; one group per column = the product of 1-D
+ * kernels built at robo/fmin/fabolas.py:104-110.  Replaces kernel.set_parameter_vector
+ * (gaussian_process.py:110,151). */
+int gpk_set_kernel(gpk_handle* h, int family, double log_amp, int n_terms,
+                   const int* axis, const int* group, const double* log_metric);
+
+/* ---- fit: K build + Cholesky + forward solve + log-det ------------------------------- */
+/* Replaces george GP.compute + GP.log_likelihood (gaussian_process.py:119,155,159):
+ *   K = k(X, X) + diag_add * I ; K = L L^T ; z = L^-1 (y - mean)
+ *   logdet = 2 sum log L_ii ; loglik = -1/2 z^T z - 1/2 logdet - n/2 log(2 pi)
+ * diag_add is the value george adds to the diagonal, yerr^2 + 1.25e-12, computed by the host
+ * exactly as george does.  Returns GPK_NOT_PD where scipy.linalg.cholesky would raise. */
+int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double* loglik);
+
+/* ---- posterior + acquisition over a candidate batch -------------------------------- */
+/* Replaces george GP.predict + np.diag + clip (gaussian_process.py:276-294):
+ * mu[m], var[m] (var clipped to >= DBL_EPSILON).  Xs is (m, d) row-major, raw (un-scaled). */
+int gpk_predict(gpk_handle* h, const double* Xs, long m, double* mu, double* var);
+
+/* full_cov=True path (gaussian_process.py:280-294): cov is (m, m) row-major, every entry
+ * clipped to >= DBL_EPSILON like the reference does. */
+int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double* cov);
+
+/* Fused predict -> acquisition -> argmax.  out (m values) may be NULL when only the argmax
+ * is wanted.  best_idx follows numpy.argmax (first maximum; NaN counts as maximum) as used at
+ * robo/maximizers/random_sampling.py:50.  n_negative counts EI values < 0 (the reference
+ * raises ValueError on any, ei.py:86-88).  mu/var may be NULL. */
+int gpk_acq(gpk_handle* h, const double* Xs, long m, int acq_kind, double eta, double par,
+            double* out, double* mu, double* var,
+            double* best_val, long* best_idx, long* n_negative);
+
+/* Device-pointer variant, asynchronous on the handle's stream.  d_Xs: (m, d) fp64 row-major
+ * on the device.  d_out/d_mu/d_var (m doubles each) may be NULL.  d_best: 16 bytes
+ * {double value; long long index}.  */
+int gpk_acq_dev(gpk_handle* h, const void* d_Xs, long m, int acq_kind, double eta, double par,
+                void* d_out, void* d_mu, void* d_var, void* d_best);
+
+/* Acquisition closed forms on caller-supplied moments (host arrays), evaluated by the same
+ * device function as the fused path.  Serves models that are not GPU GPs (e.g. the
+ * reference's test/dummy_model.py).  No handle state is used except the device/stream. */
+int gpk_acq_moments(gpk_handle* h, const double* mu, const double* var, long m, int acq_kind,
+                    double eta, double par, double* out, long* n_negative);
+
+/* kernel.get_value(X1, X2) (test/test_models/test_gaussian_process.py:44-46) with the
+ * handle's current kernel; no input scaling.  out is (n1, n2) row-major. */
+int gpk_kernel_matrix(gpk_handle* h, const double* X1, long n1, const double* X2, long n2,
+                      int d, double* out);
+
+/* ---- marginal-likelihood gradient (gaussian_process.py:168-191, corrected noise term) -- */
+/* grad[n_terms + 2] = d(-loglik)/d[log_amp, log_metric_t..., log sigma^2]; requires a
+ * preceding successful gpk_fit with the same parameters.  noise_var = sigma^2. */
+int gpk_nll_grad(gpk_handle* h, double noise_var, double* grad);
+
+/* ---- introspection (tests / debugging) ----------------------------------------------- */
+int gpk_get_factor(gpk_handle* h, double* L /* n x n row-major, lower */);
+int gpk_get_linv(gpk_handle* h, double* Linv /* n x n row-major, lower */);
+int gpk_get_z(gpk_handle* h, double* z /* n */);
+/* last fit/score timings measured with CUDA events on the handle's stream, milliseconds:
+ * out[0] fit total, [1] K build, [2] Cholesky, [3] L^-1, [4] last score call total,
+ * [5] K* build, [6] variance GEMM, [7] epilogue (5-7: last candidate chunk of that call);
+ * out[8] = variance-GEMM launches so far,
+ * out[9] = total kernel launches so far. */
+int gpk_get_timings(gpk_handle* h, double* out10);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPK_H_ */

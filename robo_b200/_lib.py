@@ -1,0 +1,260 @@
+"""ctypes binding of include/gpk.h — the stub a RoBO maintainer would add.
+
+There is deliberately NO CPU fallback: if libgpk.so cannot be loaded, or no CUDA device is
+present, every compute call raises.  Status codes map to the exceptions the reference's
+callers already handle (SURVEY.md section 8b "Error conventions"):
+    GPK_NOT_PD     -> numpy.linalg.LinAlgError   (gaussian_process.py:120,156)
+    GPK_BAD_ARG    -> ValueError
+    GPK_CUDA_ERROR -> RuntimeError
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+GPK_OK, GPK_NOT_PD, GPK_BAD_ARG, GPK_CUDA_ERROR, GPK_NOT_FITTED = range(5)
+MATERN52, EXPSQUARED, MATERN32 = 0, 1, 2
+ACQ_NONE, ACQ_EI, ACQ_LOG_EI, ACQ_PI, ACQ_LCB = range(5)
+ACQ_KIND = {"ei": ACQ_EI, "log_ei": ACQ_LOG_EI, "pi": ACQ_PI, "lcb": ACQ_LCB, "none": ACQ_NONE}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_long)
+_vp = C.c_void_p
+
+_SIGNATURES = {
+    "gpk_create": [C.POINTER(_vp), C.c_int],
+    "gpk_destroy": [_vp],
+    "gpk_set_option": [_vp, C.c_char_p, C.c_long],
+    "gpk_set_stream": [_vp, _vp],
+    "gpk_synchronize": [_vp],
+    "gpk_set_data": [_vp, _dp, _dp, C.c_int, C.c_int],
+    "gpk_set_input_bounds": [_vp, _dp, _dp, C.c_int],
+    "gpk_set_output_transform": [_vp, C.c_int, C.c_double, C.c_double],
+    "gpk_set_kernel": [_vp, C.c_int, C.c_double, C.c_int, _ip, _ip, _dp],
+    "gpk_fit": [_vp, C.c_double, C.c_double, _dp, _dp],
+    "gpk_predict": [_vp, _dp, C.c_long, _dp, _dp],
+    "gpk_predict_cov": [_vp, _dp, C.c_long, _dp, _dp],
+    "gpk_acq": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _lp, _lp],
+    "gpk_acq_dev": [_vp, _vp, C.c_long, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp],
+    "gpk_acq_moments": [_vp, _dp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _lp],
+    "gpk_kernel_matrix": [_vp, _dp, C.c_long, _dp, C.c_long, C.c_int, _dp],
+    "gpk_nll_grad": [_vp, C.c_double, _dp],
+    "gpk_get_factor": [_vp, _dp],
+    "gpk_get_linv": [_vp, _dp],
+    "gpk_get_z": [_vp, _dp],
+    "gpk_get_timings": [_vp, _dp],
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """dlopen libgpk.so (building it first if the sources are newer). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if build_if_missing and os.environ.get("GPK_NO_BUILD") != "1":
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    if not os.path.exists(path):
+        raise RuntimeError("libgpk.so is missing (%s) and could not be built; there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.gpk_last_error.argtypes = [_vp]
+    lib.gpk_last_error.restype = C.c_char_p
+    lib.gpk_version.argtypes = []
+    lib.gpk_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGNATURES) + ["gpk_last_error", "gpk_version"])
+
+
+def _as_dp(a):
+    return a.ctypes.data_as(_dp)
+
+
+def f64(a):
+    """C-contiguous float64 view/copy (the ABI takes plain double*)."""
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Handle(object):
+    """Owns one gpk_handle (one fitted GP on one GPU)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self.device = int(device)
+        h = _vp()
+        rc = self.lib.gpk_create(C.byref(h), self.device)
+        if rc != GPK_OK:
+            raise RuntimeError("gpk_create failed on device %d (status %d): no usable CUDA device; "
+                               "robo_b200 has no CPU fallback" % (self.device, rc))
+        self._h = h
+        # test/diagnostic overrides: GPK_LOADER=0|1 (cp.async | TMA staging), GPK_CHUNK=<multiple of 128>
+        if os.environ.get("GPK_LOADER"):
+            self.set_option("loader", int(os.environ["GPK_LOADER"]))
+        if os.environ.get("GPK_CHUNK"):
+            self.set_option("chunk", int(os.environ["GPK_CHUNK"]))
+
+    # -- plumbing -----------------------------------------------------------------
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self.lib.gpk_destroy(h)
+            except Exception:
+                pass
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc == GPK_OK:
+            return
+        msg = self.lib.gpk_last_error(self._h)
+        msg = msg.decode("utf-8", "replace") if msg else ""
+        if rc == GPK_NOT_PD:
+            raise np.linalg.LinAlgError(msg or "Matrix is not positive definite")
+        if rc == GPK_BAD_ARG:
+            raise ValueError(msg)
+        if rc == GPK_NOT_FITTED:
+            raise RuntimeError(msg or "model not fitted")
+        raise RuntimeError("gpk: " + msg)
+
+    def set_option(self, key, value):
+        self._check(self.lib.gpk_set_option(self._h, key.encode(), int(value)))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.gpk_set_stream(self._h, _vp(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self.lib.gpk_synchronize(self._h))
+
+    # -- model state ----------------------------------------------------------------
+    def set_data(self, X, y):
+        X, y = f64(X), f64(y)
+        n, d = X.shape
+        self._check(self.lib.gpk_set_data(self._h, _as_dp(X), _as_dp(y), n, d))
+
+    def set_input_bounds(self, lower, upper):
+        if lower is None or upper is None:
+            self._check(self.lib.gpk_set_input_bounds(self._h, None, None, 0))
+            return
+        lo, up = f64(lower).ravel(), f64(upper).ravel()
+        self._check(self.lib.gpk_set_input_bounds(self._h, _as_dp(lo), _as_dp(up), lo.size))
+
+    def set_output_transform(self, enabled, y_mean=0.0, y_std=1.0):
+        self._check(self.lib.gpk_set_output_transform(self._h, int(bool(enabled)), float(y_mean), float(y_std)))
+
+    def set_kernel(self, family, log_amp, axis, group, log_metric):
+        axis = np.ascontiguousarray(axis, dtype=np.int32)
+        group = np.ascontiguousarray(group, dtype=np.int32)
+        lm = f64(log_metric)
+        self._check(self.lib.gpk_set_kernel(self._h, int(family), float(log_amp), axis.size,
+                                            axis.ctypes.data_as(_ip), group.ctypes.data_as(_ip), _as_dp(lm)))
+
+    def fit(self, diag_add, mean):
+        logdet, ll = C.c_double(), C.c_double()
+        self._check(self.lib.gpk_fit(self._h, float(diag_add), float(mean), C.byref(logdet), C.byref(ll)))
+        return logdet.value, ll.value
+
+    # -- scoring ----------------------------------------------------------------------
+    def predict(self, Xs):
+        Xs = f64(Xs)
+        m = Xs.shape[0]
+        mu, var = np.empty(m), np.empty(m)
+        self._check(self.lib.gpk_predict(self._h, _as_dp(Xs), m, _as_dp(mu), _as_dp(var)))
+        return mu, var
+
+    def predict_cov(self, Xs):
+        Xs = f64(Xs)
+        m = Xs.shape[0]
+        mu, cov = np.empty(m), np.empty((m, m))
+        self._check(self.lib.gpk_predict_cov(self._h, _as_dp(Xs), m, _as_dp(mu), _as_dp(cov)))
+        return mu, cov
+
+    def acq(self, Xs, kind, eta=0.0, par=0.0, want_values=True, want_moments=False):
+        """-> dict(values, mu, var, best_val, best_idx, n_negative)"""
+        Xs = f64(Xs)
+        m = Xs.shape[0]
+        out = np.empty(m) if want_values else None
+        mu = np.empty(m) if want_moments else None
+        var = np.empty(m) if want_moments else None
+        bv, bi, nn = C.c_double(), C.c_long(-1), C.c_long(0)
+        self._check(self.lib.gpk_acq(self._h, _as_dp(Xs), m, int(kind), float(eta), float(par),
+                                     _as_dp(out) if want_values else None,
+                                     _as_dp(mu) if want_moments else None,
+                                     _as_dp(var) if want_moments else None,
+                                     C.byref(bv), C.byref(bi), C.byref(nn)))
+        return dict(values=out, mu=mu, var=var, best_val=bv.value, best_idx=bi.value, n_negative=nn.value)
+
+    def acq_dev(self, d_Xs_ptr, m, kind, eta, par, d_out_ptr=0, d_mu_ptr=0, d_var_ptr=0, d_best_ptr=0):
+        """Device-pointer variant (asynchronous on the handle's stream)."""
+        self._check(self.lib.gpk_acq_dev(self._h, _vp(d_Xs_ptr), int(m), int(kind), float(eta), float(par),
+                                         _vp(d_out_ptr or 0), _vp(d_mu_ptr or 0), _vp(d_var_ptr or 0),
+                                         _vp(d_best_ptr or 0)))
+
+    def acq_moments(self, mu, var, kind, eta=0.0, par=0.0):
+        mu, var = f64(mu).ravel(), f64(var).ravel()
+        out = np.empty(mu.size)
+        nn = C.c_long(0)
+        self._check(self.lib.gpk_acq_moments(self._h, _as_dp(mu), _as_dp(var), mu.size, int(kind), float(eta),
+                                             float(par), _as_dp(out), C.byref(nn)))
+        return out, nn.value
+
+    def kernel_matrix(self, X1, X2):
+        X1, X2 = f64(X1), f64(X2)
+        out = np.empty((X1.shape[0], X2.shape[0]))
+        self._check(self.lib.gpk_kernel_matrix(self._h, _as_dp(X1), X1.shape[0], _as_dp(X2), X2.shape[0],
+                                               X1.shape[1], _as_dp(out)))
+        return out
+
+    # -- introspection ----------------------------------------------------------------
+    def get_factor(self, n):
+        L = np.empty((n, n))
+        self._check(self.lib.gpk_get_factor(self._h, _as_dp(L)))
+        return L
+
+    def get_linv(self, n):
+        L = np.empty((n, n))
+        self._check(self.lib.gpk_get_linv(self._h, _as_dp(L)))
+        return L
+
+    def get_z(self, n):
+        z = np.empty(n)
+        self._check(self.lib.gpk_get_z(self._h, _as_dp(z)))
+        return z
+
+    def timings(self):
+        t = np.zeros(10)
+        self._check(self.lib.gpk_get_timings(self._h, _as_dp(t)))
+        keys = ["fit_ms", "kbuild_ms", "potrf_ms", "linv_ms", "score_ms", "kstar_ms", "vargemm_ms", "finish_ms",
+                "launches_vargemm", "launches_total"]
+        return dict(zip(keys, t.tolist()))
+
+
+_moments_handle = {}
+
+
+def moments_handle(device=0):
+    """Shared handle for gpk_acq_moments (acquisition on non-GPU models)."""
+    if device not in _moments_handle:
+        _moments_handle[device] = Handle(device)
+    return _moments_handle[device]

@@ -1,0 +1,948 @@
+// gpk_api.cu — C ABI (include/gpk.h) and host orchestration of the sm_100a kernels.
+//
+// Data layout in HBM (all fp64, row-major, NP = n rounded up to 128, nb = NP / 128):
+//   Xt    [d][NP]        training inputs, transposed (coalesced reads in the covariance builder)
+//   Kbuf  [NP+128][NP]   K, overwritten in place by its lower Cholesky factor L; block row nb is
+//                        the augmented right-hand side: after the factorisation row NP holds
+//                        z = L^-1 (y - mean), so the log-likelihood needs no separate solve
+//   P     [NP][NP]       L^-1   (lower; diagonal blocks come out of the Cholesky diag kernel)
+//   Q     [NP][NP]       L^-T   (upper) — only needed while building P, and for alpha
+//   W     [NP][NP]       scratch of the recursive triangular inverse
+//   Kstar [chunk][NP]    K(X*, X) of the current candidate chunk
+//   part_mu/part_ssq [nb][chunk]  per-row-block partial sums of the variance contraction
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gpk_gemm.cuh"
+#include "gpk_kernels.cuh"
+
+namespace {
+
+struct Range { int off = 0, cnt = 0; };
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct gpk_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    char err[1024] = {0};
+    int loader = LOADER_TMA;
+    long chunk = 16384;
+
+    // model
+    int n = 0, d = 0, NP = 0, nb = 0;
+    bool has_data = false, has_spec = false, fitted = false, linv_ready = false, alpha_ready = false;
+    KSpec spec;
+    double log_amp = 0.0;
+    std::vector<double> log_metric;
+    bool has_bounds = false;
+    int norm_out = 0;
+    double y_mean = 0.0, y_std = 1.0, mean = 0.0, diag_add = 0.0;
+
+    // device buffers
+    DevBuf Xrow, Xt, y, Kbuf, P, Q, W, lower, upper, logdet_part, scal, status, jobs;
+    DevBuf cand, Kstar, part_mu, part_ssq, out_mu, out_var, out_acq, block_best, best, nneg;
+    DevBuf Vt, cov, XsT, tmpjobs, alpha, tmp1, tmp2, tmp3;
+    int layout_NP = -1;           // NP the P/Q/W buffers were zeroed for
+    int jobs_nb = -1;
+
+    // job tables
+    std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r;
+
+    // tensor maps
+    CUtensorMap mapK, mapP, mapQ, mapW, mapKs, mapVt;
+    bool maps_ok = false;
+    long mapKs_rows = 0, mapVt_rows = 0;
+
+    // timing
+    cudaEvent_t ev[16];
+    bool ev_ok = false;
+    bool fit_timed = false, score_timed = false;
+    double launches_total = 0, launches_var = 0;
+    long last_chunk_rows = 0;
+};
+
+namespace {
+
+void set_err(gpk_handle* h, const char* fmt, ...) {
+    if (!h) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+}
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            set_err(h, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return GPK_CUDA_ERROR;                                                               \
+        }                                                                                        \
+    } while (0)
+
+#define CKL()                                                                                    \
+    do {                                                                                         \
+        cudaError_t e_ = cudaGetLastError();                                                     \
+        if (e_ != cudaSuccess) {                                                                 \
+            set_err(h, "kernel launch -> %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return GPK_CUDA_ERROR;                                                               \
+        }                                                                                        \
+        h->launches_total += 1;                                                                  \
+    } while (0)
+
+#define BAD(...)                           \
+    do {                                   \
+        set_err(h, __VA_ARGS__);           \
+        return GPK_BAD_ARG;                \
+    } while (0)
+
+int ensure(gpk_handle* h, DevBuf& b, size_t bytes, bool* grew = nullptr) {
+    if (grew) *grew = false;
+    if (bytes <= b.cap && b.p) return GPK_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = std::max<size_t>(bytes, 256);
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    if (grew) *grew = true;
+    return GPK_OK;
+}
+
+template <typename T> T* ptr(const DevBuf& b) { return reinterpret_cast<T*>(b.p); }
+
+inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
+
+// ---- tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp64 row-major matrix [rows][ld]; box = 128 rows x 16 doubles (128 B), 128B swizzle.
+int make_map(gpk_handle* h, CUtensorMap* map, void* base, long rows, long cols, long ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_err(h, "cuTensorMapEncodeTiled entry point not available");
+        return GPK_CUDA_ERROR;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_err(h, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%ld cols=%ld ld=%ld)", (int)r, rows, cols, ld);
+        return GPK_CUDA_ERROR;
+    }
+    return GPK_OK;
+}
+
+// ---- GEMM launch ---------------------------------------------------------------------------
+template <int EPI>
+int launch_gemm(gpk_handle* h, const CUtensorMap& mA, const CUtensorMap& mB, const GemmArgs& a, int njobs) {
+    if (njobs <= 0) return GPK_OK;
+    if (h->loader == LOADER_TMA)
+        gpk_gemm_nt_kernel<EPI, LOADER_TMA><<<njobs, GEMM_THREADS, GEMM_SMEM_TMA, h->stream>>>(mA, mB, a);
+    else
+        gpk_gemm_nt_kernel<EPI, LOADER_CPASYNC><<<njobs, GEMM_THREADS, GEMM_SMEM_PAD, h->stream>>>(mA, mB, a);
+    CKL();
+    return GPK_OK;
+}
+
+int set_kernel_attrs(gpk_handle* h) {
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_CPASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
+    CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+    return GPK_OK;
+}
+
+// ---- job tables ----------------------------------------------------------------------------
+struct Node { int lo, mid, hi, height; };
+
+int build_nodes(int lo, int hi, std::vector<Node>& nodes) {
+    if (hi - lo <= 1) return 0;
+    int mid = lo + (hi - lo + 1) / 2;
+    int hl = build_nodes(lo, mid, nodes);
+    int hr = build_nodes(mid, hi, nodes);
+    int ht = 1 + std::max(hl, hr);
+    nodes.push_back({lo, mid, hi, ht});
+    return ht;
+}
+
+int build_job_tables(gpk_handle* h) {
+    const int nb = h->nb;
+    if (h->jobs_nb == nb) return GPK_OK;
+    std::vector<GemmJob> jobs;
+    h->trsm_r.assign(nb, Range());
+    h->syrk_r.assign(nb, Range());
+    for (int k = 0; k < nb; ++k) {
+        h->trsm_r[k].off = (int)jobs.size();
+        for (int i = k + 1; i <= nb; ++i)          // i == nb: augmented rhs block row
+            jobs.push_back({i * BM, k * BM, k * BM, (k + 1) * BM, i * BM, k * BM, 0, 0});
+        h->trsm_r[k].cnt = (int)jobs.size() - h->trsm_r[k].off;
+        h->syrk_r[k].off = (int)jobs.size();
+        for (int j = k + 1; j < nb; ++j)
+            for (int i = j; i <= nb; ++i)
+                jobs.push_back({i * BM, j * BM, k * BM, (k + 1) * BM, i * BM, j * BM, 0, 0});
+        h->syrk_r[k].cnt = (int)jobs.size() - h->syrk_r[k].off;
+    }
+    std::vector<Node> nodes;
+    int hmax = build_nodes(0, nb, nodes);
+    h->tri1_r.assign(hmax + 1, Range());
+    h->tri2_r.assign(hmax + 1, Range());
+    auto by_len = [](const GemmJob& a, const GemmJob& b) { return (a.k1 - a.k0) > (b.k1 - b.k0); };
+    for (int ht = 1; ht <= hmax; ++ht) {
+        size_t s1 = jobs.size();
+        for (const Node& nd : nodes) {
+            if (nd.height != ht) continue;
+            for (int c = nd.lo; c < nd.mid; ++c)
+                for (int i = nd.mid; i < nd.hi; ++i)   // T'[c][i] = sum_{k=c..mid} Q[c][k] L[i][k]
+                    jobs.push_back({c * BM, i * BM, c * BM, nd.mid * BM, c * BM, i * BM, 0, 0});
+        }
+        std::stable_sort(jobs.begin() + s1, jobs.end(), by_len);
+        h->tri1_r[ht].off = (int)s1;
+        h->tri1_r[ht].cnt = (int)(jobs.size() - s1);
+        size_t s2 = jobs.size();
+        for (const Node& nd : nodes) {
+            if (nd.height != ht) continue;
+            for (int i = nd.mid; i < nd.hi; ++i)
+                for (int c = nd.lo; c < nd.mid; ++c)   // R[i][c] = -sum_{k=mid..i} P[i][k] T'[c][k]
+                    jobs.push_back({i * BM, c * BM, nd.mid * BM, (i + 1) * BM, i * BM, c * BM, 0, 0});
+        }
+        std::stable_sort(jobs.begin() + s2, jobs.end(), by_len);
+        h->tri2_r[ht].off = (int)s2;
+        h->tri2_r[ht].cnt = (int)(jobs.size() - s2);
+    }
+    if (jobs.empty()) jobs.push_back({0, 0, 0, 0, 0, 0, 0, 0});
+    int rc = ensure(h, h->jobs, jobs.size() * sizeof(GemmJob));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->jobs.p, jobs.data(), jobs.size() * sizeof(GemmJob), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->jobs_nb = nb;
+    return GPK_OK;
+}
+
+int rebuild_maps(gpk_handle* h) {
+    if (h->loader != LOADER_TMA) { h->maps_ok = true; return GPK_OK; }
+    const long NP = h->NP;
+    int rc;
+    if ((rc = make_map(h, &h->mapK, h->Kbuf.p, NP + BM, NP, NP))) return rc;
+    if ((rc = make_map(h, &h->mapP, h->P.p, NP, NP, NP))) return rc;
+    if ((rc = make_map(h, &h->mapQ, h->Q.p, NP, NP, NP))) return rc;
+    if ((rc = make_map(h, &h->mapW, h->W.p, NP, NP, NP))) return rc;
+    h->mapKs_rows = 0;
+    h->mapVt_rows = 0;
+    h->maps_ok = true;
+    return GPK_OK;
+}
+
+// scratch for scoring `rows` (multiple of 128) candidates at once
+int ensure_score_scratch(gpk_handle* h, long rows) {
+    const long NP = h->NP;
+    bool grew = false;
+    int rc;
+    if ((rc = ensure(h, h->Kstar, (size_t)rows * NP * 8, &grew))) return rc;
+    if (grew || h->mapKs_rows != rows) {
+        if (h->loader == LOADER_TMA && (rc = make_map(h, &h->mapKs, h->Kstar.p, rows, NP, NP))) return rc;
+        h->mapKs_rows = rows;
+    }
+    if ((rc = ensure(h, h->part_mu, (size_t)h->nb * rows * 8))) return rc;
+    if ((rc = ensure(h, h->part_ssq, (size_t)h->nb * rows * 8))) return rc;
+    if ((rc = ensure(h, h->block_best, (size_t)(rows / 256 + 1) * sizeof(BestPair)))) return rc;
+    if ((rc = ensure(h, h->best, sizeof(BestPair)))) return rc;
+    if ((rc = ensure(h, h->nneg, 8))) return rc;
+    return GPK_OK;
+}
+
+__global__ void gpk_fit_reduce_kernel(const double* __restrict__ z, int n, const double* __restrict__ logdet_part,
+                                      int nb, double* __restrict__ out2) {
+    // single block, fixed summation order: out2[0] = z^T z, out2[1] = 2 * sum log diag
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s = fma(z[i], z[i], s);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out2[0] = sh[0];
+        double l = 0.0;
+        for (int k = 0; k < nb; ++k) l += logdet_part[k];
+        out2[1] = 2.0 * l;
+    }
+}
+
+// mu_c = sum_k M[c][k] * z[k] over k in [k_lo(c), NP): one warp per row (tri: k >= c)
+__global__ void gpk_rowdot_kernel(const double* __restrict__ M, long ld, long rows, int NP, int tri,
+                                  const double* __restrict__ z, double* __restrict__ out) {
+    long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    double s = 0.0;
+    int kstart = tri ? (int)(row & ~31L) : 0;
+    for (int k = kstart + lane; k < NP; k += 32)
+        if (!tri || k >= row) s = fma(M[row * ld + k], z[k], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[row] = s;
+}
+
+__global__ void gpk_mu_finish_kernel(double* __restrict__ mu, long m, double mean, int norm_out, double y_mean,
+                                     double y_std) {
+    long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    double v = mu[c] + mean;
+    if (norm_out) v = v * y_std + y_mean;
+    mu[c] = v;
+}
+
+int require(gpk_handle* h, bool data, bool spec, bool fitted) {
+    if (!h) return GPK_BAD_ARG;
+    if (data && !h->has_data) { set_err(h, "gpk_set_data has not been called"); return GPK_BAD_ARG; }
+    if (spec && !h->has_spec) { set_err(h, "gpk_set_kernel has not been called"); return GPK_BAD_ARG; }
+    if (fitted && !h->fitted) { set_err(h, "model is not fitted (gpk_fit)"); return GPK_NOT_FITTED; }
+    return GPK_OK;
+}
+
+// L^-1 by recursive block inversion (P lower, Q = P^T upper), after a successful fit.
+int build_linv(gpk_handle* h) {
+    if (h->linv_ready) return GPK_OK;
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    const long NP = h->NP;
+    const int hmax = (int)h->tri1_r.size() - 1;
+    for (int ht = 1; ht <= hmax; ++ht) {
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = ptr<double>(h->Q); a.lda = NP;
+        a.B = ptr<double>(h->Kbuf); a.ldb = NP;
+        a.C = ptr<double>(h->W); a.ldc = NP;
+        a.alpha = 1.0; a.beta = 0;
+        a.jobs = ptr<GemmJob>(h->jobs) + h->tri1_r[ht].off;
+        a.job_mode = JOBS_TABLE;
+        int rc = launch_gemm<EPI_STORE>(h, h->mapQ, h->mapK, a, h->tri1_r[ht].cnt);
+        if (rc) return rc;
+        GemmArgs b;
+        memset(&b, 0, sizeof(b));
+        b.A = ptr<double>(h->P); b.lda = NP;
+        b.B = ptr<double>(h->W); b.ldb = NP;
+        b.C = ptr<double>(h->P); b.ldc = NP;
+        b.Ct = ptr<double>(h->Q); b.ldct = NP;
+        b.alpha = -1.0; b.beta = 0;
+        b.jobs = ptr<GemmJob>(h->jobs) + h->tri2_r[ht].off;
+        b.job_mode = JOBS_TABLE;
+        rc = launch_gemm<EPI_STORE>(h, h->mapP, h->mapW, b, h->tri2_r[ht].cnt);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    h->linv_ready = true;
+    return GPK_OK;
+}
+
+// Score m candidates resident on the device.  All output pointers are device pointers or NULL.
+int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, double par, double* d_out,
+              double* d_mu, double* d_var, BestPair* d_best, unsigned long long* d_nneg) {
+    int rc = build_linv(h);
+    if (rc) return rc;
+    const long NP = h->NP;
+    const long cap = std::min<long>(h->chunk, round_up(std::max<long>(m, 1), BM));
+    if ((rc = ensure_score_scratch(h, cap))) return rc;
+    if (d_best == nullptr) d_best = ptr<BestPair>(h->best);
+    if (d_nneg == nullptr) d_nneg = ptr<unsigned long long>(h->nneg);
+    CK(cudaMemsetAsync(d_best, 0xFF, sizeof(BestPair), h->stream));
+    CK(cudaMemsetAsync(d_nneg, 0, 8, h->stream));
+    CK(cudaEventRecord(h->ev[6], h->stream));
+    for (long base = 0; base < m; base += cap) {
+        const long mc = std::min(cap, m - base);
+        const long mcp = round_up(mc, BM);
+        const bool last = base + cap >= m;
+        dim3 cg((unsigned)(NP / 128), (unsigned)(mcp / 32));
+        if (last) CK(cudaEventRecord(h->ev[8], h->stream));
+        gpk_cov_kernel<<<cg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, h->n, dX + base * h->d, h->d, mc,
+                                                  h->has_bounds ? ptr<double>(h->lower) : nullptr,
+                                                  h->has_bounds ? ptr<double>(h->upper) : nullptr,
+                                                  ptr<double>(h->Kstar), NP, 0);
+        CKL();
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = ptr<double>(h->P); a.lda = NP;
+        a.B = ptr<double>(h->Kstar); a.ldb = NP;
+        a.alpha = 1.0;
+        a.job_mode = JOBS_VARIANCE;
+        a.nb = h->nb; a.mcb = (int)(mcp / BN);
+        a.z = ptr<double>(h->Kbuf) + NP * NP;
+        a.part_mu = ptr<double>(h->part_mu);
+        a.part_ssq = ptr<double>(h->part_ssq);
+        a.ldpart = cap;
+        if (last) CK(cudaEventRecord(h->ev[10], h->stream));
+        if ((rc = launch_gemm<EPI_COLREDUCE>(h, h->mapP, h->mapKs, a, h->nb * a.mcb))) return rc;
+        if (last) CK(cudaEventRecord(h->ev[11], h->stream));
+        h->launches_var += 1;
+        h->last_chunk_rows = mcp;
+        FinishArgs f;
+        memset(&f, 0, sizeof(f));
+        f.part_mu = ptr<double>(h->part_mu); f.part_ssq = ptr<double>(h->part_ssq);
+        f.ldpart = cap; f.nparts = h->nb; f.m = mc; f.base = base;
+        f.kss = h->spec.amp; f.mean = h->mean;
+        f.norm_out = h->norm_out; f.y_mean = h->y_mean; f.y_std = h->y_std;
+        f.acq_kind = kind; f.eta = eta; f.par = par;
+        f.out_mu = d_mu ? d_mu + base : nullptr;
+        f.out_var = d_var ? d_var + base : nullptr;
+        f.out_acq = d_out ? d_out + base : nullptr;
+        f.block_best = ptr<BestPair>(h->block_best);
+        f.n_negative = d_nneg;
+        const int fb = (int)((mc + 255) / 256);
+        gpk_finish_kernel<<<fb, 256, 0, h->stream>>>(f);
+        CKL();
+        if (kind != GPK_ACQ_NONE) {
+            gpk_argmax_final_kernel<<<1, 256, 0, h->stream>>>(ptr<BestPair>(h->block_best), fb, d_best);
+            CKL();
+        }
+        if (last) CK(cudaEventRecord(h->ev[12], h->stream));
+    }
+    CK(cudaEventRecord(h->ev[7], h->stream));
+    h->score_timed = true;
+    return GPK_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* gpk_version(void) { return "gpk 0.1 (sm_100a, fp64 DMMA + TMA)"; }
+
+const char* gpk_last_error(gpk_handle* h) { return h ? h->err : "null handle"; }
+
+int gpk_create(gpk_handle** out, int device) {
+    if (!out) return GPK_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return GPK_CUDA_ERROR;
+    gpk_handle* h = new gpk_handle();
+    h->device = device;
+    memset(&h->spec, 0, sizeof(h->spec));
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
+    h->stream = h->own_stream;
+    for (int i = 0; i < 16; ++i)
+        if (cudaEventCreate(&h->ev[i]) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
+    h->ev_ok = true;
+    int rc = set_kernel_attrs(h);
+    if (rc) { fprintf(stderr, "gpk_create: %s\n", h->err); delete h; return rc; }
+    rc = ensure(h, h->status, 4);
+    if (!rc) rc = ensure(h, h->scal, 64);
+    if (rc) { delete h; return rc; }
+    if (get_encode_fn() == nullptr) h->loader = LOADER_CPASYNC;
+    *out = h;
+    return GPK_OK;
+}
+
+int gpk_destroy(gpk_handle* h) {
+    if (!h) return GPK_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
+                      &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->part_mu, &h->part_ssq, &h->out_mu,
+                      &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (h->ev_ok)
+        for (int i = 0; i < 16; ++i) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return GPK_OK;
+}
+
+int gpk_set_option(gpk_handle* h, const char* key, long value) {
+    if (!h || !key) return GPK_BAD_ARG;
+    if (!strcmp(key, "loader")) {
+        if (value != LOADER_TMA && value != LOADER_CPASYNC) BAD("loader must be 0 (cp.async) or 1 (TMA)");
+        if (value == LOADER_TMA && get_encode_fn() == nullptr) BAD("TMA descriptors unavailable on this driver");
+        h->loader = (int)value;
+        h->maps_ok = false;
+        h->mapKs_rows = 0;
+        h->mapVt_rows = 0;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "chunk")) {
+        if (value < BM || value % BM) BAD("chunk must be a positive multiple of 128");
+        h->chunk = value;
+        return GPK_OK;
+    }
+    BAD("unknown option '%s'", key);
+}
+
+int gpk_set_stream(gpk_handle* h, void* s) {
+    if (!h) return GPK_BAD_ARG;
+    cudaStreamSynchronize(h->stream);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return GPK_OK;
+}
+
+int gpk_synchronize(gpk_handle* h) {
+    if (!h) return GPK_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_set_data(gpk_handle* h, const double* X, const double* y, int n, int d) {
+    if (!h) return GPK_BAD_ARG;
+    if (!X || !y || n <= 0 || d <= 0) BAD("gpk_set_data: need X, y, n > 0, d > 0");
+    if (d > GPK_MAX_TERMS) BAD("gpk_set_data: d = %d exceeds GPK_MAX_TERMS = %d", d, GPK_MAX_TERMS);
+    CK(cudaSetDevice(h->device));
+    const long NP = round_up(n, BM);
+    int rc;
+    bool g1, g2, g3, g4;
+    if ((rc = ensure(h, h->Xrow, (size_t)n * d * 8))) return rc;
+    if ((rc = ensure(h, h->Xt, (size_t)d * NP * 8))) return rc;
+    if ((rc = ensure(h, h->y, (size_t)NP * 8))) return rc;
+    if ((rc = ensure(h, h->Kbuf, (size_t)(NP + BM) * NP * 8, &g1))) return rc;
+    if ((rc = ensure(h, h->P, (size_t)NP * NP * 8, &g2))) return rc;
+    if ((rc = ensure(h, h->Q, (size_t)NP * NP * 8, &g3))) return rc;
+    if ((rc = ensure(h, h->W, (size_t)NP * NP * 8, &g4))) return rc;
+    if ((rc = ensure(h, h->logdet_part, (size_t)(NP / BM) * 8))) return rc;
+    const bool relayout = (h->layout_NP != NP) || g1 || g2 || g3 || g4;
+    h->n = n; h->d = d; h->NP = (int)NP; h->nb = (int)(NP / BM);
+    if (relayout) {
+        CK(cudaMemsetAsync(h->Kbuf.p, 0, (size_t)(NP + BM) * NP * 8, h->stream));
+        CK(cudaMemsetAsync(h->P.p, 0, (size_t)NP * NP * 8, h->stream));
+        CK(cudaMemsetAsync(h->Q.p, 0, (size_t)NP * NP * 8, h->stream));
+        CK(cudaMemsetAsync(h->W.p, 0, (size_t)NP * NP * 8, h->stream));
+        h->layout_NP = (int)NP;
+        h->maps_ok = false;
+    }
+    CK(cudaMemcpyAsync(h->Xrow.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->y.p, 0, (size_t)NP * 8, h->stream));
+    CK(cudaMemcpyAsync(h->y.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    {
+        long total = (long)d * NP;
+        gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->Xrow), n, d, nullptr,
+                                                                                    nullptr, ptr<double>(h->Xt), NP);
+        CKL();
+    }
+    CK(cudaStreamSynchronize(h->stream));     // host buffers are caller-owned: done with them
+    if ((rc = build_job_tables(h))) return rc;
+    if (!h->maps_ok && (rc = rebuild_maps(h))) return rc;
+    h->has_data = true;
+    h->fitted = false;
+    h->linv_ready = false;
+    h->alpha_ready = false;
+    return GPK_OK;
+}
+
+int gpk_set_input_bounds(gpk_handle* h, const double* lower, const double* upper, int d) {
+    if (!h) return GPK_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!lower || !upper) { h->has_bounds = false; return GPK_OK; }
+    if (d <= 0 || d > GPK_MAX_TERMS) BAD("gpk_set_input_bounds: bad d");
+    int rc;
+    if ((rc = ensure(h, h->lower, (size_t)d * 8))) return rc;
+    if ((rc = ensure(h, h->upper, (size_t)d * 8))) return rc;
+    CK(cudaMemcpyAsync(h->lower.p, lower, (size_t)d * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->upper.p, upper, (size_t)d * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_bounds = true;
+    return GPK_OK;
+}
+
+int gpk_set_output_transform(gpk_handle* h, int enabled, double y_mean, double y_std) {
+    if (!h) return GPK_BAD_ARG;
+    h->norm_out = enabled ? 1 : 0;
+    h->y_mean = y_mean;
+    h->y_std = y_std;
+    return GPK_OK;
+}
+
+int gpk_set_kernel(gpk_handle* h, int family, double log_amp, int n_terms, const int* axis, const int* group,
+                   const double* log_metric) {
+    if (!h) return GPK_BAD_ARG;
+    if (family < GPK_MATERN52 || family > GPK_MATERN32) BAD("gpk_set_kernel: unknown family %d", family);
+    if (n_terms <= 0 || n_terms > GPK_MAX_TERMS || !axis || !group || !log_metric)
+        BAD("gpk_set_kernel: need 1..%d terms", GPK_MAX_TERMS);
+    KSpec s;
+    memset(&s, 0, sizeof(s));
+    s.family = family;
+    s.n_terms = n_terms;
+    s.amp = exp(log_amp);
+    for (int t = 0; t < n_terms; ++t) {
+        if (axis[t] < 0 || axis[t] >= GPK_MAX_TERMS) BAD("gpk_set_kernel: axis out of range");
+        if (t > 0 && (group[t] < group[t - 1] || group[t] > group[t - 1] + 1)) BAD("gpk_set_kernel: groups must be contiguous");
+        s.axis[t] = axis[t];
+        s.inv_metric[t] = 1.0 / exp(log_metric[t]);
+        s.last[t] = (t == n_terms - 1) || (group[t + 1] != group[t]);
+    }
+    if (group[0] != 0) BAD("gpk_set_kernel: groups must start at 0");
+    h->spec = s;
+    h->log_amp = log_amp;
+    h->log_metric.assign(log_metric, log_metric + n_terms);
+    h->has_spec = true;
+    h->fitted = false;
+    h->linv_ready = false;
+    h->alpha_ready = false;
+    return GPK_OK;
+}
+
+int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double* loglik) {
+    int rc = require(h, true, true, false);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    for (int t = 0; t < h->spec.n_terms; ++t)
+        if (h->spec.axis[t] >= h->d) BAD("gpk_fit: kernel axis %d >= d = %d", h->spec.axis[t], h->d);
+    const long NP = h->NP;
+    const int nb = h->nb;
+    h->fitted = false;
+    h->linv_ready = false;
+    h->alpha_ready = false;
+    h->mean = mean;
+    h->diag_add = diag_add;
+    double* K = ptr<double>(h->Kbuf);
+
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    {
+        dim3 cg((unsigned)(NP / 128), (unsigned)(NP / 32));
+        gpk_cov_kernel<<<cg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->Xrow), h->d,
+                                                  (long)h->n, nullptr, nullptr, K, NP, 1);
+        CKL();
+        gpk_kfix_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, h->stream>>>(K, NP, h->n, (int)NP, diag_add,
+                                                                            ptr<double>(h->y), mean);
+        CKL();
+    }
+    CK(cudaMemsetAsync(h->status.p, 0, 4, h->stream));
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    for (int k = 0; k < nb; ++k) {
+        gpk_potrf_diag_kernel<<<1, 256, DIAG_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
+                                                                ptr<int>(h->status), ptr<double>(h->logdet_part));
+        CKL();
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = K; a.lda = NP;
+        a.B = ptr<double>(h->P); a.ldb = NP;
+        a.C = K; a.ldc = NP;
+        a.alpha = 1.0; a.beta = 0;
+        a.jobs = ptr<GemmJob>(h->jobs) + h->trsm_r[k].off;
+        a.job_mode = JOBS_TABLE;
+        a.status = ptr<int>(h->status);
+        if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapP, a, h->trsm_r[k].cnt))) return rc;
+        GemmArgs s;
+        memset(&s, 0, sizeof(s));
+        s.A = K; s.lda = NP;
+        s.B = K; s.ldb = NP;
+        s.C = K; s.ldc = NP;
+        s.alpha = -1.0; s.beta = 1;
+        s.jobs = ptr<GemmJob>(h->jobs) + h->syrk_r[k].off;
+        s.job_mode = JOBS_TABLE;
+        s.status = ptr<int>(h->status);
+        if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, h->syrk_r[k].cnt))) return rc;
+    }
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    gpk_fit_reduce_kernel<<<1, 256, 0, h->stream>>>(K + NP * NP, h->n, ptr<double>(h->logdet_part), nb,
+                                                    ptr<double>(h->scal));
+    CKL();
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    double sc[2];
+    int st = 0;
+    CK(cudaMemcpyAsync(sc, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&st, h->status.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->fit_timed = true;
+    if (st != 0) {
+        set_err(h, "matrix is not positive definite: pivot %d <= 0", st - 1);
+        return GPK_NOT_PD;
+    }
+    const double ld = sc[1];
+    const double ll = -0.5 * sc[0] - 0.5 * ld - 0.5 * (double)h->n * log(2.0 * M_PI);
+    if (logdet) *logdet = ld;
+    if (loglik) *loglik = ll;
+    h->fitted = true;
+    return GPK_OK;
+}
+
+int gpk_acq_dev(gpk_handle* h, const void* d_Xs, long m, int kind, double eta, double par, void* d_out, void* d_mu,
+                void* d_var, void* d_best) {
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!d_Xs || m <= 0) BAD("gpk_acq_dev: need candidates");
+    if (kind < GPK_ACQ_NONE || kind > GPK_ACQ_LCB) BAD("gpk_acq_dev: unknown acquisition %d", kind);
+    CK(cudaSetDevice(h->device));
+    return score_dev(h, (const double*)d_Xs, m, kind, eta, par, (double*)d_out, (double*)d_mu, (double*)d_var,
+                     (BestPair*)d_best, nullptr);
+}
+
+int gpk_acq(gpk_handle* h, const double* Xs, long m, int kind, double eta, double par, double* out, double* mu,
+            double* var, double* best_val, long* best_idx, long* n_negative) {
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!Xs || m <= 0) BAD("gpk_acq: need candidates");
+    if (kind < GPK_ACQ_NONE || kind > GPK_ACQ_LCB) BAD("gpk_acq: unknown acquisition %d", kind);
+    CK(cudaSetDevice(h->device));
+    if ((rc = ensure(h, h->cand, (size_t)m * h->d * 8))) return rc;
+    if (out && (rc = ensure(h, h->out_acq, (size_t)m * 8))) return rc;
+    if (mu && (rc = ensure(h, h->out_mu, (size_t)m * 8))) return rc;
+    if (var && (rc = ensure(h, h->out_var, (size_t)m * 8))) return rc;
+    CK(cudaEventRecord(h->ev[14], h->stream));
+    CK(cudaMemcpyAsync(h->cand.p, Xs, (size_t)m * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = score_dev(h, ptr<double>(h->cand), m, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,
+                   mu ? ptr<double>(h->out_mu) : nullptr, var ? ptr<double>(h->out_var) : nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (out) CK(cudaMemcpyAsync(out, h->out_acq.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (mu) CK(cudaMemcpyAsync(mu, h->out_mu.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (var) CK(cudaMemcpyAsync(var, h->out_var.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    BestPair bp;
+    unsigned long long nn = 0;
+    CK(cudaMemcpyAsync(&bp, h->best.p, sizeof(bp), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&nn, h->nneg.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev[15], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (best_val) *best_val = bp.val;
+    if (best_idx) *best_idx = (long)bp.idx;
+    if (n_negative) *n_negative = (long)nn;
+    return GPK_OK;
+}
+
+int gpk_predict(gpk_handle* h, const double* Xs, long m, double* mu, double* var) {
+    return gpk_acq(h, Xs, m, GPK_ACQ_NONE, 0.0, 0.0, nullptr, mu, var, nullptr, nullptr, nullptr);
+}
+
+int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double* cov) {
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!Xs || m <= 0 || !mu || !cov) BAD("gpk_predict_cov: need Xs, mu, cov");
+    if (m > 16384) BAD("gpk_predict_cov: m = %ld too large for a dense m x m covariance", m);
+    CK(cudaSetDevice(h->device));
+    if ((rc = build_linv(h))) return rc;
+    const long NP = h->NP, mp = round_up(m, BM);
+    const int nb = h->nb, mb = (int)(mp / BM);
+    if ((rc = ensure(h, h->cand, (size_t)m * h->d * 8))) return rc;
+    if ((rc = ensure_score_scratch(h, mp))) return rc;
+    bool grew = false;
+    if ((rc = ensure(h, h->Vt, (size_t)mp * NP * 8, &grew))) return rc;
+    if (grew || h->mapVt_rows != mp) {
+        if (h->loader == LOADER_TMA && (rc = make_map(h, &h->mapVt, h->Vt.p, mp, NP, NP))) return rc;
+        h->mapVt_rows = mp;
+    }
+    if ((rc = ensure(h, h->cov, (size_t)mp * mp * 8))) return rc;
+    if ((rc = ensure(h, h->XsT, (size_t)h->d * mp * 8))) return rc;
+    if ((rc = ensure(h, h->out_mu, (size_t)mp * 8))) return rc;
+    CK(cudaMemcpyAsync(h->cand.p, Xs, (size_t)m * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
+    const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
+    // K* (mp x NP)
+    gpk_cov_kernel<<<dim3((unsigned)(NP / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
+        h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->cand), h->d, m, lo, up, ptr<double>(h->Kstar), NP, 0);
+    CKL();
+    // K** (mp x mp): candidates against (scaled, transposed) candidates
+    {
+        long total = (long)h->d * mp;
+        gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->cand), m, h->d, lo,
+                                                                                    up, ptr<double>(h->XsT), mp);
+        CKL();
+        gpk_cov_kernel<<<dim3((unsigned)(mp / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
+            h->spec, ptr<double>(h->XsT), mp, (int)m, ptr<double>(h->cand), h->d, m, lo, up, ptr<double>(h->cov), mp, 0);
+        CKL();
+    }
+    // V^T = (L^-1 K*^T)^T  ->  Vt[cand][i]
+    std::vector<GemmJob> jobs;
+    for (int ib = nb - 1; ib >= 0; --ib)
+        for (int cb = 0; cb < mb; ++cb) jobs.push_back({ib * BM, cb * BM, 0, (ib + 1) * BM, ib * BM, cb * BM, 0, 0});
+    const size_t n1 = jobs.size();
+    for (int a = 0; a < mb; ++a)
+        for (int b = 0; b < mb; ++b) jobs.push_back({a * BM, b * BM, 0, (int)NP, a * BM, b * BM, 0, 0});
+    if ((rc = ensure(h, h->tmpjobs, jobs.size() * sizeof(GemmJob)))) return rc;
+    CK(cudaMemcpyAsync(h->tmpjobs.p, jobs.data(), jobs.size() * sizeof(GemmJob), cudaMemcpyHostToDevice, h->stream));
+    {
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = ptr<double>(h->P); a.lda = NP;
+        a.B = ptr<double>(h->Kstar); a.ldb = NP;
+        a.Ct = ptr<double>(h->Vt); a.ldct = NP;
+        a.alpha = 1.0;
+        a.jobs = ptr<GemmJob>(h->tmpjobs);
+        a.job_mode = JOBS_TABLE;
+        if ((rc = launch_gemm<EPI_STORE>(h, h->mapP, h->mapKs, a, (int)n1))) return rc;
+    }
+    // mu = Vt z ; cov = K** - Vt Vt^T
+    gpk_rowdot_kernel<<<(unsigned)((mp + 7) / 8), 256, 0, h->stream>>>(ptr<double>(h->Vt), NP, m, (int)NP, 0,
+                                                                        ptr<double>(h->Kbuf) + NP * NP,
+                                                                        ptr<double>(h->out_mu));
+    CKL();
+    gpk_mu_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->out_mu), m, h->mean,
+                                                                            h->norm_out, h->y_mean, h->y_std);
+    CKL();
+    {
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = ptr<double>(h->Vt); a.lda = NP;
+        a.B = ptr<double>(h->Vt); a.ldb = NP;
+        a.C = ptr<double>(h->cov); a.ldc = mp;
+        a.alpha = -1.0; a.beta = 1;
+        a.jobs = ptr<GemmJob>(h->tmpjobs) + n1;
+        a.job_mode = JOBS_TABLE;
+        if ((rc = launch_gemm<EPI_STORE>(h, h->mapVt, h->mapVt, a, (int)(jobs.size() - n1)))) return rc;
+    }
+    gpk_cov_finish_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->cov), mp, m,
+                                                                                 h->norm_out, h->y_std);
+    CKL();
+    CK(cudaMemcpyAsync(mu, h->out_mu.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(cov, (size_t)m * 8, h->cov.p, (size_t)mp * 8, (size_t)m * 8, (size_t)m, cudaMemcpyDeviceToHost,
+                         h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_acq_moments(gpk_handle* h, const double* mu, const double* var, long m, int kind, double eta, double par,
+                    double* out, long* n_negative) {
+    if (!h) return GPK_BAD_ARG;
+    if (!mu || !var || !out || m <= 0) BAD("gpk_acq_moments: need mu, var, out");
+    if (kind < GPK_ACQ_EI || kind > GPK_ACQ_LCB) BAD("gpk_acq_moments: unknown acquisition %d", kind);
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure(h, h->tmp1, (size_t)m * 8))) return rc;
+    if ((rc = ensure(h, h->tmp2, (size_t)m * 8))) return rc;
+    if ((rc = ensure(h, h->tmp3, (size_t)m * 8))) return rc;
+    if ((rc = ensure(h, h->nneg, 8))) return rc;
+    CK(cudaMemcpyAsync(h->tmp1.p, mu, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp2.p, var, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->nneg.p, 0, 8, h->stream));
+    gpk_acq_moments_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(
+        ptr<double>(h->tmp1), ptr<double>(h->tmp2), m, kind, eta, par, ptr<double>(h->tmp3),
+        ptr<unsigned long long>(h->nneg));
+    CKL();
+    unsigned long long nn = 0;
+    CK(cudaMemcpyAsync(out, h->tmp3.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&nn, h->nneg.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_negative) *n_negative = (long)nn;
+    return GPK_OK;
+}
+
+int gpk_kernel_matrix(gpk_handle* h, const double* X1, long n1, const double* X2, long n2, int d, double* out) {
+    int rc = require(h, false, true, false);
+    if (rc) return rc;
+    if (!X1 || !X2 || !out || n1 <= 0 || n2 <= 0 || d <= 0 || d > GPK_MAX_TERMS) BAD("gpk_kernel_matrix: bad arguments");
+    for (int t = 0; t < h->spec.n_terms; ++t)
+        if (h->spec.axis[t] >= d) BAD("gpk_kernel_matrix: kernel axis %d >= d = %d", h->spec.axis[t], d);
+    CK(cudaSetDevice(h->device));
+    const long n1p = round_up(n1, 32), n2p = round_up(n2, 128);
+    if ((rc = ensure(h, h->tmp1, (size_t)n1 * d * 8))) return rc;
+    if ((rc = ensure(h, h->tmp2, (size_t)std::max<long>(n2 * d, d * n2p) * 8 * 2))) return rc;
+    if ((rc = ensure(h, h->tmp3, (size_t)n1p * n2p * 8))) return rc;
+    double* X2row = ptr<double>(h->tmp2);
+    double* X2t = X2row + n2 * d;
+    CK(cudaMemcpyAsync(h->tmp1.p, X1, (size_t)n1 * d * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(X2row, X2, (size_t)n2 * d * 8, cudaMemcpyHostToDevice, h->stream));
+    long total = (long)d * n2p;
+    gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(X2row, n2, d, nullptr, nullptr, X2t, n2p);
+    CKL();
+    gpk_cov_kernel<<<dim3((unsigned)(n2p / 128), (unsigned)(n1p / 32)), 256, 0, h->stream>>>(
+        h->spec, X2t, n2p, (int)n2, ptr<double>(h->tmp1), d, n1, nullptr, nullptr, ptr<double>(h->tmp3), n2p, 0);
+    CKL();
+    CK(cudaMemcpy2DAsync(out, (size_t)n2 * 8, h->tmp3.p, (size_t)n2p * 8, (size_t)n2 * 8, (size_t)n1,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_nll_grad(gpk_handle* h, double noise_var, double* grad) {
+    (void)noise_var; (void)grad;
+    if (!h) return GPK_BAD_ARG;
+    BAD("gpk_nll_grad: not implemented in this build");
+}
+
+int gpk_get_factor(gpk_handle* h, double* L) {
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!L) BAD("gpk_get_factor: null output");
+    CK(cudaSetDevice(h->device));
+    const long n = h->n, NP = h->NP;
+    CK(cudaMemcpy2DAsync(L, (size_t)n * 8, h->Kbuf.p, (size_t)NP * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost,
+                         h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (long i = 0; i < n; ++i)
+        for (long j = i + 1; j < n; ++j) L[i * n + j] = 0.0;
+    return GPK_OK;
+}
+
+int gpk_get_linv(gpk_handle* h, double* Linv) {
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!Linv) BAD("gpk_get_linv: null output");
+    CK(cudaSetDevice(h->device));
+    if ((rc = build_linv(h))) return rc;
+    const long n = h->n, NP = h->NP;
+    CK(cudaMemcpy2DAsync(Linv, (size_t)n * 8, h->P.p, (size_t)NP * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost,
+                         h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_get_z(gpk_handle* h, double* z) {
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!z) BAD("gpk_get_z: null output");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(z, ptr<double>(h->Kbuf) + (long)h->NP * h->NP, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_get_timings(gpk_handle* h, double* out) {
+    if (!h || !out) return GPK_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 10; ++i) out[i] = 0.0;
+    float ms = 0.f;
+    if (h->fit_timed) {
+        if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]) == cudaSuccess) out[0] = ms;
+        if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) out[1] = ms;
+        if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) out[2] = ms;
+    }
+    if (h->linv_ready && cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) out[3] = ms;
+    if (h->score_timed) {
+        if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) out[4] = ms;
+        if (cudaEventElapsedTime(&ms, h->ev[8], h->ev[10]) == cudaSuccess) out[5] = ms;    // K* of the last chunk
+        if (cudaEventElapsedTime(&ms, h->ev[10], h->ev[11]) == cudaSuccess) out[6] = ms;   // variance GEMM, last chunk
+        if (cudaEventElapsedTime(&ms, h->ev[11], h->ev[12]) == cudaSuccess) out[7] = ms;   // epilogue, last chunk
+    }
+    cudaGetLastError();
+    out[8] = h->launches_var;
+    out[9] = h->launches_total;
+    return GPK_OK;
+}
+
+}  // extern "C"

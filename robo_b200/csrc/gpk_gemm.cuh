@@ -1,0 +1,308 @@
+// gpk_gemm.cuh — fp64 tensor-core (DMMA) tile engine:  C(128x128) (+)= alpha * A(128xK) * B(128xK)^T
+//
+// Every dense contraction of the hot path is an "NT" product of two K-contiguous operands:
+//   Cholesky panel solve    L_ik  =  A_ik * inv(L_kk)^T                     (store)
+//   Cholesky trailing update A_ij -=  L_ik * L_jk^T                          (store, beta = 1)
+//   triangular inverse       T'   =  Q * L^T ;  R = -P * T'^T               (store C and C^T)
+//   predictive variance      V    =  L^-1 * K*^T  ->  sum_i V_ic^2 , sum_i V_ic z_i   (column reduce)
+// One CTA = one 128x128 output tile described by a GemmJob; 8 warps, each a 64x32 sub-tile of
+// m8n8k4 DMMA fragments (64 fp64 accumulators per thread).  Operand tiles (128 rows x 16 k,
+// 16 KB each) are staged through a 4-stage shared-memory ring either by
+//   LOADER_TMA     cp.async.bulk.tensor.2d + mbarrier complete_tx, 128B-swizzled (sm_90+/sm_100a)
+//   LOADER_CPASYNC cp.async.cg 16B with a padded (conflict-free) row stride
+// Both give bank-conflict-free 8-byte fragment loads (see frag_offsets()).
+#pragma once
+#include "gpk_internal.cuh"
+
+enum { LOADER_CPASYNC = 0, LOADER_TMA = 1 };
+enum { EPI_STORE = 0, EPI_COLREDUCE = 1 };
+enum { JOBS_TABLE = 0, JOBS_VARIANCE = 1 };
+
+constexpr int BM = 128, BN = 128, BK = 16, NSTAGE = 4, GEMM_THREADS = 256;
+constexpr int PAD_STRIDE = 20;                                   // doubles per row, cp.async mode
+constexpr int STAGE_BYTES_TMA = (BM + BN) * BK * 8;              // 32768
+constexpr int STAGE_BYTES_PAD = (BM + BN) * PAD_STRIDE * 8;      // 40960
+constexpr int GEMM_SMEM_TMA = NSTAGE * STAGE_BYTES_TMA + 1024 /*align*/ + 64 /*barriers*/ + 2048 /*reduce*/;
+constexpr int GEMM_SMEM_PAD = NSTAGE * STAGE_BYTES_PAD + 1024 + 64 + 2048;
+
+struct GemmJob {
+    int a_row;      // first row of the A tile
+    int b_row;      // first row of the B tile
+    int k0, k1;     // contraction range [k0, k1), multiples of BK
+    int c_row;      // output tile origin (row follows A rows, col follows B rows)
+    int c_col;
+    int aux;        // EPI_COLREDUCE: partial-sum slot
+    int pad;
+};
+
+struct GemmArgs {
+    const double* A; long lda;         // used by the cp.async loader (TMA uses the tensor maps)
+    const double* B; long ldb;
+    double* C; long ldc;               // may be NULL
+    double* Ct; long ldct;             // transposed copy of the output tile, may be NULL
+    double alpha;                      // +1 / -1
+    int beta;                          // 0: overwrite, 1: accumulate into C
+    const GemmJob* jobs;
+    int job_mode;                      // JOBS_TABLE / JOBS_VARIANCE
+    int nb, mcb;                       // JOBS_VARIANCE generator: nb row-blocks x mcb candidate blocks
+    const double* z;                   // EPI_COLREDUCE: row weights (z = L^-1 (y - mean))
+    double* part_mu; double* part_ssq; long ldpart;
+    const int* status;                 // non-zero -> factorisation failed, skip work
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm ("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c_inner, int c_outer,
+                                            uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_dst), "l"((uint64_t)map), "r"(bar), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Which tile row feeds fragment row g (0..7) of an 8-row block.  With the 128B TMA swizzle the
+// 16-byte chunk index is XORed with (row & 7); mapping fragment rows {0,1,2,3 | 4,5,6,7} to tile
+// rows {0,2,4,6 | 1,3,5,7} makes the 16 lanes of each half-warp (4 rows x 4 k) hit 16 distinct
+// 8-byte banks.  The padded layout (stride 20 doubles) is conflict-free with the identity map.
+template <int LOADER> __device__ __forceinline__ int rowmap(int g) {
+    return LOADER == LOADER_TMA ? (((g & 3) << 1) | (g >> 2)) : g;
+}
+
+// Byte offset inside an operand stage of element (row, k).
+template <int LOADER> __device__ __forceinline__ int tile_off(int row, int k) {
+    if (LOADER == LOADER_TMA) return row * 128 + ((((k >> 1) ^ (row & 7))) << 4) + ((k & 1) << 3);
+    return (row * PAD_STRIDE + k) * 8;
+}
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+template <int EPI, int LOADER>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const GemmArgs g)
+{
+    if (g.status != nullptr && *g.status != 0) return;
+
+    extern __shared__ unsigned char smem_raw[];
+    // all shared-memory traffic goes through 32-bit shared-window addresses (LDS/STS, not generic LD/ST)
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024B alignment for the 128B swizzle
+    constexpr int STAGE_BYTES = LOADER == LOADER_TMA ? STAGE_BYTES_TMA : STAGE_BYTES_PAD;
+    constexpr int A_BYTES = LOADER == LOADER_TMA ? BM * BK * 8 : BM * PAD_STRIDE * 8;
+    const uint32_t full_bar = smem + NSTAGE * STAGE_BYTES;              // NSTAGE x 8 bytes
+    const uint32_t red = smem + NSTAGE * STAGE_BYTES + 64;              // 2 x 128 doubles
+
+    // ---- job ----
+    GemmJob job;
+    if (g.job_mode == JOBS_TABLE) {
+        job = g.jobs[blockIdx.x];
+    } else {                                     // longest contractions first
+        int ib = g.nb - 1 - (int)(blockIdx.x / g.mcb);
+        int cb = (int)(blockIdx.x % g.mcb);
+        job.a_row = ib * BM; job.b_row = cb * BN; job.k0 = 0; job.k1 = (ib + 1) * BM;
+        job.c_row = ib * BM; job.c_col = cb * BN; job.aux = ib; job.pad = 0;
+    }
+    const int KT = (job.k1 - job.k0) / BK;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    // per-thread fragment offsets (bytes) inside a stage
+    constexpr int BLK = LOADER == LOADER_TMA ? 8 * 128 : 8 * PAD_STRIDE * 8;   // 8 tile rows
+    const int rA = wm * 64 + rowmap<LOADER>(gq);
+    const int rB = wn * 32 + rowmap<LOADER>(gq);
+    int kxA[4], kxB[4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        kxA[ks] = tile_off<LOADER>(rA, ks * 4 + tq);
+        kxB[ks] = A_BYTES + tile_off<LOADER>(rB, ks * 4 + tq);
+    }
+
+    if (LOADER == LOADER_TMA) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < NSTAGE; ++s) mbar_init(full_bar + 8 * s, 1);
+            fence_barrier_init();
+            fence_proxy_async();
+        }
+        __syncthreads();
+    }
+
+    auto issue_load = [&](int kt) {
+        const int s = kt % NSTAGE;
+        const uint32_t st = smem + s * STAGE_BYTES;
+        const int kcol = job.k0 + kt * BK;
+        if (LOADER == LOADER_TMA) {
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES_TMA);
+                tma_load_2d(st, &mapA, kcol, job.a_row, full_bar + 8 * s);
+                tma_load_2d(st + A_BYTES, &mapB, kcol, job.b_row, full_bar + 8 * s);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int c = tid + i * GEMM_THREADS;          // 1024 16-byte chunks per operand
+                int row = c >> 3, kc = c & 7;
+                cp_async16(st + (uint32_t)((row * PAD_STRIDE + kc * 2) * 8),
+                           g.A + (long)(job.a_row + row) * g.lda + kcol + kc * 2);
+                cp_async16(st + (uint32_t)(A_BYTES + (row * PAD_STRIDE + kc * 2) * 8),
+                           g.B + (long)(job.b_row + row) * g.ldb + kcol + kc * 2);
+            }
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+    // ---- prologue ----
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (s < KT) issue_load(s);
+        if (LOADER == LOADER_CPASYNC) cp_async_commit();
+    }
+
+    // ---- main loop ----
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % NSTAGE;
+        if (LOADER == LOADER_TMA) {
+            const uint32_t parity = (uint32_t)((kt / NSTAGE) & 1);
+            while (!mbar_try_wait(full_bar + 8 * s, parity)) { }
+        } else {
+            cp_async_wait<NSTAGE - 2>();
+        }
+        __syncthreads();          // stage s visible to all; everyone is done with stage (kt-1)%NSTAGE
+        if (kt + NSTAGE - 1 < KT) issue_load(kt + NSTAGE - 1);
+        if (LOADER == LOADER_CPASYNC) cp_async_commit();
+
+        const uint32_t st = smem + s * STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) a[mi] = lds64(st + kxA[ks] + mi * BLK);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = lds64(st + kxB[ks] + ni * BLK);
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    if (LOADER == LOADER_CPASYNC) cp_async_wait<0>();
+
+    // ---- epilogue ----
+    // acc[mi][ni][j]  <->  tile row  wm*64 + mi*8 + rowmap(gq),  tile col  wn*32 + ni*8 + rowmap(2*tq + j)
+    if (EPI == EPI_STORE) {
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) {
+            const long r = job.c_row + wm * 64 + mi * 8 + rowmap<LOADER>(gq);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const long c = job.c_col + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j);
+                    double v = g.alpha * acc[mi][ni][j];
+                    if (g.beta) v += g.C[r * g.ldc + c];
+                    if (g.C) g.C[r * g.ldc + c] = v;
+                    if (g.Ct) g.Ct[c * g.ldct + r] = v;
+                }
+            }
+        }
+    } else {
+        // column reductions over the tile's 128 rows: sum v^2 and sum v * z[row]
+        double zr[8];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) zr[mi] = g.z[job.c_row + wm * 64 + mi * 8 + rowmap<LOADER>(gq)];
+        double ssq[4][2], smu[4][2];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                double s2 = 0.0, sm = 0.0;
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi) {
+                    double v = acc[mi][ni][j];
+                    s2 = fma(v, v, s2);
+                    sm = fma(v, zr[mi], sm);
+                }
+                // reduce over the 8 lanes sharing tq (lane bits 2..4)
+#pragma unroll
+                for (int off = 4; off < 32; off <<= 1) {
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+                    sm += __shfl_xor_sync(0xffffffffu, sm, off);
+                }
+                ssq[ni][j] = s2; smu[ni][j] = sm;
+            }
+        // cross-warp (wm = 0,1) reduction through 'red' [2][128], ssq first, then mu
+        if (gq == 0) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    sts64(red + 8 * (wm * 128 + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j)), ssq[ni][j]);
+        }
+        __syncthreads();
+        if (tid < 128)
+            g.part_ssq[(long)job.aux * g.ldpart + job.c_col + tid] = lds64(red + 8 * tid) + lds64(red + 8 * (128 + tid));
+        __syncthreads();
+        if (gq == 0) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    sts64(red + 8 * (wm * 128 + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j)), smu[ni][j]);
+        }
+        __syncthreads();
+        if (tid < 128)
+            g.part_mu[(long)job.aux * g.ldpart + job.c_col + tid] = lds64(red + 8 * tid) + lds64(red + 8 * (128 + tid));
+    }
+}

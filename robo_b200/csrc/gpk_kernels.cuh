@@ -1,0 +1,308 @@
+// gpk_kernels.cuh — covariance builders, diagonal-block Cholesky/inverse, scoring epilogue.
+#pragma once
+#include "gpk_internal.cuh"
+
+// ---------------------------------------------------------------------------------------
+// Covariance tile builder.  out[c][j] = k(cand_c, train_j)   (row-major, ld = ldo)
+//   train points: transposed, column-contiguous  Xt[axis][j]  (coalesced across threads)
+//   candidates  : row-major raw inputs, optionally scaled (x - lower) / (upper - lower)
+// CTA = 128 train points x 32 candidates, 256 threads, 16 candidates per thread.
+// Rows c >= m and columns j >= n are written as exact zeros (padding must not contribute to
+// the contractions that follow).  tri != 0: skip tiles entirely above the diagonal (K build).
+// Used for K (cand = train), K* (scoring), K** (full_cov) and kernel.get_value.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gpk_cov_kernel(const KSpec ks, const double* __restrict__ Xt, long ldx, int n,
+               const double* __restrict__ cand, int dc, long m,
+               const double* __restrict__ lower, const double* __restrict__ upper,
+               double* __restrict__ out, long ldo, int tri)
+{
+    __shared__ double sc[32][GPK_MAX_TERMS + 1];
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x * 128 + (tid & 127);
+    const long c0 = (long)blockIdx.y * 32;
+    if (tri && (long)blockIdx.x * 128 > c0 + 31) return;
+
+    const int nt = ks.n_terms;
+    for (int e = tid; e < 32 * nt; e += 256) {
+        int c = e / nt, t = e - c * nt;
+        long ci = c0 + c;
+        double v = 0.0;
+        if (ci < m) {
+            int a = ks.axis[t];
+            v = cand[ci * dc + a];
+            if (lower != nullptr) v = (v - lower[a]) / (upper[a] - lower[a]);
+        }
+        sc[c][t] = v;
+    }
+    __syncthreads();
+
+    const int cg = (tid >> 7) * 16;
+    const bool jv = j < n;
+    double r2[16], pr[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { r2[c] = 0.0; pr[c] = 1.0; }
+    for (int t = 0; t < nt; ++t) {
+        const double xj = jv ? Xt[(long)ks.axis[t] * ldx + j] : 0.0;
+        const double im = ks.inv_metric[t];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            double d = sc[cg + c][t] - xj;
+            r2[c] = fma(d * d, im, r2[c]);
+        }
+        if (ks.last[t]) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { pr[c] *= gpk_radial(ks.family, r2[c]); r2[c] = 0.0; }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        long ci = c0 + cg + c;
+        out[ci * ldo + j] = (jv && ci < m) ? ks.amp * pr[c] : 0.0;
+    }
+}
+
+// Xt[a][j] = X[j][a] (optionally scaled), zero padded to ldx columns.
+__global__ void gpk_transpose_kernel(const double* __restrict__ X, long n, int d,
+                                     const double* __restrict__ lower, const double* __restrict__ upper,
+                                     double* __restrict__ Xt, long ldx)
+{
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)d * ldx;
+    if (idx >= total) return;
+    int a = (int)(idx / ldx);
+    long j = idx - (long)a * ldx;
+    double v = 0.0;
+    if (j < n) {
+        v = X[j * d + a];
+        if (lower != nullptr) v = (v - lower[a]) / (upper[a] - lower[a]);
+    }
+    Xt[idx] = v;
+}
+
+// After the K build: diagonal += diag_add (george: yerr^2 + TINY), unit diagonal on padding rows,
+// and the augmented right-hand-side row  K[NP][j] = y_j - mean  (so the blocked Cholesky also
+// produces z = L^-1 (y - mean) as row NP of the factor; rows NP+1.. stay zero).
+__global__ void gpk_kfix_kernel(double* __restrict__ K, long ld, int n, int NP, double diag_add,
+                                const double* __restrict__ y, double mean)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP) return;
+    K[(long)i * ld + i] = (i < n) ? K[(long)i * ld + i] + diag_add : 1.0;
+    K[(long)NP * ld + i] = (i < n) ? y[i] - mean : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Diagonal block: L_kk = chol(A_kk) in shared memory, then inv(L_kk) in place.
+//   writes L_kk (lower, upper zeroed) back to K,
+//   inv(L_kk) to the diagonal block of P (lower) and its transpose to Q (upper),
+//   sum log diag(L_kk) to logdet_part[kb], and flags a non-positive pivot in *status
+//   (1 + global pivot index), which is what scipy.linalg.cholesky reports as LinAlgError.
+// One CTA, 256 threads, dynamic smem 128 x 129 doubles + 3 x 128.
+// ---------------------------------------------------------------------------------------
+constexpr int DIAG_SMEM = (128 * 129 + 2 * 128) * 8;
+
+__global__ void __launch_bounds__(256)
+gpk_potrf_diag_kernel(double* __restrict__ K, long ld, int kb,
+                      double* __restrict__ P, double* __restrict__ Q, long ldp,
+                      int* __restrict__ status, double* __restrict__ logdet_part)
+{
+    extern __shared__ double dsm[];
+    double (*A)[129] = (double (*)[129])dsm;
+    double* dsq = dsm + 128 * 129;       // sqrt of pivots
+    double* vbuf = dsq + 128;
+    __shared__ double pb2[256];
+    __shared__ int s_bad;
+
+    const int tid = threadIdx.x;
+    if (*status != 0) return;
+    if (tid == 0) s_bad = 0;
+
+    double* Kt = K + (long)kb * 128 * ld + (long)kb * 128;
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        A[r][c] = Kt[(long)r * ld + c];
+    }
+    __syncthreads();
+
+    const int i = tid & 127, h = tid >> 7;
+    // ---- elimination: after step j, column j holds the un-scaled column, A[j][j] = pivot d_j
+    for (int j = 0; j < 128; ++j) {
+        double d = A[j][j];
+        if (!(d > 0.0) || isinf(d)) {
+            if (tid == 0 && s_bad == 0) s_bad = kb * 128 + j + 1;
+            d = 1.0;
+        }
+        const double invd = 1.0 / d;
+        if (i > j) {
+            const double lij = A[i][j] * invd;
+            for (int c = j + 1 + h; c <= i; c += 2) A[i][c] -= lij * A[c][j];
+        }
+        __syncthreads();
+    }
+    if (tid < 128) {
+        double d = A[tid][tid];
+        if (!(d > 0.0) || isinf(d)) d = 1.0;
+        dsq[tid] = sqrt(d);
+    }
+    __syncthreads();
+    // ---- finalise L and write it back
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        double v = 0.0;
+        if (c < r) { v = A[r][c] / dsq[c]; }
+        else if (c == r) v = dsq[c];
+        Kt[(long)r * ld + c] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        if (c < r) A[r][c] = A[r][c] / dsq[c];
+    }
+    if (tid < 32) {
+        double s = 0.0;
+        for (int q = tid; q < 128; q += 32) s += log(dsq[q]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (tid == 0) logdet_part[kb] = s;
+    }
+    __syncthreads();
+    if (tid == 0 && s_bad != 0) atomicCAS(status, 0, s_bad);
+
+    // ---- in-place inverse of the lower-triangular block, right to left (LAPACK dtrti2 order)
+    for (int j = 127; j >= 0; --j) {
+        const double ajj = 1.0 / dsq[j];
+        if (tid < 128 && tid > j) vbuf[tid] = A[tid][j];
+        __syncthreads();
+        double part = 0.0;
+        if (i > j) {
+            for (int c = j + 1 + h; c <= i; c += 2) part = fma(A[i][c], vbuf[c], part);
+        }
+        pb2[tid] = part;
+        __syncthreads();
+        if (h == 0 && i > j) A[i][j] = -(pb2[i] + pb2[128 + i]) * ajj;
+        if (tid == 0) A[j][j] = ajj;
+    }
+    __syncthreads();
+    double* Pt = P + (long)kb * 128 * ldp + (long)kb * 128;
+    double* Qt = Q + (long)kb * 128 * ldp + (long)kb * 128;
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        Pt[(long)r * ldp + c] = (c <= r) ? A[r][c] : 0.0;
+        Qt[(long)r * ldp + c] = (c >= r) ? A[c][r] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Scoring epilogue: sum the per-row-block partials in fixed order, finish mean / variance,
+// apply the output transform + clip (gaussian_process.py:282-294), the acquisition closed form,
+// and a per-block arg-max with numpy.argmax tie-breaking.
+// ---------------------------------------------------------------------------------------
+struct FinishArgs {
+    const double* part_mu; const double* part_ssq; long ldpart; int nparts;
+    long m;                 // valid candidates in this chunk
+    long base;              // global index of the chunk's first candidate
+    double kss;             // k(x*, x*) = amplitude (stationary kernels)
+    double mean;            // GP constant mean
+    int norm_out; double y_mean, y_std;
+    int acq_kind; double eta, par;
+    double* out_mu; double* out_var; double* out_acq;    // chunk-local device arrays, may be NULL
+    BestPair* block_best;   // one per block
+    unsigned long long* n_negative;
+};
+
+__global__ void __launch_bounds__(256) gpk_finish_kernel(const FinishArgs f)
+{
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    double val = 0.0;
+    long long idx = -1;
+    if (c < f.m) {
+        double ssq = 0.0, mu = 0.0;
+        for (int p = 0; p < f.nparts; ++p) {
+            ssq += f.part_ssq[(long)p * f.ldpart + c];
+            mu += f.part_mu[(long)p * f.ldpart + c];
+        }
+        double var = f.kss - ssq;
+        mu += f.mean;
+        if (f.norm_out) { mu = mu * f.y_std + f.y_mean; var = var * (f.y_std * f.y_std); }
+        if (var < GPK_EPS) var = GPK_EPS;                  // np.clip(var, eps, inf); NaN stays NaN
+        if (f.out_mu) f.out_mu[c] = mu;
+        if (f.out_var) f.out_var[c] = var;
+        if (f.acq_kind != GPK_ACQ_NONE) {
+            val = gpk_acq_value(f.acq_kind, mu, var, f.eta, f.par);
+            if (f.out_acq) f.out_acq[c] = val;
+            if (f.acq_kind == GPK_ACQ_EI && val < 0.0 && f.n_negative) atomicAdd(f.n_negative, 1ULL);
+            idx = f.base + c;
+        }
+    }
+    if (f.acq_kind == GPK_ACQ_NONE || f.block_best == nullptr) return;
+    // block arg-max
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, val, off);
+        long long oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (gpk_better(ov, oi, val, idx)) { val = ov; idx = oi; }
+    }
+    __shared__ double sv[8];
+    __shared__ long long si[8];
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = val; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (gpk_better(sv[w], si[w], val, idx)) { val = sv[w]; idx = si[w]; }
+        f.block_best[blockIdx.x].val = val;
+        f.block_best[blockIdx.x].idx = idx;
+    }
+}
+
+// Final arg-max over block results, merged into *best (which may hold the running best of
+// earlier chunks; idx < 0 means empty).
+__global__ void __launch_bounds__(256) gpk_argmax_final_kernel(const BestPair* __restrict__ bb, int nblocks,
+                                                               BestPair* __restrict__ best)
+{
+    double val = 0.0;
+    long long idx = -1;
+    for (int b = threadIdx.x; b < nblocks; b += 256)
+        if (gpk_better(bb[b].val, bb[b].idx, val, idx)) { val = bb[b].val; idx = bb[b].idx; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, val, off);
+        long long oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (gpk_better(ov, oi, val, idx)) { val = ov; idx = oi; }
+    }
+    __shared__ double sv[8];
+    __shared__ long long si[8];
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = val; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (gpk_better(sv[w], si[w], val, idx)) { val = sv[w]; idx = si[w]; }
+        if (gpk_better(val, idx, best->val, best->idx)) { best->val = val; best->idx = idx; }
+    }
+}
+
+// Acquisition closed form on supplied moments (gpk_acq_moments).
+__global__ void gpk_acq_moments_kernel(const double* __restrict__ mu, const double* __restrict__ var, long m,
+                                       int kind, double eta, double par, double* __restrict__ out,
+                                       unsigned long long* n_negative)
+{
+    long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    double v = gpk_acq_value(kind, mu[c], var[c], eta, par);
+    out[c] = v;
+    if (kind == GPK_ACQ_EI && v < 0.0) atomicAdd(n_negative, 1ULL);
+}
+
+// full_cov epilogue: clip every entry to >= eps after the output transform
+// (gaussian_process.py:282-294 applies the clip to the whole matrix).
+__global__ void gpk_cov_finish_kernel(double* __restrict__ cov, long ld, long m, int norm_out, double y_std)
+{
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * m) return;
+    long r = idx / m, c = idx - r * m;
+    double v = cov[r * ld + c];
+    if (norm_out) v *= y_std * y_std;
+    if (v < GPK_EPS) v = GPK_EPS;
+    cov[r * ld + c] = v;
+}
+
