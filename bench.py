@@ -175,7 +175,9 @@ def run_ours(args, rank, world, local_rank):
     X, y, Xs, theta, noise = problem(M, seed_cand=4321 + rank)
 
     h = _lib.Handle(local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: the handle launches on it, and torch.cuda.Event timing sees it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
     h.set_option("chunk", args.chunk)
     h.set_data(X, y)

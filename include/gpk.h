@@ -59,7 +59,8 @@ int gpk_destroy(gpk_handle* h);
 const char* gpk_last_error(gpk_handle* h);
 const char* gpk_version(void);
 /* key in {"loader" (0 = cp.async staging, 1 = TMA staging [default]), "chunk" (candidates per
- * scoring pass, multiple of 128), "graph" (1 = replay the fit as a CUDA graph)} */
+ * scoring pass, multiple of 128), "diag" (diagonal-block Cholesky kernel: 1 = register-tiled
+ * [default], 0 = simple shared-memory version kept as a cross-check)} */
 int gpk_set_option(gpk_handle* h, const char* key, long value);
 /* run on an existing CUDA stream (cudaStream_t passed as void*); NULL = the handle's own */
 int gpk_set_stream(gpk_handle* h, void* cuda_stream);

@@ -39,6 +39,7 @@ struct gpk_handle {
     char err[1024] = {0};
     int loader = LOADER_TMA;
     long chunk = 16384;
+    int diag_kernel = 1;          // 1 = register-tiled diagonal block kernel, 0 = simple shared-memory one
 
     // model
     int n = 0, d = 0, NP = 0, nb = 0;
@@ -183,6 +184,7 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_CPASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+    CK(cudaFuncSetAttribute(gpk_potrf_diag_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
     return GPK_OK;
 }
 
@@ -499,6 +501,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->mapVt_rows = 0;
         return GPK_OK;
     }
+    if (!strcmp(key, "diag")) {
+        if (value != 0 && value != 1) BAD("diag must be 0 (shared-memory kernel) or 1 (register-tiled kernel)");
+        h->diag_kernel = (int)value;
+        return GPK_OK;
+    }
     if (!strcmp(key, "chunk")) {
         if (value < BM || value % BM) BAD("chunk must be a positive multiple of 128");
         h->chunk = value;
@@ -646,8 +653,12 @@ int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double*
     CK(cudaMemsetAsync(h->status.p, 0, 4, h->stream));
     CK(cudaEventRecord(h->ev[1], h->stream));
     for (int k = 0; k < nb; ++k) {
-        gpk_potrf_diag_kernel<<<1, 256, DIAG_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
-                                                                ptr<int>(h->status), ptr<double>(h->logdet_part));
+        if (h->diag_kernel == 1)
+            gpk_potrf_diag_reg_kernel<<<1, 256, DIAG2_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
+                                                                         ptr<int>(h->status), ptr<double>(h->logdet_part));
+        else
+            gpk_potrf_diag_kernel<<<1, 256, DIAG_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
+                                                                    ptr<int>(h->status), ptr<double>(h->logdet_part));
         CKL();
         GemmArgs a;
         memset(&a, 0, sizeof(a));

@@ -68,6 +68,15 @@ __device__ __forceinline__ double gpk_acq_value(int kind, double m, double v, do
     double s = sqrt(v);
     if (kind == GPK_ACQ_EI) {
         double z = (eta - m - par) / s;
+        if (z < -30.0) {
+            // deep lower tail: z Phi(z) + phi(z) = phi(z) (1 - |z| R(|z|)), R = Mills ratio
+            // = sqrt(pi/2) erfcx(|z|/sqrt 2).  Same value as the direct form (both lose ~z^2 ulp to
+            // cancellation) but the sign is decided in the normal range, so EI never turns negative
+            // when phi and Phi go subnormal (|z| > 37.6), where the reference's scipy result is >= 0.
+            double az = -z;
+            double bracket = 1.0 - az * 1.25331413731550025121 * erfcx(az * 0.70710678118654752440);
+            return s * (gpk_norm_pdf(z) * bracket);
+        }
         return s * (z * gpk_ndtr(z) + gpk_norm_pdf(z));
     } else if (kind == GPK_ACQ_PI) {
         return gpk_ndtr((eta - m - par) / s);
