@@ -19,6 +19,7 @@ enum { EPI_STORE = 0, EPI_COLREDUCE = 1 };
 enum { JOBS_TABLE = 0, JOBS_VARIANCE = 1 };
 
 constexpr int BM = 128, BN = 128, BK = 16, NSTAGE = 4, GEMM_THREADS = 256;
+constexpr int VAR_GROUP = 16;                                    // candidate blocks per L2-resident group
 constexpr int PAD_STRIDE = 20;                                   // doubles per row, cp.async mode
 constexpr int STAGE_BYTES_TMA = (BM + BN) * BK * 8;              // 32768
 constexpr int STAGE_BYTES_PAD = (BM + BN) * PAD_STRIDE * 8;      // 40960
@@ -140,9 +141,16 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     GemmJob job;
     if (g.job_mode == JOBS_TABLE) {
         job = g.jobs[blockIdx.x];
-    } else {                                     // longest contractions first
-        int ib = g.nb - 1 - (int)(blockIdx.x / g.mcb);
-        int cb = (int)(blockIdx.x % g.mcb);
+    } else {
+        // Candidate blocks are taken in groups of VAR_GROUP (16 blocks = 2048 candidates = 64 MB of
+        // K* at N = 4096, which stays L2-resident while the group walks all row-blocks of L^-1);
+        // inside a group the longest contractions (largest row-block) come first.
+        const int full = g.mcb / VAR_GROUP;
+        int id = (int)blockIdx.x, grp = id / (g.nb * VAR_GROUP), gsz = VAR_GROUP;
+        if (grp >= full) { grp = full; gsz = g.mcb - full * VAR_GROUP; }
+        id -= grp * g.nb * VAR_GROUP;
+        int ib = g.nb - 1 - id / gsz;
+        int cb = grp * VAR_GROUP + id % gsz;
         job.a_row = ib * BM; job.b_row = cb * BN; job.k0 = 0; job.k1 = (ib + 1) * BM;
         job.c_row = ib * BM; job.c_col = cb * BN; job.aux = ib; job.pad = 0;
     }

@@ -202,12 +202,12 @@ gpk_potrf_diag_kernel(double* __restrict__ K, long ld, int kb,
 // forward substitution L X = I with X in registers, L read from shared memory, row j of X
 // broadcast through a second double-buffered vector (1 barrier per row).
 // ---------------------------------------------------------------------------------------
-constexpr int DIAG2_SMEM = (128 * 129 + 4 * 128) * 8;
+constexpr int DIAG2_SMEM = (128 * 129 + 5 * 128) * 8;
 
 // columns 16*JB .. 16*JB+15 of the factorisation (JB is compile-time so A[][] stays in registers)
 template <int JB>
-__device__ __forceinline__ void diag_factor_block(double (&A)[8][8], double* colbuf, int ty, int tx, int tid,
-                                                  int kb, int* s_bad)
+__device__ __forceinline__ void diag_factor_block(double (&A)[8][8], double* colbuf, double* rdiag, int ty, int tx,
+                                                  int tid, int kb, int* s_bad)
 {
     for (int jj = 0; jj < 16; ++jj) {
         const int j = JB * 16 + jj;
@@ -222,8 +222,10 @@ __device__ __forceinline__ void diag_factor_block(double (&A)[8][8], double* col
             if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 1;
             d = 1.0;
         }
-        const double sq = sqrt(d);
-        const double rs = 1.0 / sq;
+        // one rsqrt on the critical path instead of sqrt + divide: L_jj = d * rsqrt(d) (<= 2 ulp)
+        const double rs = rsqrt(d);
+        const double sq = d * rs;
+        if (tid == 0) rdiag[j] = rs;      // 1 / L_jj for the inversion below
         double lr[8], lc[8];
 #pragma unroll
         for (int a = JB; a < 8; ++a) lr[a] = cb[ty + 16 * a] * rs;
@@ -252,12 +254,12 @@ __device__ __forceinline__ void diag_factor_block(double (&A)[8][8], double* col
 // rows 16*JB .. 16*JB+15 of the forward substitution L X = I
 template <int JB>
 __device__ __forceinline__ void diag_invert_block(double (&X)[8][8], const double (*Ls)[129], double* rowbuf,
-                                                  int ty, int tx)
+                                                  const double* rdiag, int ty, int tx)
 {
     for (int jj = 0; jj < 16; ++jj) {
         const int j = JB * 16 + jj;
         double* rb = rowbuf + (j & 1) * 128;
-        const double inv = 1.0 / Ls[j][j];
+        const double inv = rdiag[j];
         if (ty == jj) {           // row owners finish row j of X (entries right of the diagonal are 0)
 #pragma unroll
             for (int b = 0; b <= JB; ++b) {
@@ -291,6 +293,7 @@ gpk_potrf_diag_reg_kernel(double* __restrict__ K, long ld, int kb,
     double (*Ls)[129] = (double (*)[129])dsm;
     double* colbuf = dsm + 128 * 129;     // 2 x 128
     double* rowbuf = colbuf + 256;        // 2 x 128
+    double* rdiag = rowbuf + 256;         // 128: 1 / L_jj
     __shared__ int s_bad;
 
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -308,14 +311,14 @@ gpk_potrf_diag_reg_kernel(double* __restrict__ K, long ld, int kb,
         }
 
     // ---------------- factorisation ----------------
-    diag_factor_block<0>(A, colbuf, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<1>(A, colbuf, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<2>(A, colbuf, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<3>(A, colbuf, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<4>(A, colbuf, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<5>(A, colbuf, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<6>(A, colbuf, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<7>(A, colbuf, ty, tx, tid, kb, &s_bad);
+    diag_factor_block<0>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
+    diag_factor_block<1>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
+    diag_factor_block<2>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
+    diag_factor_block<3>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
+    diag_factor_block<4>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
+    diag_factor_block<5>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
+    diag_factor_block<6>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
+    diag_factor_block<7>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
 
     // ---------------- publish L ----------------
 #pragma unroll
@@ -345,14 +348,14 @@ gpk_potrf_diag_reg_kernel(double* __restrict__ K, long ld, int kb,
     for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 8; ++b) X[a][b] = (ty + 16 * a == tx + 16 * b) ? 1.0 : 0.0;
-    diag_invert_block<0>(X, Ls, rowbuf, ty, tx);
-    diag_invert_block<1>(X, Ls, rowbuf, ty, tx);
-    diag_invert_block<2>(X, Ls, rowbuf, ty, tx);
-    diag_invert_block<3>(X, Ls, rowbuf, ty, tx);
-    diag_invert_block<4>(X, Ls, rowbuf, ty, tx);
-    diag_invert_block<5>(X, Ls, rowbuf, ty, tx);
-    diag_invert_block<6>(X, Ls, rowbuf, ty, tx);
-    diag_invert_block<7>(X, Ls, rowbuf, ty, tx);
+    diag_invert_block<0>(X, Ls, rowbuf, rdiag, ty, tx);
+    diag_invert_block<1>(X, Ls, rowbuf, rdiag, ty, tx);
+    diag_invert_block<2>(X, Ls, rowbuf, rdiag, ty, tx);
+    diag_invert_block<3>(X, Ls, rowbuf, rdiag, ty, tx);
+    diag_invert_block<4>(X, Ls, rowbuf, rdiag, ty, tx);
+    diag_invert_block<5>(X, Ls, rowbuf, rdiag, ty, tx);
+    diag_invert_block<6>(X, Ls, rowbuf, rdiag, ty, tx);
+    diag_invert_block<7>(X, Ls, rowbuf, rdiag, ty, tx);
 
     // ---------------- publish L^-1 (P lower) and its transpose (Q upper) ----------------
     __syncthreads();

@@ -306,7 +306,8 @@ def test_optimize_reaches_reference_optimum(golden_dir):
     model.train(d["X"], d["y"], do_optimize=True)
     # the optimum sits at sigma^2 ~ 1e-8 (cond(K) ~ 1e12): nll is noisy at 1e-4 relative there and
     # L-BFGS-B differentiates it numerically, so trajectories differ; the reached level must match
-    assert model.nll(model.hypers) <= float(d["nll_opt"]) * (1 + 5e-3)
+    got = model.nll(model.hypers)
+    assert got <= float(d["nll_opt"]) * 1.02 and got < 1e-3 * float(d["nll_p0"])
 
 
 def test_random_sampling_maximizer():
@@ -353,8 +354,7 @@ def test_full_size_properties():
     """BASELINE.json config 2 size (N=4096, D=16): properties that need no CPU oracle run.
       * chunking invariance (bit-identical results for different candidate chunk sizes)
       * staging invariance (TMA vs cp.async operand staging, equal to rounding; the fit is bit-identical)
-      * interpolation: the posterior mean at the training inputs reproduces K alpha + mean, i.e.
-        |mu(X) - y| is bounded by the noise level, and var(X) < noise
+      * at the training inputs y - mu(X) = diag_add * alpha (alpha = L^-T z), and var(X) < noise
       * arg-max returned by the fused kernel == numpy.argmax of the returned values
       * L^-1 consistency: ||L^-1 k*||^2 = k*^T K^-1 k* checked through var >= eps and var <= k**
     """
@@ -388,10 +388,13 @@ def test_full_size_properties():
     amp = float(np.exp(theta[0]))
     assert np.all(r1["var"] >= np.finfo(float).eps) and np.all(r1["var"] <= amp * (1 + 1e-12))
     assert np.all(r1["values"] >= 0)
-    # at the training inputs
+    # at the training inputs: mu(X) - mean = (K - diag_add I) alpha = r - diag_add alpha, i.e.
+    # y - mu(X) = diag_add * alpha with alpha = L^-T z rebuilt from the device factors
     mu_t, var_t = h.predict(X[:1024])
     assert np.all(var_t < noise) and np.all(var_t > 0)
-    assert np.max(np.abs(mu_t - y[:1024])) < 5 * np.sqrt(noise)
+    alpha = h.get_linv(N).T @ h.get_z(N)
+    resid = y[:1024] - mu_t - diag_add * alpha[:1024]
+    assert np.max(np.abs(resid)) < 1e-9 * np.abs(y).max()
     # log-likelihood identity: ll = -1/2 z^T z - 1/2 logdet - n/2 log 2pi with z from the device
     z = h.get_z(N)
     assert abs(ll - (-0.5 * z @ z - 0.5 * logdet - 0.5 * N * np.log(2 * np.pi))) <= 1e-12 * abs(ll)
