@@ -96,6 +96,14 @@ int gpk_set_kernel(gpk_handle* h, int family, double log_amp, int n_terms,
  * exactly as george does.  Returns GPK_NOT_PD where scipy.linalg.cholesky would raise. */
 int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double* loglik);
 
+/* The same in two halves, for evaluating many hyper-parameter vectors at once: gpk_fit_begin only
+ * enqueues the work on the handle's stream and returns; gpk_fit_end waits and returns the
+ * results.  With one handle per theta (each on its own stream) the latency-bound Cholesky chains
+ * of several thetas overlap on the GPU: this is how GaussianProcessMCMC.loglikelihood
+ * (gaussian_process_mcmc.py:168-202) is served for a half-ensemble of emcee walkers per step. */
+int gpk_fit_begin(gpk_handle* h, double diag_add, double mean);
+int gpk_fit_end(gpk_handle* h, double* logdet, double* loglik);
+
 /* ---- posterior + acquisition over a candidate batch -------------------------------- */
 /* Replaces george GP.predict + np.diag + clip (gaussian_process.py:276-294):
  * mu[m], var[m] (var clipped to >= DBL_EPSILON).  Xs is (m, d) row-major, raw (un-scaled). */
@@ -124,6 +132,14 @@ int gpk_acq_dev(gpk_handle* h, const void* d_Xs, long m, int acq_kind, double et
  * reference's test/dummy_model.py).  No handle state is used except the device/stream. */
 int gpk_acq_moments(gpk_handle* h, const double* mu, const double* var, long m, int acq_kind,
                     double eta, double par, double* out, long* n_negative);
+
+/* Reductions over the n_models hyper-parameter samples of a GP-MCMC model; A, B are
+ * (n_models, m) row-major host arrays.
+ *   mode 0: out1 = mean_i A_i                      MarginalizationGPMCMC.compute (marginalization.py:115-121)
+ *   mode 1: out1 = mean_i A_i, out2 = var_i(A_i) + mean_i(B_i) clipped at DBL_EPSILON
+ *                                                  GaussianProcessMCMC.predict (gaussian_process_mcmc.py:235-247) */
+int gpk_reduce_models(gpk_handle* h, const double* A, const double* B, int n_models, long m, int mode,
+                      double* out1, double* out2);
 
 /* kernel.get_value(X1, X2) (test/test_models/test_gaussian_process.py:44-46) with the
  * handle's current kernel; no input scaling.  out is (n1, n2) row-major. */

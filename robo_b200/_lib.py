@@ -35,12 +35,15 @@ _SIGNATURES = {
     "gpk_set_output_transform": [_vp, C.c_int, C.c_double, C.c_double],
     "gpk_set_kernel": [_vp, C.c_int, C.c_double, C.c_int, _ip, _ip, _dp],
     "gpk_fit": [_vp, C.c_double, C.c_double, _dp, _dp],
+    "gpk_fit_begin": [_vp, C.c_double, C.c_double],
+    "gpk_fit_end": [_vp, _dp, _dp],
     "gpk_predict": [_vp, _dp, C.c_long, _dp, _dp],
     "gpk_predict_cov": [_vp, _dp, C.c_long, _dp, _dp],
     "gpk_acq": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _lp, _lp],
     "gpk_acq_dev": [_vp, _vp, C.c_long, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp],
     "gpk_acq_moments": [_vp, _dp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _lp],
     "gpk_kernel_matrix": [_vp, _dp, C.c_long, _dp, C.c_long, C.c_int, _dp],
+    "gpk_reduce_models": [_vp, _dp, _dp, C.c_int, C.c_long, C.c_int, _dp, _dp],
     "gpk_nll_grad": [_vp, C.c_double, _dp],
     "gpk_get_factor": [_vp, _dp],
     "gpk_get_linv": [_vp, _dp],
@@ -177,6 +180,14 @@ class Handle(object):
         self._check(self.lib.gpk_fit(self._h, float(diag_add), float(mean), C.byref(logdet), C.byref(ll)))
         return logdet.value, ll.value
 
+    def fit_begin(self, diag_add, mean):
+        self._check(self.lib.gpk_fit_begin(self._h, float(diag_add), float(mean)))
+
+    def fit_end(self):
+        logdet, ll = C.c_double(), C.c_double()
+        self._check(self.lib.gpk_fit_end(self._h, C.byref(logdet), C.byref(ll)))
+        return logdet.value, ll.value
+
     # -- scoring ----------------------------------------------------------------------
     def predict(self, Xs):
         Xs = f64(Xs)
@@ -220,6 +231,25 @@ class Handle(object):
         self._check(self.lib.gpk_acq_moments(self._h, _as_dp(mu), _as_dp(var), mu.size, int(kind), float(eta),
                                              float(par), _as_dp(out), C.byref(nn)))
         return out, nn.value
+
+    def nll_grad(self, noise_var, n_terms):
+        """d(-loglik)/d[log_amp, log_metric_t..., log sigma^2] of the current fit."""
+        g = np.empty(n_terms + 2)
+        self._check(self.lib.gpk_nll_grad(self._h, float(noise_var), _as_dp(g)))
+        return g
+
+    def reduce_models(self, A, B=None):
+        """mean over models (B None) or GP-MCMC mixture moments (mean, var) (B = per-model variances)."""
+        A = f64(A)
+        n, m = A.shape
+        out1 = np.empty(m)
+        if B is None:
+            self._check(self.lib.gpk_reduce_models(self._h, _as_dp(A), None, n, m, 0, _as_dp(out1), None))
+            return out1
+        B = f64(B)
+        out2 = np.empty(m)
+        self._check(self.lib.gpk_reduce_models(self._h, _as_dp(A), _as_dp(B), n, m, 1, _as_dp(out1), _as_dp(out2)))
+        return out1, out2
 
     def kernel_matrix(self, X1, X2):
         X1, X2 = f64(X1), f64(X2)

@@ -60,6 +60,7 @@ struct gpk_handle {
 
     // job tables
     std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r;
+    Range kinv_r;
 
     // tensor maps
     CUtensorMap mapK, mapP, mapQ, mapW, mapKs, mapVt;
@@ -72,6 +73,8 @@ struct gpk_handle {
     bool fit_timed = false, score_timed = false;
     double launches_total = 0, launches_var = 0;
     long last_chunk_rows = 0;
+    double* pin = nullptr;        // pinned host: [0..1] z^T z, logdet ; [2] status (as int) for async fits
+    bool fit_pending = false;
 };
 
 namespace {
@@ -245,6 +248,13 @@ int build_job_tables(gpk_handle* h) {
         h->tri2_r[ht].off = (int)s2;
         h->tri2_r[ht].cnt = (int)(jobs.size() - s2);
     }
+    // K^-1 = Q Q^T (lower tiles), Q = L^-T upper: K^-1[i][j] = sum_{k >= i} Q[i][k] Q[j][k], i >= j
+    h->kinv_r.off = (int)jobs.size();
+    for (int j = 0; j < nb; ++j)
+        for (int i = j; i < nb; ++i)
+            jobs.push_back({i * BM, j * BM, i * BM, nb * BM, i * BM, j * BM, 0, 0});
+    std::stable_sort(jobs.begin() + h->kinv_r.off, jobs.end(), by_len);
+    h->kinv_r.cnt = (int)jobs.size() - h->kinv_r.off;
     if (jobs.empty()) jobs.push_back({0, 0, 0, 0, 0, 0, 0, 0});
     int rc = ensure(h, h->jobs, jobs.size() * sizeof(GemmJob));
     if (rc) return rc;
@@ -468,6 +478,7 @@ int gpk_create(gpk_handle** out, int device) {
     rc = ensure(h, h->status, 4);
     if (!rc) rc = ensure(h, h->scal, 64);
     if (rc) { delete h; return rc; }
+    if (cudaMallocHost((void**)&h->pin, 64) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
     if (get_encode_fn() == nullptr) h->loader = LOADER_CPASYNC;
     *out = h;
     return GPK_OK;
@@ -486,6 +497,7 @@ int gpk_destroy(gpk_handle* h) {
     if (h->ev_ok)
         for (int i = 0; i < 16; ++i) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->pin) cudaFreeHost(h->pin);
     delete h;
     return GPK_OK;
 }
@@ -625,7 +637,7 @@ int gpk_set_kernel(gpk_handle* h, int family, double log_amp, int n_terms, const
     return GPK_OK;
 }
 
-int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double* loglik) {
+int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
     int rc = require(h, true, true, false);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
@@ -686,11 +698,21 @@ int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double*
                                                     ptr<double>(h->scal));
     CKL();
     CK(cudaEventRecord(h->ev[3], h->stream));
-    double sc[2];
-    int st = 0;
-    CK(cudaMemcpyAsync(sc, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&st, h->status.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin + 2, h->status.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    h->fit_pending = true;
+    return GPK_OK;
+}
+
+int gpk_fit_end(gpk_handle* h, double* logdet, double* loglik) {
+    if (!h) return GPK_BAD_ARG;
+    if (!h->fit_pending) BAD("gpk_fit_end without gpk_fit_begin");
+    CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    h->fit_pending = false;
+    const double* sc = h->pin;
+    int st = 0;
+    memcpy(&st, h->pin + 2, 4);
     h->fit_timed = true;
     if (st != 0) {
         set_err(h, "matrix is not positive definite: pivot %d <= 0", st - 1);
@@ -702,6 +724,12 @@ int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double*
     if (loglik) *loglik = ll;
     h->fitted = true;
     return GPK_OK;
+}
+
+int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double* loglik) {
+    int rc = gpk_fit_begin(h, diag_add, mean);
+    if (rc) return rc;
+    return gpk_fit_end(h, logdet, loglik);
 }
 
 int gpk_acq_dev(gpk_handle* h, const void* d_Xs, long m, int kind, double eta, double par, void* d_out, void* d_mu,
@@ -862,6 +890,30 @@ int gpk_acq_moments(gpk_handle* h, const double* mu, const double* var, long m, 
     return GPK_OK;
 }
 
+int gpk_reduce_models(gpk_handle* h, const double* A, const double* B, int n_models, long m, int mode, double* out1,
+                      double* out2) {
+    if (!h) return GPK_BAD_ARG;
+    if (!A || !out1 || n_models <= 0 || m <= 0 || (mode != 0 && mode != 1)) BAD("gpk_reduce_models: bad arguments");
+    if (mode == 1 && (!B || !out2)) BAD("gpk_reduce_models: mode 1 needs B and out2");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    const size_t bytes = (size_t)n_models * m * 8;
+    if ((rc = ensure(h, h->tmp1, bytes))) return rc;
+    if ((rc = ensure(h, h->tmp2, mode == 1 ? bytes : 8))) return rc;
+    if ((rc = ensure(h, h->tmp3, (size_t)m * 16))) return rc;
+    CK(cudaMemcpyAsync(h->tmp1.p, A, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (mode == 1) CK(cudaMemcpyAsync(h->tmp2.p, B, bytes, cudaMemcpyHostToDevice, h->stream));
+    double* o1 = ptr<double>(h->tmp3);
+    double* o2 = o1 + m;
+    gpk_reduce_models_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(
+        ptr<double>(h->tmp1), mode == 1 ? ptr<double>(h->tmp2) : nullptr, n_models, m, mode, o1, o2);
+    CKL();
+    CK(cudaMemcpyAsync(out1, o1, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (mode == 1) CK(cudaMemcpyAsync(out2, o2, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
 int gpk_kernel_matrix(gpk_handle* h, const double* X1, long n1, const double* X2, long n2, int d, double* out) {
     int rc = require(h, false, true, false);
     if (rc) return rc;
@@ -890,9 +942,43 @@ int gpk_kernel_matrix(gpk_handle* h, const double* X1, long n1, const double* X2
 }
 
 int gpk_nll_grad(gpk_handle* h, double noise_var, double* grad) {
-    (void)noise_var; (void)grad;
-    if (!h) return GPK_BAD_ARG;
-    BAD("gpk_nll_grad: not implemented in this build");
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!grad) BAD("gpk_nll_grad: null output");
+    CK(cudaSetDevice(h->device));
+    if ((rc = build_linv(h))) return rc;
+    const long NP = h->NP;
+    const int nv = h->spec.n_terms + 2;
+    // alpha = L^-T z
+    if ((rc = ensure(h, h->alpha, (size_t)NP * 8))) return rc;
+    gpk_rowdot_kernel<<<(unsigned)((NP + 7) / 8), 256, 0, h->stream>>>(ptr<double>(h->Q), NP, NP, (int)NP, 1,
+                                                                       ptr<double>(h->Kbuf) + NP * NP,
+                                                                       ptr<double>(h->alpha));
+    CKL();
+    // K^-1 (lower tiles) into W
+    {
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = ptr<double>(h->Q); a.lda = NP;
+        a.B = ptr<double>(h->Q); a.ldb = NP;
+        a.C = ptr<double>(h->W); a.ldc = NP;
+        a.alpha = 1.0; a.beta = 0;
+        a.jobs = ptr<GemmJob>(h->jobs) + h->kinv_r.off;
+        a.job_mode = JOBS_TABLE;
+        if ((rc = launch_gemm<EPI_STORE>(h, h->mapQ, h->mapQ, a, h->kinv_r.cnt))) return rc;
+    }
+    dim3 tg((unsigned)(NP / 128), (unsigned)(NP / 32));
+    const long nblocks = (long)tg.x * tg.y;
+    if ((rc = ensure(h, h->tmp1, (size_t)nblocks * nv * 8))) return rc;
+    if ((rc = ensure(h, h->tmp2, (size_t)nv * 8))) return rc;
+    gpk_grad_trace_kernel<<<tg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->Xrow), h->d,
+                                                     ptr<double>(h->W), NP, ptr<double>(h->alpha), ptr<double>(h->tmp1));
+    CKL();
+    gpk_grad_final_kernel<<<nv, 256, 0, h->stream>>>(ptr<double>(h->tmp1), nblocks, nv, noise_var, ptr<double>(h->tmp2));
+    CKL();
+    CK(cudaMemcpyAsync(grad, h->tmp2.p, (size_t)nv * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
 }
 
 int gpk_get_factor(gpk_handle* h, double* L) {

@@ -46,6 +46,19 @@ __device__ __forceinline__ double gpk_radial_dr2(int family, double r2) {
     }
 }
 
+// d log f / d r2 (ratio f'/f in closed form: no 0/0 when f underflows)
+__device__ __forceinline__ double gpk_radial_dlog(int family, double r2) {
+    if (family == GPK_MATERN52) {
+        double r = sqrt(5.0 * r2);
+        return -(5.0 / 6.0) * (1.0 + r) / (1.0 + r + 5.0 * r2 / 3.0);
+    } else if (family == GPK_EXPSQUARED) {
+        return -0.5;
+    } else {
+        double r = sqrt(3.0 * r2);
+        return -1.5 / (1.0 + r);
+    }
+}
+
 // ---- standard normal helpers (scipy.special.ndtr / log_ndtr / norm.pdf restated) -------
 __device__ __forceinline__ double gpk_ndtr(double z) {
     return 0.5 * erfc(-z * 0.70710678118654752440);

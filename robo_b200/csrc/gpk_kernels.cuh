@@ -490,3 +490,162 @@ __global__ void gpk_cov_finish_kernel(double* __restrict__ cov, long ld, long m,
     cov[r * ld + c] = v;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Marginal-likelihood gradient, trace pass (gaussian_process.py:168-191 with the noise term
+// corrected):  d(-ll)/d theta_p = -1/2 sum_ij A_ij dK_ij/d theta_p,  A = alpha alpha^T - K^-1.
+// Same tiling as the covariance builder (128 columns j x 32 rows i per CTA, lower tiles only,
+// off-diagonal pairs counted twice); dK/d theta is recomputed on the fly and never stored
+// (the reference materialises an (N, N, H) array, :181-182).  Per CTA it writes nv = n_terms + 2
+// partial sums: [sum w k, sum_t ..., trace A]; a second kernel adds the CTAs in fixed order.
+//   dk/d log_amp      = k
+//   dk/d log_metric_t = -k * (dlog f / d r2)(r2_g) * (x_t - x'_t)^2 / metric_t      (t in group g)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gpk_grad_trace_kernel(const KSpec ks, const double* __restrict__ Xt, long ldx, int n,
+                      const double* __restrict__ Xrow, int dc,
+                      const double* __restrict__ Kinv, long ldk, const double* __restrict__ alpha,
+                      double* __restrict__ part)
+{
+    __shared__ double sc[32][GPK_MAX_TERMS + 1];
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    const int nt = ks.n_terms, nv = nt + 2;
+    const long bid = (long)blockIdx.y * gridDim.x + blockIdx.x;
+    const int j = blockIdx.x * 128 + (tid & 127);
+    const long c0 = (long)blockIdx.y * 32;
+    if ((long)blockIdx.x * 128 > c0 + 31) {                  // tile entirely above the diagonal
+        if (tid < nv) part[bid * nv + tid] = 0.0;
+        return;
+    }
+    for (int e = tid; e < 32 * nt; e += 256) {
+        int c = e / nt, t = e - c * nt;
+        long ci = c0 + c;
+        sc[c][t] = (ci < n) ? Xrow[ci * dc + ks.axis[t]] : 0.0;
+    }
+    __syncthreads();
+
+    const int cg = (tid >> 7) * 16;
+    const bool jv = j < n;
+    double gl[GPK_MAX_TERMS];                                // per-term partial sums (local memory)
+    for (int t = 0; t < nt; ++t) gl[t] = 0.0;
+    double gamp = 0.0, gtr = 0.0;
+
+    double r2[16], wk[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { r2[c] = 0.0; wk[c] = 1.0; }
+    for (int t = 0; t < nt; ++t) {                           // pass 1: k(x_i, x_j) / amp
+        const double xj = jv ? Xt[(long)ks.axis[t] * ldx + j] : 0.0;
+        const double im = ks.inv_metric[t];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            double d = sc[cg + c][t] - xj;
+            r2[c] = fma(d * d, im, r2[c]);
+        }
+        if (ks.last[t]) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { wk[c] *= gpk_radial(ks.family, r2[c]); r2[c] = 0.0; }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {                           // weights w_ij * k_ij
+        const long i = c0 + cg + c;
+        double w = 0.0;
+        if (jv && i < n && j <= i) {
+            const double a = alpha[i] * alpha[j] - Kinv[i * ldk + j];
+            if (i == j) { gtr += a; w = a; } else w = 2.0 * a;
+        }
+        wk[c] = w * ks.amp * wk[c];
+        gamp += wk[c];
+    }
+    int t0 = 0;
+    while (t0 < nt) {                                        // pass 2: group by group
+        int t1 = t0;
+        while (!ks.last[t1]) ++t1;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) r2[c] = 0.0;
+        for (int t = t0; t <= t1; ++t) {
+            const double xj = jv ? Xt[(long)ks.axis[t] * ldx + j] : 0.0;
+            const double im = ks.inv_metric[t];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double d = sc[cg + c][t] - xj;
+                r2[c] = fma(d * d, im, r2[c]);
+            }
+        }
+        double coef[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) coef[c] = -wk[c] * gpk_radial_dlog(ks.family, r2[c]);
+        for (int t = t0; t <= t1; ++t) {
+            const double xj = jv ? Xt[(long)ks.axis[t] * ldx + j] : 0.0;
+            double sacc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double d = sc[cg + c][t] - xj;
+                sacc = fma(coef[c], d * d, sacc);
+            }
+            gl[t] += sacc * ks.inv_metric[t];
+        }
+        t0 = t1 + 1;
+    }
+    // block reduction of the nv values (fixed order: lanes, then warps)
+    for (int v = 0; v < nv; ++v) {
+        double x = (v == 0) ? gamp : (v == nv - 1 ? gtr : gl[v - 1]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if ((tid & 31) == 0) red[tid >> 5] = x;
+        __syncthreads();
+        if (tid == 0) {
+            double sum = 0.0;
+            for (int w = 0; w < 8; ++w) sum += red[w];
+            part[bid * nv + v] = sum;
+        }
+        __syncthreads();
+    }
+}
+
+// out[v] = -1/2 * sum over CTAs (fixed order); the noise entry is scaled by sigma^2.
+__global__ void gpk_grad_final_kernel(const double* __restrict__ part, long nblocks, int nv, double noise_var,
+                                      double* __restrict__ out)
+{
+    const int v = blockIdx.x;
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (long b = threadIdx.x; b < nblocks; b += 256) s += part[b * nv + v];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[v] = -0.5 * sh[0] * (v == nv - 1 ? noise_var : 1.0);
+}
+
+// ---------------------------------------------------------------------------------------
+// Reductions over the hyper-parameter samples of a GP-MCMC model (A, B are [n_models][m]):
+//   mode 0: out1 = mean_i A_i                       (MarginalizationGPMCMC.compute, marginalization.py:121)
+//   mode 1: out1 = mean_i A_i ; out2 = var_i(A_i) + mean_i B_i, clipped at eps
+//           (GaussianProcessMCMC.predict, gaussian_process_mcmc.py:235-247; np.var is the
+//            two-pass population variance)
+// ---------------------------------------------------------------------------------------
+__global__ void gpk_reduce_models_kernel(const double* __restrict__ A, const double* __restrict__ B, int n_models,
+                                         long m, int mode, double* __restrict__ out1, double* __restrict__ out2)
+{
+    long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    double s = 0.0;
+    for (int i = 0; i < n_models; ++i) s += A[(long)i * m + c];
+    const double mean = s / (double)n_models;
+    out1[c] = mean;
+    if (mode == 1) {
+        double v = 0.0, sb = 0.0;
+        for (int i = 0; i < n_models; ++i) {
+            double d = A[(long)i * m + c] - mean;
+            v += d * d;
+            sb += B[(long)i * m + c];
+        }
+        double r = v / (double)n_models + sb / (double)n_models;
+        if (r < GPK_EPS) r = GPK_EPS;
+        out2[c] = r;
+    }
+}

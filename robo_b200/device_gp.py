@@ -134,6 +134,23 @@ class DeviceGP(object):
 
     lnlikelihood = log_likelihood
 
+    def grad_neg_log_likelihood(self, noise_var):
+        """d(-loglik)/d theta for theta = [kernel parameter vector ..., log sigma^2] of the current
+        factorisation (gpk_nll_grad), mapped from the device's per-term layout back onto the george
+        parameter vector (isotropic kernels sum their terms; every ConstantKernel factor receives
+        the amplitude derivative)."""
+        if not self.computed:
+            self._restore()
+        if not self.computed:
+            raise RuntimeError("You need to compute the model first")
+        f = self.kernel.flatten()
+        g = self.handle.nll_grad(noise_var, len(f["axis"]))
+        out = np.empty(len(f["slots"]) + 1)
+        for p, (kind, terms) in enumerate(f["slots"]):
+            out[p] = g[0] if kind == "amp" else sum(g[1 + t] for t in terms)
+        out[-1] = g[-1]
+        return out
+
     def predict(self, y, t, return_cov=False, return_var=True):
         self._restore()
         if return_cov:
