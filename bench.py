@@ -115,6 +115,8 @@ def run_reference(args, rank):
         return
     import threadpoolctl
     cores = os.cpu_count()
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread it can
+    threadpoolctl.threadpool_limits(limits=cores)
     fit_s, times, _ = cpu_reference_rate(args.warmup + args.steps)
     timed = times[args.warmup:]
     total = float(np.sum(timed))
@@ -269,6 +271,7 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=os.cpu_count())
         fit_s, times, _ = cpu_reference_rate(6)
         timed = times[1:]
         try:

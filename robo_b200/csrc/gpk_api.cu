@@ -36,10 +36,13 @@ struct gpk_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;     // trailing updates of the look-ahead Cholesky
+    std::vector<cudaEvent_t> ev_panel, ev_rest;
+    int lookahead = 1;
     char err[1024] = {0};
     int loader = LOADER_TMA;
     long chunk = 16384;
-    int diag_kernel = 1;          // 1 = register-tiled diagonal block kernel, 0 = simple shared-memory one
+    int diag_kernel = 2;          // 2 = fused factor+invert, 1 = register-tiled two-phase, 0 = simple shared-memory
 
     // model
     int n = 0, d = 0, NP = 0, nb = 0;
@@ -171,12 +174,14 @@ int make_map(gpk_handle* h, CUtensorMap* map, void* base, long rows, long cols, 
 
 // ---- GEMM launch ---------------------------------------------------------------------------
 template <int EPI>
-int launch_gemm(gpk_handle* h, const CUtensorMap& mA, const CUtensorMap& mB, const GemmArgs& a, int njobs) {
+int launch_gemm(gpk_handle* h, const CUtensorMap& mA, const CUtensorMap& mB, const GemmArgs& a, int njobs,
+                cudaStream_t stream = nullptr) {
     if (njobs <= 0) return GPK_OK;
+    if (stream == nullptr) stream = h->stream;
     if (h->loader == LOADER_TMA)
-        gpk_gemm_nt_kernel<EPI, LOADER_TMA><<<njobs, GEMM_THREADS, GEMM_SMEM_TMA, h->stream>>>(mA, mB, a);
+        gpk_gemm_nt_kernel<EPI, LOADER_TMA><<<njobs, GEMM_THREADS, GEMM_SMEM_TMA, stream>>>(mA, mB, a);
     else
-        gpk_gemm_nt_kernel<EPI, LOADER_CPASYNC><<<njobs, GEMM_THREADS, GEMM_SMEM_PAD, h->stream>>>(mA, mB, a);
+        gpk_gemm_nt_kernel<EPI, LOADER_CPASYNC><<<njobs, GEMM_THREADS, GEMM_SMEM_PAD, stream>>>(mA, mB, a);
     CKL();
     return GPK_OK;
 }
@@ -188,6 +193,7 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_CPASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
+    CK(cudaFuncSetAttribute(gpk_potrf_diag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
     return GPK_OK;
 }
 
@@ -468,7 +474,12 @@ int gpk_create(gpk_handle** out, int device) {
     h->device = device;
     memset(&h->spec, 0, sizeof(h->spec));
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
-    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically smallest = highest priority
+        if (cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
+        if (cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
+    }
     h->stream = h->own_stream;
     for (int i = 0; i < 16; ++i)
         if (cudaEventCreate(&h->ev[i]) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
@@ -496,6 +507,9 @@ int gpk_destroy(gpk_handle* h) {
         if (b->p) cudaFree(b->p);
     if (h->ev_ok)
         for (int i = 0; i < 16; ++i) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_rest) cudaEventDestroy(e);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->pin) cudaFreeHost(h->pin);
     delete h;
@@ -513,8 +527,13 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->mapVt_rows = 0;
         return GPK_OK;
     }
+    if (!strcmp(key, "lookahead")) {
+        if (value != 0 && value != 1) BAD("lookahead must be 0 or 1");
+        h->lookahead = (int)value;
+        return GPK_OK;
+    }
     if (!strcmp(key, "diag")) {
-        if (value != 0 && value != 1) BAD("diag must be 0 (shared-memory kernel) or 1 (register-tiled kernel)");
+        if (value < 0 || value > 2) BAD("diag must be 0 (shared-memory), 1 (register-tiled) or 2 (fused factor+invert)");
         h->diag_kernel = (int)value;
         return GPK_OK;
     }
@@ -664,8 +683,19 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
     }
     CK(cudaMemsetAsync(h->status.p, 0, 4, h->stream));
     CK(cudaEventRecord(h->ev[1], h->stream));
+    while ((int)h->ev_panel.size() < nb) {
+        cudaEvent_t e1, e2;
+        CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        h->ev_panel.push_back(e1);
+        h->ev_rest.push_back(e2);
+    }
+    std::vector<char> rest_recorded(nb, 0);
     for (int k = 0; k < nb; ++k) {
-        if (h->diag_kernel == 1)
+        if (h->diag_kernel == 2)
+            gpk_potrf_diag_fused_kernel<<<1, 256, DIAG2_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
+                                                                           ptr<int>(h->status), ptr<double>(h->logdet_part));
+        else if (h->diag_kernel == 1)
             gpk_potrf_diag_reg_kernel<<<1, 256, DIAG2_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
                                                                          ptr<int>(h->status), ptr<double>(h->logdet_part));
         else
@@ -688,10 +718,29 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         s.B = K; s.ldb = NP;
         s.C = K; s.ldc = NP;
         s.alpha = -1.0; s.beta = 1;
-        s.jobs = ptr<GemmJob>(h->jobs) + h->syrk_r[k].off;
         s.job_mode = JOBS_TABLE;
         s.status = ptr<int>(h->status);
-        if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, h->syrk_r[k].cnt))) return rc;
+        const int off = h->syrk_r[k].off, cnt = h->syrk_r[k].cnt;
+        if (!h->lookahead) {
+            s.jobs = ptr<GemmJob>(h->jobs) + off;
+            if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, cnt))) return rc;
+        } else if (cnt > 0) {
+            // Look-ahead: the first nb-k jobs update column block k+1 (what the next diagonal block
+            // and panel solve need) and stay on the critical stream; the rest of the trailing update
+            // runs on the low-priority side stream, overlapped with diag(k+1) / panel(k+1).
+            const int npu = nb - k;
+            CK(cudaEventRecord(h->ev_panel[k], h->stream));                       // panel k solved
+            if (k >= 1 && rest_recorded[k - 1]) CK(cudaStreamWaitEvent(h->stream, h->ev_rest[k - 1], 0));
+            s.jobs = ptr<GemmJob>(h->jobs) + off;
+            if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, npu))) return rc;
+            if (cnt > npu) {
+                CK(cudaStreamWaitEvent(h->side_stream, h->ev_panel[k], 0));
+                s.jobs = ptr<GemmJob>(h->jobs) + off + npu;
+                if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, cnt - npu, h->side_stream))) return rc;
+                CK(cudaEventRecord(h->ev_rest[k], h->side_stream));
+                rest_recorded[k] = 1;
+            }
+        }
     }
     CK(cudaEventRecord(h->ev[2], h->stream));
     gpk_fit_reduce_kernel<<<1, 256, 0, h->stream>>>(K + NP * NP, h->n, ptr<double>(h->logdet_part), nb,

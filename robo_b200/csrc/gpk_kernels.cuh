@@ -378,6 +378,175 @@ gpk_potrf_diag_reg_kernel(double* __restrict__ K, long ld, int kb,
 }
 
 // ---------------------------------------------------------------------------------------
+// Diagonal block, fused version: the forward substitution L X = I runs one column behind the
+// factorisation inside the SAME barrier interval (row j-1 of X and column j of A are published
+// before the one __syncthreads of step j), so the block costs 128 barrier intervals instead of 256.
+// L columns reach the substitution through registers (the scaled column every thread already
+// computed for the rank-1 update), not through shared memory.
+// ---------------------------------------------------------------------------------------
+template <int JBP>
+__device__ __forceinline__ void diag_x_publish(double (&X)[8][8], double* rb, double rs_prev, int ty, int tx, int jjp)
+{
+    if (ty == jjp) {              // owners of row jm = 16*JBP + jjp finish it: X[jm][c] *= 1/L[jm][jm]
+#pragma unroll
+        for (int b = 0; b <= JBP; ++b) {
+            const double x = X[JBP][b] * rs_prev;
+            X[JBP][b] = x;
+            rb[tx + 16 * b] = x;
+        }
+    }
+}
+
+template <int JBP>
+__device__ __forceinline__ void diag_x_update(double (&X)[8][8], const double (&lrp)[8], const double* rb,
+                                              int ty, int tx, int jjp)
+{
+    double xr[8];
+#pragma unroll
+    for (int b = 0; b <= JBP; ++b) xr[b] = rb[tx + 16 * b];
+#pragma unroll
+    for (int a = JBP; a < 8; ++a) {
+        const bool upd = (a > JBP) || (ty > jjp);                    // i > jm
+#pragma unroll
+        for (int b = 0; b <= JBP; ++b)
+            if (upd) X[a][b] = fma(-lrp[a], xr[b], X[a][b]);
+    }
+}
+
+template <int JB>
+__device__ __forceinline__ void diag_fused_block(double (&A)[8][8], double (&X)[8][8], double (&lrp)[8], double& rs_prev,
+                                                 double* colbuf, double* rowbuf, int ty, int tx, int tid, int kb,
+                                                 int* s_bad)
+{
+    for (int jj = 0; jj < 16; ++jj) {
+        const int j = JB * 16 + jj;
+        double* cb = colbuf + (j & 1) * 128;
+        double* rb = rowbuf + ((j + 1) & 1) * 128;       // parity of jm = j - 1
+        if (tx == jj) {
+#pragma unroll
+            for (int a = JB; a < 8; ++a) cb[ty + 16 * a] = A[a][JB];
+        }
+        if (jj > 0) diag_x_publish<JB>(X, rb, rs_prev, ty, tx, jj - 1);
+        else if (JB > 0) diag_x_publish<(JB > 0 ? JB - 1 : 0)>(X, rb, rs_prev, ty, tx, 15);
+        __syncthreads();
+        double d = cb[j];
+        if (!(d > 0.0) || isinf(d)) {
+            if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 1;
+            d = 1.0;
+        }
+        const double rs = rsqrt(d);
+        const double sq = d * rs;
+        double lr[8], lc[8];
+#pragma unroll
+        for (int a = JB; a < 8; ++a) lr[a] = cb[ty + 16 * a] * rs;
+#pragma unroll
+        for (int b = JB; b < 8; ++b) lc[b] = cb[tx + 16 * b] * rs;
+        if (tx == jj) {
+#pragma unroll
+            for (int a = JB; a < 8; ++a) {
+                const int i = ty + 16 * a;
+                if (i > j) A[a][JB] = lr[a];
+                else if (i == j) A[a][JB] = sq;
+            }
+        }
+        // substitution step for row jm = j - 1 (uses the column of L scaled in the previous step)
+        if (jj > 0) diag_x_update<JB>(X, lrp, rb, ty, tx, jj - 1);
+        else if (JB > 0) diag_x_update<(JB > 0 ? JB - 1 : 0)>(X, lrp, rb, ty, tx, 15);
+#pragma unroll
+        for (int b = JB; b < 8; ++b) {
+            const bool colok = (b > JB) || (tx > jj);
+#pragma unroll
+            for (int a = b; a < 8; ++a) {
+                const bool upd = colok && ((a > b) || (ty >= tx));
+                if (upd) A[a][b] = fma(-lr[a], lc[b], A[a][b]);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) lrp[a] = (a >= JB) ? lr[a] : 0.0;
+        rs_prev = rs;
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
+                            double* __restrict__ P, double* __restrict__ Q, long ldp,
+                            int* __restrict__ status, double* __restrict__ logdet_part)
+{
+    extern __shared__ double dsm[];
+    double (*Ls)[129] = (double (*)[129])dsm;
+    double* colbuf = dsm + 128 * 129;     // 2 x 128
+    double* rowbuf = colbuf + 256;        // 2 x 128
+    __shared__ int s_bad;
+
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    if (*status != 0) return;
+    if (tid == 0) s_bad = 0;
+
+    double* Kt = K + (long)kb * 128 * ld + (long)kb * 128;
+    double A[8][8], X[8][8], lrp[8];
+    double rs_prev = 1.0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        lrp[a] = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int i = ty + 16 * a, c = tx + 16 * b;
+            A[a][b] = (c <= i) ? Kt[(long)i * ld + c] : 0.0;
+            X[a][b] = (i == c) ? 1.0 : 0.0;
+        }
+    }
+    diag_fused_block<0>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<1>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<2>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<3>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<4>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<5>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<6>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<7>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    // last row of X (row 127) only needs its scaling; nobody reads the broadcast copy
+    diag_x_publish<7>(X, rowbuf, rs_prev, ty, tx, 15);
+
+    // ---------------- publish L, log-det, status ----------------
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int i = ty + 16 * a, c = tx + 16 * b;
+            const double v = (c <= i) ? A[a][b] : 0.0;
+            if (i == c) colbuf[i] = v;                     // diagonal of L for the log-det
+            Kt[(long)i * ld + c] = v;
+        }
+    __syncthreads();
+    if (tid < 32) {
+        double s = 0.0;
+        for (int q = tid; q < 128; q += 32) s += log(colbuf[q]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (tid == 0) {
+            logdet_part[kb] = s;
+            if (s_bad != 0) atomicCAS(status, 0, s_bad);
+        }
+    }
+    // ---------------- publish L^-1 (P lower) and its transpose (Q upper) ----------------
+    double* Pt = P + (long)kb * 128 * ldp + (long)kb * 128;
+    double* Qt = Q + (long)kb * 128 * ldp + (long)kb * 128;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int i = ty + 16 * a, c = tx + 16 * b;
+            const double v = (c <= i) ? X[a][b] : 0.0;
+            Ls[i][c] = v;
+            Pt[(long)i * ldp + c] = v;
+        }
+    __syncthreads();
+    for (int e = tid; e < 128 * 128; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        Qt[(long)r * ldp + c] = (c >= r) ? Ls[c][r] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Scoring epilogue: sum the per-row-block partials in fixed order, finish mean / variance,
 // apply the output transform + clip (gaussian_process.py:282-294), the acquisition closed form,
 // and a per-block arg-max with numpy.argmax tie-breaking.

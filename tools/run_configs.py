@@ -1,0 +1,149 @@
+#!/usr/bin/env python
+"""Times the other BASELINE.json configs on one GPU (C3, C4, C5 of SURVEY.md section 8d) and prints one
+JSON object per config.  Parity for these sizes is covered by tests/; this script only measures."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from robo_b200 import _lib                                   # noqa: E402
+from robo_b200 import kernels as K                           # noqa: E402
+
+TINY = 1.25e-12
+
+
+def diag_add(noise):
+    return float(np.sqrt(np.float64(np.sqrt(noise)) ** 2 + TINY) ** 2)
+
+
+def synth(N, D, M, seed=1234):
+    rng = np.random.RandomState(seed)
+    X = rng.rand(N, D)
+    y = np.sinc(X * 10 - 5).sum(axis=1) + 0.01 * rng.randn(N)
+    Xs = np.random.RandomState(4321).rand(M, D)
+    theta = np.concatenate(([0.0], np.full(D, np.log(D / 4.0))))
+    return X, y, Xs, theta, 1e-3
+
+
+def set_ard(h, theta, D):
+    f = K.Product(K.ConstantKernel(theta[0], ndim=D), K.Matern52Kernel(np.exp(theta[1:]), ndim=D)).flatten()
+    h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+
+
+def c3():
+    """batched EI over 2^20 candidates, N=1024, D=8 (one GPU's share is M/world)."""
+    N, D, M = 1024, 8, 2 ** 20
+    X, y, Xs, theta, noise = synth(N, D, M)
+    h = _lib.Handle(0)
+    h.set_data(X, y)
+    set_ard(h, theta, D)
+    h.fit(diag_add(noise), float(np.mean(y)))
+    eta = float(np.min(y))
+    h.acq(Xs[:4096], _lib.ACQ_EI, eta, 0.0, want_values=False)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=False)
+        ts.append(time.perf_counter() - t0)
+    t = h.timings()
+    return {"config": "C3 batched EI, N=1024 D=8 M=2^20, 1 GPU, host candidates (H2D included)",
+            "wall_ms": 1e3 * min(ts), "ei_per_s": M / min(ts), "device_score_ms": t["score_ms"],
+            "ei_per_s_device": M / (t["score_ms"] * 1e-3), "fit_ms": t["fit_ms"], "best_idx": r["best_idx"],
+            "roofline_tflops": M * (N * N + 2 * N) / (t["score_ms"] * 1e-3) / 1e12}
+
+
+def c4():
+    """Fabolas-shaped GP-MCMC: N=2048, 3 input columns, product of 1-D Matern-5/2, 20 theta samples."""
+    N, D, n_theta = 2048, 3, 20
+    rng = np.random.RandomState(7)
+    X = rng.rand(N, D)
+    y = np.cos(3 * X).prod(axis=1) + 0.01 * rng.randn(N)
+    thetas = np.column_stack([np.log(rng.lognormal(-2, 1, n_theta)), rng.uniform(-6, 2, (n_theta, D)),
+                              rng.uniform(-8, -3, n_theta)])
+    kern = K.ConstantKernel(0.0, ndim=D)
+    for d in range(D):
+        kern = K.Product(kern, K.Matern52Kernel(np.ones(1), ndim=D, axes=d))
+    handles = []
+    for _ in range(n_theta // 2):
+        h = _lib.Handle(0)
+        h.set_data(X, y)
+        handles.append(h)
+    mean = float(np.mean(y))
+
+    def set_theta(h, th):
+        kern.set_parameter_vector(th[:-1])
+        f = kern.flatten()
+        h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+
+    def seq(ths):
+        out = []
+        for th in ths:
+            set_theta(handles[0], th)
+            try:
+                out.append(handles[0].fit(diag_add(np.exp(th[-1])), mean)[1])
+            except np.linalg.LinAlgError:
+                out.append(-np.inf)
+        return out
+
+    def conc(ths):
+        out = []
+        for i in range(0, len(ths), len(handles)):
+            part = ths[i:i + len(handles)]
+            for h, th in zip(handles, part):
+                set_theta(h, th)
+                h.fit_begin(diag_add(np.exp(th[-1])), mean)
+            for h, th in zip(handles, part):
+                try:
+                    out.append(h.fit_end()[1])
+                except np.linalg.LinAlgError:
+                    out.append(-np.inf)
+        return out
+
+    seq(thetas[:2]); conc(thetas[:len(handles)])
+    t0 = time.perf_counter(); a = seq(thetas); t_seq = time.perf_counter() - t0
+    t0 = time.perf_counter(); b = conc(thetas); t_conc = time.perf_counter() - t0
+    assert np.allclose(a, b, rtol=1e-12, equal_nan=True)
+    sweep = np.tile(thetas, (10, 1))            # 200 likelihood evaluations = 10 emcee steps of 20 walkers
+    t0 = time.perf_counter(); conc(sweep); t_sweep = time.perf_counter() - t0
+    return {"config": "C4 GP-MCMC likelihoods, N=2048, 3 cols, prod-of-1D Matern52, 20 thetas",
+            "fits20_sequential_ms": 1e3 * t_seq, "fits20_concurrent10_ms": 1e3 * t_conc,
+            "per_fit_sequential_ms": 1e3 * t_seq / n_theta, "per_fit_concurrent_ms": 1e3 * t_conc / n_theta,
+            "sweep200_concurrent_ms": 1e3 * t_sweep, "projected_4000_factorisations_s": t_sweep * 20}
+
+
+def c5():
+    """marginal log-likelihood + gradient, N=8192, D=32 (H = 34)."""
+    N, D = 8192, 32
+    X, y, _, theta, noise = synth(N, D, 1)
+    h = _lib.Handle(0)
+    h.set_data(X, y)
+    rng = np.random.RandomState(5)
+    res = []
+    for rep in range(3):
+        th = theta + 0.1 * rng.randn(D + 1)
+        set_ard(h, th, D)
+        t0 = time.perf_counter()
+        logdet, ll = h.fit(diag_add(noise), float(np.mean(y)))
+        t1 = time.perf_counter()
+        g = h.nll_grad(noise, D)
+        t2 = time.perf_counter()
+        res.append((t1 - t0, t2 - t1, ll, float(np.linalg.norm(g))))
+    fit_ms = 1e3 * min(r[0] for r in res)
+    grad_ms = 1e3 * min(r[1] for r in res[1:])
+    flops = N ** 3 / 3 + 2 * N ** 3 / 3 + N * N * (3 * D + 40) + N * N * (6 * D + 60)
+    return {"config": "C5 nll + gradient, N=8192 D=32 (H=34)", "nll_ms": fit_ms, "grad_ms_incl_linv": 1e3 * res[0][1],
+            "grad_ms_after_first": grad_ms, "per_theta_ms": fit_ms + grad_ms, "loglik": res[-1][2],
+            "grad_norm": res[-1][3], "tflops_equiv": flops / ((fit_ms + grad_ms) * 1e-3) / 1e12,
+            "timings": h.timings()}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c3", "c4", "c5"]
+    for name in which:
+        out = {"c3": c3, "c4": c4, "c5": c5}[name]()
+        print(json.dumps(out))
+        sys.stdout.flush()
