@@ -39,6 +39,7 @@ struct gpk_handle {
     cudaStream_t side_stream = nullptr;     // trailing updates of the look-ahead Cholesky
     std::vector<cudaEvent_t> ev_panel, ev_rest;
     int lookahead = 1;
+    int smalltile = 1;              // 32-row tiles for the panel solve / next-panel update
     char err[1024] = {0};
     int loader = LOADER_TMA;
     long chunk = 16384;
@@ -62,11 +63,12 @@ struct gpk_handle {
     int jobs_nb = -1;
 
     // job tables
-    std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r;
+    std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r, trsm32_r, pu32_r;
     Range kinv_r;
 
     // tensor maps
     CUtensorMap mapK, mapP, mapQ, mapW, mapKs, mapVt;
+    CUtensorMap mapK32;            // Kbuf with a 32-row box: A operand of the small-tile chain GEMMs
     bool maps_ok = false;
     long mapKs_rows = 0, mapVt_rows = 0;
 
@@ -152,7 +154,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // fp64 row-major matrix [rows][ld]; box = 128 rows x 16 doubles (128 B), 128B swizzle.
-int make_map(gpk_handle* h, CUtensorMap* map, void* base, long rows, long cols, long ld) {
+int make_map(gpk_handle* h, CUtensorMap* map, void* base, long rows, long cols, long ld, int box_rows = BM) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_err(h, "cuTensorMapEncodeTiled entry point not available");
@@ -160,7 +162,7 @@ int make_map(gpk_handle* h, CUtensorMap* map, void* base, long rows, long cols, 
     }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -173,24 +175,26 @@ int make_map(gpk_handle* h, CUtensorMap* map, void* base, long rows, long cols, 
 }
 
 // ---- GEMM launch ---------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, int MI = 8>
 int launch_gemm(gpk_handle* h, const CUtensorMap& mA, const CUtensorMap& mB, const GemmArgs& a, int njobs,
                 cudaStream_t stream = nullptr) {
     if (njobs <= 0) return GPK_OK;
     if (stream == nullptr) stream = h->stream;
     if (h->loader == LOADER_TMA)
-        gpk_gemm_nt_kernel<EPI, LOADER_TMA><<<njobs, GEMM_THREADS, GEMM_SMEM_TMA, stream>>>(mA, mB, a);
+        gpk_gemm_nt_kernel<EPI, LOADER_TMA, MI><<<njobs, GEMM_THREADS, gemm_smem_bytes(LOADER_TMA, MI), stream>>>(mA, mB, a);
     else
-        gpk_gemm_nt_kernel<EPI, LOADER_CPASYNC><<<njobs, GEMM_THREADS, GEMM_SMEM_PAD, stream>>>(mA, mB, a);
+        gpk_gemm_nt_kernel<EPI, LOADER_CPASYNC, MI><<<njobs, GEMM_THREADS, gemm_smem_bytes(LOADER_CPASYNC, MI), stream>>>(mA, mB, a);
     CKL();
     return GPK_OK;
 }
 
 int set_kernel_attrs(gpk_handle* h) {
-    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
-    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
-    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
-    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_CPASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_TMA, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_CPASYNC, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 2)));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
@@ -226,6 +230,27 @@ int build_job_tables(gpk_handle* h) {
             for (int i = j; i <= nb; ++i)
                 jobs.push_back({i * BM, j * BM, k * BM, (k + 1) * BM, i * BM, j * BM, 0, 0});
         h->syrk_r[k].cnt = (int)jobs.size() - h->syrk_r[k].off;
+    }
+    // 32-row versions of the two GEMMs on the critical chain (row split only: the in-place panel solve
+    // stays race-free because every CTA reads and writes its own rows)
+    h->trsm32_r.assign(nb, Range());
+    h->pu32_r.assign(nb, Range());
+    for (int k = 0; k < nb; ++k) {
+        h->trsm32_r[k].off = (int)jobs.size();
+        for (int i = k + 1; i <= nb; ++i)
+            for (int q = 0; q < 4; ++q) {
+                if (i == nb && q > 0) break;         // augmented block: only its first rows are non-zero
+                jobs.push_back({i * BM + 32 * q, k * BM, k * BM, (k + 1) * BM, i * BM + 32 * q, k * BM, 0, 0});
+            }
+        h->trsm32_r[k].cnt = (int)jobs.size() - h->trsm32_r[k].off;
+        h->pu32_r[k].off = (int)jobs.size();
+        if (k + 1 < nb)
+            for (int i = k + 1; i <= nb; ++i)
+                for (int q = 0; q < 4; ++q) {
+                    if (i == nb && q > 0) break;
+                    jobs.push_back({i * BM + 32 * q, (k + 1) * BM, k * BM, (k + 1) * BM, i * BM + 32 * q, (k + 1) * BM, 0, 0});
+                }
+        h->pu32_r[k].cnt = (int)jobs.size() - h->pu32_r[k].off;
     }
     std::vector<Node> nodes;
     int hmax = build_nodes(0, nb, nodes);
@@ -275,6 +300,7 @@ int rebuild_maps(gpk_handle* h) {
     const long NP = h->NP;
     int rc;
     if ((rc = make_map(h, &h->mapK, h->Kbuf.p, NP + BM, NP, NP))) return rc;
+    if ((rc = make_map(h, &h->mapK32, h->Kbuf.p, NP + BM, NP, NP, 32))) return rc;
     if ((rc = make_map(h, &h->mapP, h->P.p, NP, NP, NP))) return rc;
     if ((rc = make_map(h, &h->mapQ, h->Q.p, NP, NP, NP))) return rc;
     if ((rc = make_map(h, &h->mapW, h->W.p, NP, NP, NP))) return rc;
@@ -527,6 +553,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->mapVt_rows = 0;
         return GPK_OK;
     }
+    if (!strcmp(key, "smalltile")) {
+        if (value != 0 && value != 1) BAD("smalltile must be 0 or 1");
+        h->smalltile = (int)value;
+        return GPK_OK;
+    }
     if (!strcmp(key, "lookahead")) {
         if (value != 0 && value != 1) BAD("lookahead must be 0 or 1");
         h->lookahead = (int)value;
@@ -708,10 +739,15 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         a.B = ptr<double>(h->P); a.ldb = NP;
         a.C = K; a.ldc = NP;
         a.alpha = 1.0; a.beta = 0;
-        a.jobs = ptr<GemmJob>(h->jobs) + h->trsm_r[k].off;
         a.job_mode = JOBS_TABLE;
         a.status = ptr<int>(h->status);
-        if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapP, a, h->trsm_r[k].cnt))) return rc;
+        if (h->smalltile) {
+            a.jobs = ptr<GemmJob>(h->jobs) + h->trsm32_r[k].off;
+            if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapP, a, h->trsm32_r[k].cnt))) return rc;
+        } else {
+            a.jobs = ptr<GemmJob>(h->jobs) + h->trsm_r[k].off;
+            if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapP, a, h->trsm_r[k].cnt))) return rc;
+        }
         GemmArgs s;
         memset(&s, 0, sizeof(s));
         s.A = K; s.lda = NP;
@@ -731,8 +767,13 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
             const int npu = nb - k;
             CK(cudaEventRecord(h->ev_panel[k], h->stream));                       // panel k solved
             if (k >= 1 && rest_recorded[k - 1]) CK(cudaStreamWaitEvent(h->stream, h->ev_rest[k - 1], 0));
-            s.jobs = ptr<GemmJob>(h->jobs) + off;
-            if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, npu))) return rc;
+            if (h->smalltile) {
+                s.jobs = ptr<GemmJob>(h->jobs) + h->pu32_r[k].off;
+                if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapK, s, h->pu32_r[k].cnt))) return rc;
+            } else {
+                s.jobs = ptr<GemmJob>(h->jobs) + off;
+                if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, npu))) return rc;
+            }
             if (cnt > npu) {
                 CK(cudaStreamWaitEvent(h->side_stream, h->ev_panel[k], 0));
                 s.jobs = ptr<GemmJob>(h->jobs) + off + npu;

@@ -23,8 +23,18 @@ constexpr int VAR_GROUP = 16;                                    // candidate bl
 constexpr int PAD_STRIDE = 20;                                   // doubles per row, cp.async mode
 constexpr int STAGE_BYTES_TMA = (BM + BN) * BK * 8;              // 32768
 constexpr int STAGE_BYTES_PAD = (BM + BN) * PAD_STRIDE * 8;      // 40960
-constexpr int GEMM_SMEM_TMA = NSTAGE * STAGE_BYTES_TMA + 1024 /*align*/ + 64 /*barriers*/ + 2048 /*reduce*/;
-constexpr int GEMM_SMEM_PAD = NSTAGE * STAGE_BYTES_PAD + 1024 + 64 + 2048;
+constexpr int CT_STRIDE = 129;                                   // doubles per row of the epilogue staging tile
+constexpr int CT_BYTES = BM * CT_STRIDE * 8;                     // 132096
+constexpr int RING_TMA = NSTAGE * STAGE_BYTES_TMA > CT_BYTES ? NSTAGE * STAGE_BYTES_TMA : ((CT_BYTES + 1023) / 1024) * 1024;
+constexpr int RING_PAD = NSTAGE * STAGE_BYTES_PAD > CT_BYTES ? NSTAGE * STAGE_BYTES_PAD : ((CT_BYTES + 1023) / 1024) * 1024;
+constexpr int GEMM_SMEM_TMA = RING_TMA + 1024 /*align*/ + 64 /*barriers*/ + 2048 /*reduce*/;
+constexpr int GEMM_SMEM_PAD = RING_PAD + 1024 + 64 + 2048;
+// Tile height is a template parameter: MI = 8 -> 128 rows (throughput tiles), MI = 2 -> 32 rows (the
+// latency-critical panel solve / next-panel update of the Cholesky chain: 4x more CTAs, 1/4 the time each).
+constexpr int gemm_smem_bytes(int loader, int mi) {
+    return mi == 8 ? (loader == LOADER_TMA ? GEMM_SMEM_TMA : GEMM_SMEM_PAD)
+                   : NSTAGE * ((16 * mi + BN) * (loader == LOADER_TMA ? BK : PAD_STRIDE) * 8) + 1024 + 64 + 2048;
+}
 
 struct GemmJob {
     int a_row;      // first row of the A tile
@@ -120,22 +130,32 @@ template <int LOADER> __device__ __forceinline__ int tile_off(int row, int k) {
 }
 
 // ---------------------------------------------------------------------------------------
-// the kernel
+// the kernel: output tile (16*MI) x 128
 // ---------------------------------------------------------------------------------------
-template <int EPI, int LOADER>
+template <int EPI, int LOADER, int MI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const GemmArgs g)
 {
     if (g.status != nullptr && *g.status != 0) return;
+    static_assert(MI == 8 || MI == 4 || MI == 2, "tile height 128, 64 or 32");
+    static_assert(EPI == EPI_STORE || MI == 8, "column-reduce epilogue uses full tiles");
+    constexpr int TM = 16 * MI;                                          // tile rows (A rows)
+    constexpr int HM = TM / 2;                                           // rows per warp row-group
 
     extern __shared__ unsigned char smem_raw[];
     // all shared-memory traffic goes through 32-bit shared-window addresses (LDS/STS, not generic LD/ST)
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024B alignment for the 128B swizzle
-    constexpr int STAGE_BYTES = LOADER == LOADER_TMA ? STAGE_BYTES_TMA : STAGE_BYTES_PAD;
-    constexpr int A_BYTES = LOADER == LOADER_TMA ? BM * BK * 8 : BM * PAD_STRIDE * 8;
-    const uint32_t full_bar = smem + NSTAGE * STAGE_BYTES;              // NSTAGE x 8 bytes
-    const uint32_t red = smem + NSTAGE * STAGE_BYTES + 64;              // 2 x 128 doubles
+    constexpr int ROWB = LOADER == LOADER_TMA ? BK * 8 : PAD_STRIDE * 8; // bytes per staged row
+    constexpr int A_BYTES = TM * ROWB;
+    constexpr int STAGE_BYTES = (TM + BN) * ROWB;
+    constexpr int RING_MIN = NSTAGE * STAGE_BYTES;
+    constexpr int CT_NEED = ((TM * CT_STRIDE * 8 + 1023) / 1024) * 1024;
+    constexpr int RING = MI == 8 ? (LOADER == LOADER_TMA ? RING_TMA : RING_PAD)
+                                 : RING_MIN;                            // (32/64-row tiles: CT tile fits the ring)
+    static_assert(RING >= CT_NEED, "epilogue staging tile must fit the operand ring");
+    const uint32_t full_bar = smem + RING;                              // NSTAGE x 8 bytes
+    const uint32_t red = smem + RING + 64;                              // 2 x 128 doubles
 
     // ---- job ----
     GemmJob job;
@@ -161,8 +181,8 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const int wm = warp >> 2, wn = warp & 3;
 
     // per-thread fragment offsets (bytes) inside a stage
-    constexpr int BLK = LOADER == LOADER_TMA ? 8 * 128 : 8 * PAD_STRIDE * 8;   // 8 tile rows
-    const int rA = wm * 64 + rowmap<LOADER>(gq);
+    constexpr int BLK = 8 * ROWB;                                        // 8 tile rows
+    const int rA = wm * HM + rowmap<LOADER>(gq);
     const int rB = wn * 32 + rowmap<LOADER>(gq);
     int kxA[4], kxB[4];
 #pragma unroll
@@ -188,26 +208,27 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (LOADER == LOADER_TMA) {
             if (tid == 0) {
                 fence_proxy_async();
-                mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES_TMA);
-                tma_load_2d(st, &mapA, kcol, job.a_row, full_bar + 8 * s);
-                tma_load_2d(st + A_BYTES, &mapB, kcol, job.b_row, full_bar + 8 * s);
+                mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+                tma_load_2d(st, &mapA, kcol, job.a_row, full_bar + 8 * s);            // box TM rows x 16
+                tma_load_2d(st + A_BYTES, &mapB, kcol, job.b_row, full_bar + 8 * s);  // box 128 rows x 16
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                int c = tid + i * GEMM_THREADS;          // 1024 16-byte chunks per operand
+                int c = tid + i * GEMM_THREADS;          // 16-byte chunks, 8 per row
                 int row = c >> 3, kc = c & 7;
-                cp_async16(st + (uint32_t)((row * PAD_STRIDE + kc * 2) * 8),
-                           g.A + (long)(job.a_row + row) * g.lda + kcol + kc * 2);
+                if (row < TM)
+                    cp_async16(st + (uint32_t)((row * PAD_STRIDE + kc * 2) * 8),
+                               g.A + (long)(job.a_row + row) * g.lda + kcol + kc * 2);
                 cp_async16(st + (uint32_t)(A_BYTES + (row * PAD_STRIDE + kc * 2) * 8),
                            g.B + (long)(job.b_row + row) * g.ldb + kcol + kc * 2);
             }
         }
     };
 
-    double acc[8][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
 
@@ -216,6 +237,21 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     for (int s = 0; s < NSTAGE - 1; ++s) {
         if (s < KT) issue_load(s);
         if (LOADER == LOADER_CPASYNC) cp_async_commit();
+    }
+    if (EPI == EPI_STORE && g.beta) {
+        // C_new = C_old + alpha * A B^T with alpha = +-1: start the accumulators at alpha * C_old; the
+        // loads overlap the pipeline fill instead of sitting in the epilogue.
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+            const long r = job.c_row + wm * HM + mi * 8 + rowmap<LOADER>(gq);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const long c = job.c_col + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j);
+                    acc[mi][ni][j] = g.alpha * g.C[r * g.ldc + c];
+                }
+        }
     }
 
     // ---- main loop ----
@@ -234,13 +270,13 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const uint32_t st = smem + s * STAGE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            double a[8], b[4];
+            double a[MI], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi) a[mi] = lds64(st + kxA[ks] + mi * BLK);
+            for (int mi = 0; mi < MI; ++mi) a[mi] = lds64(st + kxA[ks] + mi * BLK);
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) b[ni] = lds64(st + kxB[ks] + ni * BLK);
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
+            for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
@@ -248,28 +284,40 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (LOADER == LOADER_CPASYNC) cp_async_wait<0>();
 
     // ---- epilogue ----
-    // acc[mi][ni][j]  <->  tile row  wm*64 + mi*8 + rowmap(gq),  tile col  wn*32 + ni*8 + rowmap(2*tq + j)
+    // acc[mi][ni][j]  <->  tile row  wm*HM + mi*8 + rowmap(gq),  tile col  wn*32 + ni*8 + rowmap(2*tq + j)
     if (EPI == EPI_STORE) {
+        // stage the tile through shared memory (the operand ring is free now) so that the global
+        // stores of C and of its transpose are fully coalesced
+        __syncthreads();
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) {
-            const long r = job.c_row + wm * 64 + mi * 8 + rowmap<LOADER>(gq);
+        for (int mi = 0; mi < MI; ++mi) {
+            const int r = wm * HM + mi * 8 + rowmap<LOADER>(gq);
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
+            for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const long c = job.c_col + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j);
-                    double v = g.alpha * acc[mi][ni][j];
-                    if (g.beta) v += g.C[r * g.ldc + c];
-                    if (g.C) g.C[r * g.ldc + c] = v;
-                    if (g.Ct) g.Ct[c * g.ldct + r] = v;
+                    const int c = wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j);
+                    sts64(smem + 8 * (r * CT_STRIDE + c), g.alpha * acc[mi][ni][j]);
                 }
+        }
+        __syncthreads();
+        if (g.C) {
+            for (int e = tid; e < TM * BN; e += GEMM_THREADS) {
+                const int r = e >> 7, c = e & 127;
+                g.C[(long)(job.c_row + r) * g.ldc + job.c_col + c] = lds64(smem + 8 * (r * CT_STRIDE + c));
+            }
+        }
+        if (g.Ct) {
+            for (int e = tid; e < TM * BN; e += GEMM_THREADS) {
+                const int c = e / TM, r = e - c * TM;
+                g.Ct[(long)(job.c_col + c) * g.ldct + job.c_row + r] = lds64(smem + 8 * (r * CT_STRIDE + c));
             }
         }
     } else {
         // column reductions over the tile's 128 rows: sum v^2 and sum v * z[row]
-        double zr[8];
+        double zr[MI];
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) zr[mi] = g.z[job.c_row + wm * 64 + mi * 8 + rowmap<LOADER>(gq)];
+        for (int mi = 0; mi < MI; ++mi) zr[mi] = g.z[job.c_row + wm * HM + mi * 8 + rowmap<LOADER>(gq)];
         double ssq[4][2], smu[4][2];
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni)
@@ -277,7 +325,7 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             for (int j = 0; j < 2; ++j) {
                 double s2 = 0.0, sm = 0.0;
 #pragma unroll
-                for (int mi = 0; mi < 8; ++mi) {
+                for (int mi = 0; mi < MI; ++mi) {
                     double v = acc[mi][ni][j];
                     s2 = fma(v, v, s2);
                     sm = fma(v, zr[mi], sm);
