@@ -300,7 +300,11 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                      "peak_source": "datasheet FP64-tensor 37 TF/s (SURVEY 8d P64); MEASURED_PEAKS.json has no fp64 figure",
                      "dgemm_cublas_tflops": dgemm, "frac_of_cublas_dgemm": achieved / dgemm if dgemm > 0 else None,
-                     "launch_ms": gemm_ms, "launch_candidates": int(last_rows), "traffic": None},
+                     "launch_ms": gemm_ms, "launch_candidates": int(last_rows),
+                     "traffic": 1.598e9 if last_rows == 16384 else None,
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one 16384-candidate "
+                                       "launch (profiles/r01_vargemm_ncu_full_raw.csv); algorithmic minimum 0.60e9 "
+                                       "(L^-1 lower triangle 67 MB + K* 537 MB read once)"},
         "kernel_ms_last_chunk": {k: tim[k] for k in ("kstar_ms", "vargemm_ms", "finish_ms")},
         "cpu_baseline": cpu, "clocks": clocks,
     }

@@ -57,6 +57,7 @@ struct gpk_handle {
 
     // device buffers
     DevBuf Xrow, Xt, y, Kbuf, P, Q, W, lower, upper, logdet_part, scal, status, jobs;
+    DevBuf Kstar2;
     DevBuf cand, Kstar, part_mu, part_ssq, out_mu, out_var, out_acq, block_best, best, nneg;
     DevBuf Vt, cov, XsT, tmpjobs, alpha, tmp1, tmp2, tmp3;
     int layout_NP = -1;           // NP the P/Q/W buffers were zeroed for
@@ -68,12 +69,16 @@ struct gpk_handle {
 
     // tensor maps
     CUtensorMap mapK, mapP, mapQ, mapW, mapKs, mapVt;
-    CUtensorMap mapK32;            // Kbuf with a 32-row box: A operand of the small-tile chain GEMMs
+    CUtensorMap mapK32, mapKs2;
+    long mapKs2_rows = 0;
+    std::vector<cudaEvent_t> ev_cov, ev_gemm;
+    int overlap = 1;                // build K* of chunk i+1 on the side stream while chunk i contracts            // Kbuf with a 32-row box: A operand of the small-tile chain GEMMs
     bool maps_ok = false;
     long mapKs_rows = 0, mapVt_rows = 0;
 
     // timing
     cudaEvent_t ev[16];
+    cudaEvent_t ev_order = nullptr;
     bool ev_ok = false;
     bool fit_timed = false, score_timed = false;
     double launches_total = 0, launches_var = 0;
@@ -305,6 +310,7 @@ int rebuild_maps(gpk_handle* h) {
     if ((rc = make_map(h, &h->mapQ, h->Q.p, NP, NP, NP))) return rc;
     if ((rc = make_map(h, &h->mapW, h->W.p, NP, NP, NP))) return rc;
     h->mapKs_rows = 0;
+    h->mapKs2_rows = 0;
     h->mapVt_rows = 0;
     h->maps_ok = true;
     return GPK_OK;
@@ -319,6 +325,13 @@ int ensure_score_scratch(gpk_handle* h, long rows) {
     if (grew || h->mapKs_rows != rows) {
         if (h->loader == LOADER_TMA && (rc = make_map(h, &h->mapKs, h->Kstar.p, rows, NP, NP))) return rc;
         h->mapKs_rows = rows;
+    }
+    if (h->overlap) {
+        if ((rc = ensure(h, h->Kstar2, (size_t)rows * NP * 8, &grew))) return rc;
+        if (grew || h->mapKs2_rows != rows) {
+            if (h->loader == LOADER_TMA && (rc = make_map(h, &h->mapKs2, h->Kstar2.p, rows, NP, NP))) return rc;
+            h->mapKs2_rows = rows;
+        }
     }
     if ((rc = ensure(h, h->part_mu, (size_t)h->nb * rows * 8))) return rc;
     if ((rc = ensure(h, h->part_ssq, (size_t)h->nb * rows * 8))) return rc;
@@ -427,21 +440,66 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
     CK(cudaMemsetAsync(d_best, 0xFF, sizeof(BestPair), h->stream));
     CK(cudaMemsetAsync(d_nneg, 0, 8, h->stream));
     CK(cudaEventRecord(h->ev[6], h->stream));
-    for (long base = 0; base < m; base += cap) {
+    const int nchunks = (int)((m + cap - 1) / cap);
+    // With more than one chunk, K* of chunk i+1 is built on the low-priority side stream (8 candidates
+    // per thread, ~60 registers: its CTAs fit next to the resident GEMM CTAs and use the FP64 ALUs while
+    // the GEMM keeps the DMMA pipe busy); two K* buffers alternate.
+    const bool pipelined = h->overlap && nchunks > 1;
+    if (pipelined) {
+        while ((int)h->ev_cov.size() < nchunks) {
+            cudaEvent_t e1, e2;
+            CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            h->ev_cov.push_back(e1);
+            h->ev_gemm.push_back(e2);
+        }
+    }
+    auto launch_cov = [&](int ci, cudaStream_t st, bool small) -> int {
+        const long base = (long)ci * cap;
         const long mc = std::min(cap, m - base);
         const long mcp = round_up(mc, BM);
-        const bool last = base + cap >= m;
-        dim3 cg((unsigned)(NP / 128), (unsigned)(mcp / 32));
-        if (last) CK(cudaEventRecord(h->ev[8], h->stream));
-        gpk_cov_kernel<<<cg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, h->n, dX + base * h->d, h->d, mc,
-                                                  h->has_bounds ? ptr<double>(h->lower) : nullptr,
-                                                  h->has_bounds ? ptr<double>(h->upper) : nullptr,
-                                                  ptr<double>(h->Kstar), NP, 0);
+        double* dst = (pipelined && (ci & 1)) ? ptr<double>(h->Kstar2) : ptr<double>(h->Kstar);
+        const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
+        const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
+        if (small) {
+            dim3 cg((unsigned)(NP / 128), (unsigned)(mcp / 16));
+            gpk_cov_kernel<8><<<cg, 256, 0, st>>>(h->spec, ptr<double>(h->Xt), NP, h->n, dX + base * h->d, h->d, mc, lo, up,
+                                                  dst, NP, 0);
+        } else {
+            dim3 cg((unsigned)(NP / 128), (unsigned)(mcp / 32));
+            gpk_cov_kernel<16><<<cg, 256, 0, st>>>(h->spec, ptr<double>(h->Xt), NP, h->n, dX + base * h->d, h->d, mc, lo, up,
+                                                   dst, NP, 0);
+        }
         CKL();
+        return GPK_OK;
+    };
+    if (pipelined) {
+        CK(cudaEventRecord(h->ev_order, h->stream));          // side stream starts after all prior work
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_order, 0));
+        if ((rc = launch_cov(0, h->side_stream, false))) return rc;
+        CK(cudaEventRecord(h->ev_cov[0], h->side_stream));
+    }
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const long base = (long)ci * cap;
+        const long mc = std::min(cap, m - base);
+        const long mcp = round_up(mc, BM);
+        const bool last = ci == nchunks - 1;
+        if (last) CK(cudaEventRecord(h->ev[8], h->stream));
+        if (pipelined) {
+            CK(cudaStreamWaitEvent(h->stream, h->ev_cov[ci], 0));
+            if (ci + 1 < nchunks) {
+                if (ci >= 1) CK(cudaStreamWaitEvent(h->side_stream, h->ev_gemm[ci - 1], 0));   // buffer (ci+1)&1 is free
+                if ((rc = launch_cov(ci + 1, h->side_stream, true))) return rc;
+                CK(cudaEventRecord(h->ev_cov[ci + 1], h->side_stream));
+            }
+        } else {
+            if ((rc = launch_cov(ci, h->stream, false))) return rc;
+        }
+        const bool second = pipelined && (ci & 1);
         GemmArgs a;
         memset(&a, 0, sizeof(a));
         a.A = ptr<double>(h->P); a.lda = NP;
-        a.B = ptr<double>(h->Kstar); a.ldb = NP;
+        a.B = second ? ptr<double>(h->Kstar2) : ptr<double>(h->Kstar); a.ldb = NP;
         a.alpha = 1.0;
         a.job_mode = JOBS_VARIANCE;
         a.nb = h->nb; a.mcb = (int)(mcp / BN);
@@ -450,8 +508,9 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         a.part_ssq = ptr<double>(h->part_ssq);
         a.ldpart = cap;
         if (last) CK(cudaEventRecord(h->ev[10], h->stream));
-        if ((rc = launch_gemm<EPI_COLREDUCE>(h, h->mapP, h->mapKs, a, h->nb * a.mcb))) return rc;
+        if ((rc = launch_gemm<EPI_COLREDUCE>(h, h->mapP, second ? h->mapKs2 : h->mapKs, a, h->nb * a.mcb))) return rc;
         if (last) CK(cudaEventRecord(h->ev[11], h->stream));
+        if (pipelined) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
         h->launches_var += 1;
         h->last_chunk_rows = mcp;
         FinishArgs f;
@@ -510,6 +569,7 @@ int gpk_create(gpk_handle** out, int device) {
     for (int i = 0; i < 16; ++i)
         if (cudaEventCreate(&h->ev[i]) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
     h->ev_ok = true;
+    if (cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
     int rc = set_kernel_attrs(h);
     if (rc) { fprintf(stderr, "gpk_create: %s\n", h->err); delete h; return rc; }
     rc = ensure(h, h->status, 4);
@@ -526,15 +586,18 @@ int gpk_destroy(gpk_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
-                      &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->part_mu, &h->part_ssq, &h->out_mu,
+                      &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
                       &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->ev_ok)
         for (int i = 0; i < 16; ++i) cudaEventDestroy(h->ev[i]);
+    if (h->ev_order) cudaEventDestroy(h->ev_order);
     for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_rest) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_cov) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_gemm) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->pin) cudaFreeHost(h->pin);
@@ -551,6 +614,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->maps_ok = false;
         h->mapKs_rows = 0;
         h->mapVt_rows = 0;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "overlap")) {
+        if (value != 0 && value != 1) BAD("overlap must be 0 or 1");
+        h->overlap = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "smalltile")) {
@@ -705,7 +773,7 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
     CK(cudaEventRecord(h->ev[0], h->stream));
     {
         dim3 cg((unsigned)(NP / 128), (unsigned)(NP / 32));
-        gpk_cov_kernel<<<cg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->Xrow), h->d,
+        gpk_cov_kernel<16><<<cg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->Xrow), h->d,
                                                   (long)h->n, nullptr, nullptr, K, NP, 1);
         CKL();
         gpk_kfix_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, h->stream>>>(K, NP, h->n, (int)NP, diag_add,
@@ -892,7 +960,7 @@ int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double*
     const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
     const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
     // K* (mp x NP)
-    gpk_cov_kernel<<<dim3((unsigned)(NP / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
+    gpk_cov_kernel<16><<<dim3((unsigned)(NP / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
         h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->cand), h->d, m, lo, up, ptr<double>(h->Kstar), NP, 0);
     CKL();
     // K** (mp x mp): candidates against (scaled, transposed) candidates
@@ -901,7 +969,7 @@ int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double*
         gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->cand), m, h->d, lo,
                                                                                     up, ptr<double>(h->XsT), mp);
         CKL();
-        gpk_cov_kernel<<<dim3((unsigned)(mp / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
+        gpk_cov_kernel<16><<<dim3((unsigned)(mp / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
             h->spec, ptr<double>(h->XsT), mp, (int)m, ptr<double>(h->cand), h->d, m, lo, up, ptr<double>(h->cov), mp, 0);
         CKL();
     }
@@ -1022,7 +1090,7 @@ int gpk_kernel_matrix(gpk_handle* h, const double* X1, long n1, const double* X2
     long total = (long)d * n2p;
     gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(X2row, n2, d, nullptr, nullptr, X2t, n2p);
     CKL();
-    gpk_cov_kernel<<<dim3((unsigned)(n2p / 128), (unsigned)(n1p / 32)), 256, 0, h->stream>>>(
+    gpk_cov_kernel<16><<<dim3((unsigned)(n2p / 128), (unsigned)(n1p / 32)), 256, 0, h->stream>>>(
         h->spec, X2t, n2p, (int)n2, ptr<double>(h->tmp1), d, n1, nullptr, nullptr, ptr<double>(h->tmp3), n2p, 0);
     CKL();
     CK(cudaMemcpy2DAsync(out, (size_t)n2 * 8, h->tmp3.p, (size_t)n2p * 8, (size_t)n2 * 8, (size_t)n1,

@@ -11,20 +11,24 @@
 // the contractions that follow).  tri != 0: skip tiles entirely above the diagonal (K build).
 // Used for K (cand = train), K* (scoring), K** (full_cov) and kernel.get_value.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int CPT>
+__global__ void __launch_bounds__(256, CPT == 16 ? 1 : 2)
 gpk_cov_kernel(const KSpec ks, const double* __restrict__ Xt, long ldx, int n,
                const double* __restrict__ cand, int dc, long m,
                const double* __restrict__ lower, const double* __restrict__ upper,
                double* __restrict__ out, long ldo, int tri)
 {
-    __shared__ double sc[32][GPK_MAX_TERMS + 1];
+    // CPT candidates per thread: 16 (tile 128 x 32, standalone launches) or 8 (tile 128 x 16, ~60
+    // registers so that a CTA fits next to a resident variance-GEMM CTA when the two overlap)
+    constexpr int TC = 2 * CPT;
+    __shared__ double sc[TC][GPK_MAX_TERMS + 1];
     const int tid = threadIdx.x;
     const int j = blockIdx.x * 128 + (tid & 127);
-    const long c0 = (long)blockIdx.y * 32;
-    if (tri && (long)blockIdx.x * 128 > c0 + 31) return;
+    const long c0 = (long)blockIdx.y * TC;
+    if (tri && (long)blockIdx.x * 128 > c0 + TC - 1) return;
 
     const int nt = ks.n_terms;
-    for (int e = tid; e < 32 * nt; e += 256) {
+    for (int e = tid; e < TC * nt; e += 256) {
         int c = e / nt, t = e - c * nt;
         long ci = c0 + c;
         double v = 0.0;
@@ -37,26 +41,26 @@ gpk_cov_kernel(const KSpec ks, const double* __restrict__ Xt, long ldx, int n,
     }
     __syncthreads();
 
-    const int cg = (tid >> 7) * 16;
+    const int cg = (tid >> 7) * CPT;
     const bool jv = j < n;
-    double r2[16], pr[16];
+    double r2[CPT], pr[CPT];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) { r2[c] = 0.0; pr[c] = 1.0; }
+    for (int c = 0; c < CPT; ++c) { r2[c] = 0.0; pr[c] = 1.0; }
     for (int t = 0; t < nt; ++t) {
         const double xj = jv ? Xt[(long)ks.axis[t] * ldx + j] : 0.0;
         const double im = ks.inv_metric[t];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < CPT; ++c) {
             double d = sc[cg + c][t] - xj;
             r2[c] = fma(d * d, im, r2[c]);
         }
         if (ks.last[t]) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) { pr[c] *= gpk_radial(ks.family, r2[c]); r2[c] = 0.0; }
+            for (int c = 0; c < CPT; ++c) { pr[c] *= gpk_radial(ks.family, r2[c]); r2[c] = 0.0; }
         }
     }
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < CPT; ++c) {
         long ci = c0 + cg + c;
         out[ci * ldo + j] = (jv && ci < m) ? ks.amp * pr[c] : 0.0;
     }
