@@ -185,7 +185,9 @@ int launch_gemm(gpk_handle* h, const CUtensorMap& mA, const CUtensorMap& mB, con
                 cudaStream_t stream = nullptr) {
     if (njobs <= 0) return GPK_OK;
     if (stream == nullptr) stream = h->stream;
-    if (h->loader == LOADER_TMA)
+    if (h->loader == LOADER_TMA_WS && MI == 8)
+        gpk_gemm_ws_kernel<EPI><<<njobs, WS_THREADS, GEMM_SMEM_TMA, stream>>>(mA, mB, a);
+    else if (h->loader != LOADER_CPASYNC)
         gpk_gemm_nt_kernel<EPI, LOADER_TMA, MI><<<njobs, GEMM_THREADS, gemm_smem_bytes(LOADER_TMA, MI), stream>>>(mA, mB, a);
     else
         gpk_gemm_nt_kernel<EPI, LOADER_CPASYNC, MI><<<njobs, GEMM_THREADS, gemm_smem_bytes(LOADER_CPASYNC, MI), stream>>>(mA, mB, a);
@@ -198,6 +200,8 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_TMA, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_COLREDUCE, LOADER_CPASYNC, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAD));
+    CK(cudaFuncSetAttribute(gpk_gemm_ws_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
+    CK(cudaFuncSetAttribute(gpk_gemm_ws_kernel<EPI_COLREDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 2)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
@@ -301,7 +305,7 @@ int build_job_tables(gpk_handle* h) {
 }
 
 int rebuild_maps(gpk_handle* h) {
-    if (h->loader != LOADER_TMA) { h->maps_ok = true; return GPK_OK; }
+    if (h->loader == LOADER_CPASYNC) { h->maps_ok = true; return GPK_OK; }
     const long NP = h->NP;
     int rc;
     if ((rc = make_map(h, &h->mapK, h->Kbuf.p, NP + BM, NP, NP))) return rc;
@@ -323,13 +327,13 @@ int ensure_score_scratch(gpk_handle* h, long rows) {
     int rc;
     if ((rc = ensure(h, h->Kstar, (size_t)rows * NP * 8, &grew))) return rc;
     if (grew || h->mapKs_rows != rows) {
-        if (h->loader == LOADER_TMA && (rc = make_map(h, &h->mapKs, h->Kstar.p, rows, NP, NP))) return rc;
+        if (h->loader != LOADER_CPASYNC && (rc = make_map(h, &h->mapKs, h->Kstar.p, rows, NP, NP))) return rc;
         h->mapKs_rows = rows;
     }
     if (h->overlap) {
         if ((rc = ensure(h, h->Kstar2, (size_t)rows * NP * 8, &grew))) return rc;
         if (grew || h->mapKs2_rows != rows) {
-            if (h->loader == LOADER_TMA && (rc = make_map(h, &h->mapKs2, h->Kstar2.p, rows, NP, NP))) return rc;
+            if (h->loader != LOADER_CPASYNC && (rc = make_map(h, &h->mapKs2, h->Kstar2.p, rows, NP, NP))) return rc;
             h->mapKs2_rows = rows;
         }
     }
@@ -608,8 +612,8 @@ int gpk_destroy(gpk_handle* h) {
 int gpk_set_option(gpk_handle* h, const char* key, long value) {
     if (!h || !key) return GPK_BAD_ARG;
     if (!strcmp(key, "loader")) {
-        if (value != LOADER_TMA && value != LOADER_CPASYNC) BAD("loader must be 0 (cp.async) or 1 (TMA)");
-        if (value == LOADER_TMA && get_encode_fn() == nullptr) BAD("TMA descriptors unavailable on this driver");
+        if (value < LOADER_CPASYNC || value > LOADER_TMA_WS) BAD("loader must be 0 (cp.async), 1 (TMA) or 2 (TMA, warp-specialised)");
+        if (value != LOADER_CPASYNC && get_encode_fn() == nullptr) BAD("TMA descriptors unavailable on this driver");
         h->loader = (int)value;
         h->maps_ok = false;
         h->mapKs_rows = 0;
@@ -950,7 +954,7 @@ int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double*
     bool grew = false;
     if ((rc = ensure(h, h->Vt, (size_t)mp * NP * 8, &grew))) return rc;
     if (grew || h->mapVt_rows != mp) {
-        if (h->loader == LOADER_TMA && (rc = make_map(h, &h->mapVt, h->Vt.p, mp, NP, NP))) return rc;
+        if (h->loader != LOADER_CPASYNC && (rc = make_map(h, &h->mapVt, h->Vt.p, mp, NP, NP))) return rc;
         h->mapVt_rows = mp;
     }
     if ((rc = ensure(h, h->cov, (size_t)mp * mp * 8))) return rc;

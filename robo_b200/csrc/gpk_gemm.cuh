@@ -14,7 +14,7 @@
 #pragma once
 #include "gpk_internal.cuh"
 
-enum { LOADER_CPASYNC = 0, LOADER_TMA = 1 };
+enum { LOADER_CPASYNC = 0, LOADER_TMA = 1, LOADER_TMA_WS = 2 };
 enum { EPI_STORE = 0, EPI_COLREDUCE = 1 };
 enum { JOBS_TABLE = 0, JOBS_VARIANCE = 1 };
 
@@ -107,6 +107,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
                  " [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_dst), "l"((uint64_t)map), "r"(bar), "r"(c_inner), "r"(c_outer)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -358,6 +364,202 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     sts64(red + 8 * (wm * 128 + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j)), smu[ni][j]);
         }
         __syncthreads();
+        if (tid < 128)
+            g.part_mu[(long)job.aux * g.ldpart + job.c_col + tid] = lds64(red + 8 * tid) + lds64(red + 8 * (128 + tid));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp-specialised variant of the 128 x 128 tile kernel (TMA staging only): warp 8 is a dedicated
+// producer (one elected lane issues the TMA loads), warps 0-7 are DMMA consumers.  Stage hand-over
+// uses a full/empty mbarrier pair per stage instead of a block-wide __syncthreads per k-step, so
+// consumer warps never rendezvous with each other inside the main loop and may drift by up to
+// NSTAGE-1 stages.  Same fragment layout, accumulation order and epilogues as gpk_gemm_nt_kernel
+// <EPI, LOADER_TMA, 8>: results are bit-identical.
+// ---------------------------------------------------------------------------------------
+constexpr int WS_THREADS = GEMM_THREADS + 32;
+
+template <int EPI>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+gpk_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const GemmArgs g)
+{
+    if (g.status != nullptr && *g.status != 0) return;
+    constexpr int LOADER = LOADER_TMA;
+    constexpr int MI = 8, TM = 128, HM = 64;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int ROWB = BK * 8;
+    constexpr int A_BYTES = TM * ROWB;
+    constexpr int STAGE_BYTES = (TM + BN) * ROWB;
+    constexpr int RING = RING_TMA;
+    const uint32_t full_bar = smem + RING;               // NSTAGE x 8 bytes
+    const uint32_t empty_bar = smem + RING + 32;         // NSTAGE x 8 bytes
+    const uint32_t red = smem + RING + 64;
+
+    GemmJob job;
+    if (g.job_mode == JOBS_TABLE) {
+        job = g.jobs[blockIdx.x];
+    } else {
+        const int full = g.mcb / VAR_GROUP;
+        int id = (int)blockIdx.x, grp = id / (g.nb * VAR_GROUP), gsz = VAR_GROUP;
+        if (grp >= full) { grp = full; gsz = g.mcb - full * VAR_GROUP; }
+        id -= grp * g.nb * VAR_GROUP;
+        int ib = g.nb - 1 - id / gsz;
+        int cb = grp * VAR_GROUP + id % gsz;
+        job.a_row = ib * BM; job.b_row = cb * BN; job.k0 = 0; job.k1 = (ib + 1) * BM;
+        job.c_row = ib * BM; job.c_col = cb * BN; job.aux = ib; job.pad = 0;
+    }
+    const int KT = (job.k1 - job.k0) / BK;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 8); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % NSTAGE;
+                if (kt >= NSTAGE) {                      // wait until all 8 consumer warps released use (kt/NSTAGE - 1)
+                    const uint32_t parity = (uint32_t)(((kt / NSTAGE) - 1) & 1);
+                    while (!mbar_try_wait(empty_bar + 8 * s, parity)) { }
+                }
+                const uint32_t st = smem + s * STAGE_BYTES;
+                const int kcol = job.k0 + kt * BK;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+                tma_load_2d(st, &mapA, kcol, job.a_row, full_bar + 8 * s);
+                tma_load_2d(st + A_BYTES, &mapB, kcol, job.b_row, full_bar + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers (warps 0-7) ----------------
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    constexpr int BLK = 8 * ROWB;
+    const int rA = wm * HM + rowmap<LOADER>(gq);
+    const int rB = wn * 32 + rowmap<LOADER>(gq);
+    int kxA[4], kxB[4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        kxA[ks] = tile_off<LOADER>(rA, ks * 4 + tq);
+        kxB[ks] = A_BYTES + tile_off<LOADER>(rB, ks * 4 + tq);
+    }
+    double acc[MI][4][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    if (EPI == EPI_STORE && g.beta) {
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+            const long r = job.c_row + wm * HM + mi * 8 + rowmap<LOADER>(gq);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const long c = job.c_col + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j);
+                    acc[mi][ni][j] = g.alpha * g.C[r * g.ldc + c];
+                }
+        }
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % NSTAGE;
+        const uint32_t parity = (uint32_t)((kt / NSTAGE) & 1);
+        while (!mbar_try_wait(full_bar + 8 * s, parity)) { }
+        const uint32_t st = smem + s * STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            double a[MI], b[4];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) a[mi] = lds64(st + kxA[ks] + mi * BLK);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = lds64(st + kxB[ks] + ni * BLK);
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar + 8 * s);   // this warp is done reading stage s
+    }
+
+    if (EPI == EPI_STORE) {
+        named_bar_sync(1, GEMM_THREADS);                 // all consumers finished the ring
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+            const int r = wm * HM + mi * 8 + rowmap<LOADER>(gq);
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j);
+                    sts64(smem + 8 * (r * CT_STRIDE + c), g.alpha * acc[mi][ni][j]);
+                }
+        }
+        named_bar_sync(1, GEMM_THREADS);
+        if (g.C) {
+            for (int e = tid; e < TM * BN; e += GEMM_THREADS) {
+                const int r = e >> 7, c = e & 127;
+                g.C[(long)(job.c_row + r) * g.ldc + job.c_col + c] = lds64(smem + 8 * (r * CT_STRIDE + c));
+            }
+        }
+        if (g.Ct) {
+            for (int e = tid; e < TM * BN; e += GEMM_THREADS) {
+                const int c = e / TM, r = e - c * TM;
+                g.Ct[(long)(job.c_col + c) * g.ldct + job.c_row + r] = lds64(smem + 8 * (r * CT_STRIDE + c));
+            }
+        }
+    } else {
+        double zr[MI];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) zr[mi] = g.z[job.c_row + wm * HM + mi * 8 + rowmap<LOADER>(gq)];
+        double ssq[4][2], smu[4][2];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                double s2 = 0.0, sm = 0.0;
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) {
+                    double v = acc[mi][ni][j];
+                    s2 = fma(v, v, s2);
+                    sm = fma(v, zr[mi], sm);
+                }
+#pragma unroll
+                for (int off = 4; off < 32; off <<= 1) {
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+                    sm += __shfl_xor_sync(0xffffffffu, sm, off);
+                }
+                ssq[ni][j] = s2; smu[ni][j] = sm;
+            }
+        if (gq == 0) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    sts64(red + 8 * (wm * 128 + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j)), ssq[ni][j]);
+        }
+        named_bar_sync(1, GEMM_THREADS);
+        if (tid < 128)
+            g.part_ssq[(long)job.aux * g.ldpart + job.c_col + tid] = lds64(red + 8 * tid) + lds64(red + 8 * (128 + tid));
+        named_bar_sync(1, GEMM_THREADS);
+        if (gq == 0) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    sts64(red + 8 * (wm * 128 + wn * 32 + ni * 8 + rowmap<LOADER>(2 * tq + j)), smu[ni][j]);
+        }
+        named_bar_sync(1, GEMM_THREADS);
         if (tid < 128)
             g.part_mu[(long)job.aux * g.ldpart + job.c_col + tid] = lds64(red + 8 * tid) + lds64(red + 8 * (128 + tid));
     }

@@ -29,9 +29,11 @@ def _need_gpu():
         pytest.skip("no CUDA device")
 
 
-@pytest.fixture(params=["tma", "cpasync"])
+@pytest.fixture(params=["tma", "cpasync", "tma_ws"])
 def loader(request, monkeypatch):
-    monkeypatch.setenv("GPK_LOADER", "1" if request.param == "tma" else "0")
+    """operand staging of the GEMM tile engine: TMA (default), cp.async (cross-check), TMA with a
+    dedicated producer warp"""
+    monkeypatch.setenv("GPK_LOADER", {"cpasync": "0", "tma": "1", "tma_ws": "2"}[request.param])
     return request.param
 
 
@@ -430,6 +432,58 @@ def test_fmin_branin_config0():
     res = bayesian_optimization(_branin, lower, upper, num_iterations=6, n_init=3, chain_length=10, burnin_steps=10,
                                 rng=np.random.RandomState(1))
     assert len(res["y"]) == 6 and np.all(np.array(res["X"]) >= lower) and np.all(np.array(res["X"]) <= upper)
+
+
+@pytest.mark.parametrize("N,D,M", [(1, 1, 1), (2, 1, 3), (5, 64, 7), (128, 2, 129), (257, 3, 1000)])
+def test_edge_shapes(N, D, M):
+    """Smallest / ragged sizes: single training point, single candidate, D = 1 and D = GPK_MAX_TERMS,
+    N and M straddling the 128-row tile boundary."""
+    rng = np.random.RandomState(N * 1000 + D)
+    X, Xs = rng.rand(N, D), rng.rand(M, D)
+    y = np.sin(X.sum(axis=1)) + 0.5
+    theta = np.concatenate(([0.2], rng.uniform(-1.0, 1.0, D)))
+    st = O.gp_fit(oracle_kernel("matern52", theta, D), X, y, noise=1e-3, normalize_input=False)
+    mu_ref, var_ref = O.gp_predict(st, Xs)
+    from robo_b200.acquisition_functions import EI, LCB
+    from robo_b200.models.gaussian_process import GaussianProcess
+    model = GaussianProcess(product_kernel("matern52", theta, D), noise=1e-3, normalize_input=False)
+    model.train(X, y, do_optimize=False)
+    mu, var = model.predict(Xs)
+    assert mu.shape == (M,) and var.shape == (M,)
+    assert_mean_close(mu, mu_ref, np.append(y, [0.0, 1.0]))
+    assert_var_close(var, var_ref, float(np.exp(theta[0])))
+    assert_acq_close(EI(model).compute(Xs), O.acquisition(st, Xs, "ei"))
+    assert_acq_close(LCB(model).compute(Xs), O.acquisition(st, Xs, "lcb"), rtol=1e-9)
+    mu_c, cov = model.predict(Xs[:min(M, 130)], full_cov=True)
+    _, cov_ref = O.gp_predict(st, Xs[:min(M, 130)], full_cov=True)
+    assert np.max(np.abs(cov - cov_ref)) <= 1e-10 * float(np.exp(theta[0]))
+    ll_ref, _ = O.gp_loglik_terms(st)
+    assert abs(model.gp.log_likelihood(y) - ll_ref) <= 1e-10 * max(1.0, abs(ll_ref))
+
+
+def test_bad_arguments_raise_value_errors():
+    from robo_b200 import _lib
+    h = _lib.Handle(0)
+    with pytest.raises(ValueError):
+        h.set_data(np.zeros((3, 65)), np.zeros(3))                 # d > GPK_MAX_TERMS
+    with pytest.raises(ValueError):
+        h.fit(1e-3, 0.0)                                           # no data / kernel yet
+    h.set_data(np.random.rand(4, 2), np.random.rand(4))
+    with pytest.raises(ValueError):
+        h.set_kernel(7, 0.0, [0, 1], [0, 0], [0.0, 0.0])            # unknown family
+    with pytest.raises(ValueError):
+        h.set_kernel(0, 0.0, [0, 1], [1, 1], [0.0, 0.0])            # groups must start at 0
+    h.set_kernel(0, 0.0, [0, 5], [0, 0], [0.0, 0.0])
+    with pytest.raises(ValueError):
+        h.fit(1e-3, 0.0)                                           # kernel axis >= d
+    h.set_kernel(0, 0.0, [0, 1], [0, 0], [0.0, 0.0])
+    with pytest.raises(RuntimeError):
+        h.predict(np.random.rand(3, 2))                            # not fitted
+    h.fit(1e-3, 0.0)
+    with pytest.raises(ValueError):
+        h.set_option("chunk", 100)
+    with pytest.raises(ValueError):
+        h.set_option("nonsense", 1)
 
 
 # --------------------------------------------------------------------------- larger sizes
