@@ -58,9 +58,15 @@ int gpk_create(gpk_handle** h, int device);
 int gpk_destroy(gpk_handle* h);
 const char* gpk_last_error(gpk_handle* h);
 const char* gpk_version(void);
-/* key in {"loader" (0 = cp.async staging, 1 = TMA staging [default]), "chunk" (candidates per
- * scoring pass, multiple of 128), "diag" (diagonal-block Cholesky kernel: 1 = register-tiled
- * [default], 0 = simple shared-memory version kept as a cross-check)} */
+/* key in
+ *   "loader"    operand staging of the GEMM tile engine: 2 = TMA with a dedicated producer warp and
+ *               full/empty mbarriers [default], 1 = TMA issued by a consumer thread, 0 = cp.async (cross-check)
+ *   "chunk"     candidates per scoring pass (multiple of 128, default 16384)
+ *   "diag"      diagonal-block Cholesky kernel: 2 = fused factor + invert [default], 1 = two-phase
+ *               register-tiled, 0 = simple shared-memory version (cross-check)
+ *   "lookahead" 1 = trailing updates on a side stream, overlapped with the next diag/panel [default]
+ *   "smalltile" 1 = 32-row tiles for the panel solve / next-panel update [default]
+ *   "overlap"   1 = build K* of chunk i+1 on the side stream while chunk i contracts [default] */
 int gpk_set_option(gpk_handle* h, const char* key, long value);
 /* run on an existing CUDA stream (cudaStream_t passed as void*); NULL = the handle's own */
 int gpk_set_stream(gpk_handle* h, void* cuda_stream);

@@ -41,7 +41,7 @@ struct gpk_handle {
     int lookahead = 1;
     int smalltile = 1;              // 32-row tiles for the panel solve / next-panel update
     char err[1024] = {0};
-    int loader = LOADER_TMA;
+    int loader = LOADER_TMA_WS;
     long chunk = 16384;
     int diag_kernel = 2;          // 2 = fused factor+invert, 1 = register-tiled two-phase, 0 = simple shared-memory
 

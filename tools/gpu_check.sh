@@ -16,7 +16,7 @@ fi
 if [[ $what == ncu || $what == all ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 3 --m 16384 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:ILi1ELi1 -s 2 -c 1 \
+  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:gpk_gemm_ws_kernelILi1E -s 2 -c 1 \
       -f -o gpurun_out/prof_vargemm python bench.py --steps 1 --warmup 3 --m 16384 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
   tail -3 gpurun_out/ncu_full.log
 fi
