@@ -133,6 +133,23 @@ int gpk_acq(gpk_handle* h, const double* Xs, long m, int acq_kind, double eta, d
 int gpk_acq_dev(gpk_handle* h, const void* d_Xs, long m, int acq_kind, double eta, double par,
                 void* d_out, void* d_mu, void* d_var, void* d_best);
 
+/* RandomSampling.maximize with the candidates generated on the device
+ * (robo/maximizers/random_sampling.py:38-50).  Candidate i (global index) is
+ *   i < n_uniform : lower + (upper - lower) * U[0,1)^d
+ *   otherwise     : clip(incumbent + scale * N(0,1)^d, lower, upper)
+ * from Philox4x32-10 keyed by (seed, i, coordinate pair): independent of chunking and of how the range
+ * [first, first+count) is split over GPUs.  Returns the best candidate of the range (numpy.argmax
+ * tie-breaking), its acquisition value and its GLOBAL index; no candidate or value crosses PCIe. */
+int gpk_maximize_random(gpk_handle* h, unsigned long long seed, long first, long count, long n_uniform,
+                        const double* lower, const double* upper, const double* incumbent, double scale,
+                        int acq_kind, double eta, double par,
+                        double* best_x, double* best_val, long* best_idx);
+/* the same generator, candidates copied to the host (out: count x d row-major); tests and re-creating
+ * the winning point on another rank */
+int gpk_generate_candidates(gpk_handle* h, unsigned long long seed, long first, long count, long n_uniform, int d,
+                            const double* lower, const double* upper, const double* incumbent, double scale,
+                            double* out);
+
 /* Acquisition closed forms on caller-supplied moments (host arrays), evaluated by the same
  * device function as the fused path.  Serves models that are not GPU GPs (e.g. the
  * reference's test/dummy_model.py).  No handle state is used except the device/stream. */

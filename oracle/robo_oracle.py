@@ -314,3 +314,49 @@ def make_kernel(kind, D, theta):
     cls = {"matern52": G.Matern52Kernel, "rbf": G.ExpSquaredKernel}[kind]
     k = G.Product(G.ConstantKernel(theta[0], ndim=D), cls(np.exp(theta[1:]), ndim=D))
     return k
+
+
+# --------------------------------------------------------------------------- #
+# counter-based candidate generator (checker for gpk_generate_candidates)
+# --------------------------------------------------------------------------- #
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11; Random123 constants), vectorised over numpy uint32 arrays."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for c in (c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0 & 0xFFFFFFFF), np.uint64(k1 & 0xFFFFFFFF)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & mask, lo1, (hi0 ^ c3 ^ k1) & mask, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c0, c1, c2, c3
+
+
+def generate_candidates(seed, first, count, n_uniform, lower, upper, incumbent, scale):
+    """Restatement of gpk_candidates_kernel: random_sampling.py:38-47 with a counter-based stream."""
+    lower, upper, incumbent = [np.asarray(a, dtype=np.float64) for a in (lower, upper, incumbent)]
+    d = lower.size
+    npair = (d + 1) // 2
+    gi = (np.arange(count, dtype=np.uint64) + np.uint64(first))[:, None] + np.zeros((1, npair), dtype=np.uint64)
+    pb = np.zeros((count, 1), dtype=np.uint64) + np.arange(npair, dtype=np.uint64)[None, :]
+    r0, r1, r2, r3 = philox4x32_10(gi & np.uint64(0xFFFFFFFF), gi >> np.uint64(32), pb, np.zeros_like(pb),
+                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u0 = ((r1 << np.uint64(32) | r0) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    u1 = ((r3 << np.uint64(32) | r2) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    out = np.empty((count, 2 * npair))
+    uni = (gi[:, 0] < np.uint64(n_uniform))
+    lo2 = np.concatenate((lower, [0.0] * (2 * npair - d)))
+    up2 = np.concatenate((upper, [1.0] * (2 * npair - d)))
+    inc2 = np.concatenate((incumbent, [0.0] * (2 * npair - d)))
+    a0, a1 = np.arange(0, 2 * npair, 2), np.arange(1, 2 * npair, 2)
+    out[:, a0] = lo2[a0] + (up2[a0] - lo2[a0]) * u0
+    out[:, a1] = lo2[a1] + (up2[a1] - lo2[a1]) * u1
+    rad = np.sqrt(-2.0 * np.log(1.0 - u0))
+    g0 = np.clip(inc2[a0] + scale * rad * np.cos(2 * np.pi * u1), lo2[a0], up2[a0])
+    g1 = np.clip(inc2[a1] + scale * rad * np.sin(2 * np.pi * u1), lo2[a1], up2[a1])
+    res = out.copy()
+    res[np.ix_(~uni, a0)] = g0[~uni]
+    res[np.ix_(~uni, a1)] = g1[~uni]
+    return res[:, :d]

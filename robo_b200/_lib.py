@@ -41,6 +41,9 @@ _SIGNATURES = {
     "gpk_predict_cov": [_vp, _dp, C.c_long, _dp, _dp],
     "gpk_acq": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _lp, _lp],
     "gpk_acq_dev": [_vp, _vp, C.c_long, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp],
+    "gpk_maximize_random": [_vp, C.c_ulonglong, C.c_long, C.c_long, C.c_long, _dp, _dp, _dp, C.c_double, C.c_int,
+                            C.c_double, C.c_double, _dp, _dp, _lp],
+    "gpk_generate_candidates": [_vp, C.c_ulonglong, C.c_long, C.c_long, C.c_long, C.c_int, _dp, _dp, _dp, C.c_double, _dp],
     "gpk_acq_moments": [_vp, _dp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _lp],
     "gpk_kernel_matrix": [_vp, _dp, C.c_long, _dp, C.c_long, C.c_int, _dp],
     "gpk_reduce_models": [_vp, _dp, _dp, C.c_int, C.c_long, C.c_int, _dp, _dp],
@@ -223,6 +226,23 @@ class Handle(object):
         self._check(self.lib.gpk_acq_dev(self._h, _vp(d_Xs_ptr), int(m), int(kind), float(eta), float(par),
                                          _vp(d_out_ptr or 0), _vp(d_mu_ptr or 0), _vp(d_var_ptr or 0),
                                          _vp(d_best_ptr or 0)))
+
+    def maximize_random(self, seed, first, count, n_uniform, lower, upper, incumbent, scale, kind, eta=0.0, par=0.0):
+        """-> (best_x (d,), best_val, best_global_idx) over device-generated candidates [first, first+count)."""
+        lo, up, inc = f64(lower).ravel(), f64(upper).ravel(), f64(incumbent).ravel()
+        bx = np.empty(lo.size)
+        bv, bi = C.c_double(), C.c_long(-1)
+        self._check(self.lib.gpk_maximize_random(self._h, int(seed), int(first), int(count), int(n_uniform), _as_dp(lo),
+                                                 _as_dp(up), _as_dp(inc), float(scale), int(kind), float(eta), float(par),
+                                                 _as_dp(bx), C.byref(bv), C.byref(bi)))
+        return bx, bv.value, bi.value
+
+    def generate_candidates(self, seed, first, count, n_uniform, lower, upper, incumbent, scale):
+        lo, up, inc = f64(lower).ravel(), f64(upper).ravel(), f64(incumbent).ravel()
+        out = np.empty((count, lo.size))
+        self._check(self.lib.gpk_generate_candidates(self._h, int(seed), int(first), int(count), int(n_uniform), lo.size,
+                                                     _as_dp(lo), _as_dp(up), _as_dp(inc), float(scale), _as_dp(out)))
+        return out
 
     def acq_moments(self, mu, var, kind, eta=0.0, par=0.0):
         mu, var = f64(mu).ravel(), f64(var).ravel()

@@ -936,6 +936,58 @@ int gpk_acq(gpk_handle* h, const double* Xs, long m, int kind, double eta, doubl
     return GPK_OK;
 }
 
+// candidates [first, first+count) of the device generator into h->cand (device, count x d)
+static int generate_candidates(gpk_handle* h, unsigned long long seed, long first, long count, long n_uniform, int d,
+                               const double* lower, const double* upper, const double* incumbent, double scale) {
+    int rc;
+    if ((rc = ensure(h, h->cand, (size_t)count * d * 8))) return rc;
+    if ((rc = ensure(h, h->tmp1, (size_t)3 * d * 8))) return rc;
+    double* dl = ptr<double>(h->tmp1);
+    CK(cudaMemcpyAsync(dl, lower, (size_t)d * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dl + d, upper, (size_t)d * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dl + 2 * d, incumbent, (size_t)d * 8, cudaMemcpyHostToDevice, h->stream));
+    const long total = count * ((d + 1) / 2);
+    gpk_candidates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(seed, first, count, n_uniform, d, dl, dl + d,
+                                                                              dl + 2 * d, scale, ptr<double>(h->cand));
+    CKL();
+    return GPK_OK;
+}
+
+int gpk_generate_candidates(gpk_handle* h, unsigned long long seed, long first, long count, long n_uniform, int d,
+                            const double* lower, const double* upper, const double* incumbent, double scale,
+                            double* out) {
+    if (!h) return GPK_BAD_ARG;
+    if (!lower || !upper || !incumbent || !out || count <= 0 || d <= 0 || d > GPK_MAX_TERMS || first < 0)
+        BAD("gpk_generate_candidates: bad arguments");
+    CK(cudaSetDevice(h->device));
+    int rc = generate_candidates(h, seed, first, count, n_uniform, d, lower, upper, incumbent, scale);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, h->cand.p, (size_t)count * d * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_maximize_random(gpk_handle* h, unsigned long long seed, long first, long count, long n_uniform,
+                        const double* lower, const double* upper, const double* incumbent, double scale, int kind,
+                        double eta, double par, double* best_x, double* best_val, long* best_idx) {
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!lower || !upper || !incumbent || count <= 0 || first < 0) BAD("gpk_maximize_random: bad arguments");
+    if (kind < GPK_ACQ_EI || kind > GPK_ACQ_LCB) BAD("gpk_maximize_random: unknown acquisition %d", kind);
+    CK(cudaSetDevice(h->device));
+    if ((rc = generate_candidates(h, seed, first, count, n_uniform, h->d, lower, upper, incumbent, scale))) return rc;
+    if ((rc = score_dev(h, ptr<double>(h->cand), count, kind, eta, par, nullptr, nullptr, nullptr, nullptr, nullptr)))
+        return rc;
+    BestPair bp;
+    CK(cudaMemcpyAsync(&bp, h->best.p, sizeof(bp), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (bp.idx >= 0 && best_x)
+        CK(cudaMemcpy(best_x, ptr<double>(h->cand) + bp.idx * h->d, (size_t)h->d * 8, cudaMemcpyDeviceToHost));
+    if (best_val) *best_val = bp.val;
+    if (best_idx) *best_idx = bp.idx >= 0 ? (long)(first + bp.idx) : -1;
+    return GPK_OK;
+}
+
 int gpk_predict(gpk_handle* h, const double* Xs, long m, double* mu, double* var) {
     return gpk_acq(h, Xs, m, GPK_ACQ_NONE, 0.0, 0.0, nullptr, mu, var, nullptr, nullptr, nullptr);
 }

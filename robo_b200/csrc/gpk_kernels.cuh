@@ -822,3 +822,60 @@ __global__ void gpk_reduce_models_kernel(const double* __restrict__ A, const dou
         out2[c] = r;
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// On-device candidate generation for RandomSampling.maximize (random_sampling.py:38-47):
+//   candidate i < n_uniform : lower + (upper - lower) * U[0,1)^d          (init_random_uniform)
+//   otherwise               : clip(incumbent + scale * N(0,1)^d, lower, upper)
+// Philox4x32-10 counter-based generator keyed by (seed, global candidate index, coordinate pair):
+// the stream depends on nothing else, so results are identical for any chunking or GPU count.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void gpk_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double gpk_u01(uint32_t lo, uint32_t hi) {      // 53-bit uniform in [0, 1)
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return (double)(v >> 11) * 1.1102230246251565e-16;
+}
+
+__global__ void gpk_candidates_kernel(unsigned long long seed, long first, long count, long n_uniform, int d,
+                                      const double* __restrict__ lower, const double* __restrict__ upper,
+                                      const double* __restrict__ incumbent, double scale,
+                                      double* __restrict__ out)
+{
+    const int npair = (d + 1) / 2;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * npair) return;
+    const long li = t / npair;
+    const int pb = (int)(t - li * npair);
+    const unsigned long long gi = (unsigned long long)(first + li);
+    uint32_t r[4];
+    gpk_philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)pb, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u0 = gpk_u01(r[0], r[1]), u1 = gpk_u01(r[2], r[3]);
+    double v0, v1;
+    const int a0 = 2 * pb, a1 = 2 * pb + 1;
+    if ((long)gi < n_uniform) {
+        // explicit rounding steps (no fma contraction): bit-identical to numpy's lower + (upper-lower)*u
+        v0 = __dadd_rn(lower[a0], __dmul_rn(upper[a0] - lower[a0], u0));
+        if (a1 < d) v1 = __dadd_rn(lower[a1], __dmul_rn(upper[a1] - lower[a1], u1));
+    } else {                                              // Box-Muller, u in (0, 1]
+        const double rad = sqrt(-2.0 * log(1.0 - u0));
+        double sn, cs;
+        sincospi(2.0 * u1, &sn, &cs);
+        v0 = fmin(fmax(incumbent[a0] + scale * rad * cs, lower[a0]), upper[a0]);
+        if (a1 < d) v1 = fmin(fmax(incumbent[a1] + scale * rad * sn, lower[a1]), upper[a1]);
+    }
+    out[li * d + a0] = v0;
+    if (a1 < d) out[li * d + a1] = v1;
+}

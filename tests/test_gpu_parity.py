@@ -486,6 +486,57 @@ def test_bad_arguments_raise_value_errors():
         h.set_option("nonsense", 1)
 
 
+def test_device_candidate_generation_and_fused_maximize():
+    """gpk_generate_candidates against the oracle's Philox4x32-10 restatement (uniform part bit-exact,
+    Gaussian part to rounding), independence of the split into ranges, and the fused maximizer
+    returning exactly the arg-max of the acquisition over those candidates."""
+    from robo_b200 import _lib
+    from robo_b200.acquisition_functions import EI
+    from robo_b200.maximizers import DeviceRandomSampling
+    d, _ = load_case("gp_branin_ny0")
+    family, theta = kernel_spec("gp_branin_ny0")
+    model = product_model(d, family, theta)
+    model.train(d["X"], d["y"], do_optimize=False)
+    h = model.gp.handle
+    lower, upper = d["lower"], d["upper"]
+    inc = model.get_incumbent()[0]
+    seed, M = 0x1234567890ABCDEF, 5000
+    nu = int(M * .7)
+    got = h.generate_candidates(seed, 0, M, nu, lower, upper, inc, 0.1)
+    ref = O.generate_candidates(seed, 0, M, nu, lower, upper, inc, 0.1)
+    np.testing.assert_array_equal(got[:nu], ref[:nu])                       # integer + one fma-free affine map
+    np.testing.assert_allclose(got[nu:], ref[nu:], rtol=0, atol=1e-13)
+    assert np.all(got >= lower) and np.all(got <= upper)
+    # statistics of the proposal (random_sampling.py:38-47)
+    u = (got[:nu] - lower) / (upper - lower)
+    assert abs(u.mean() - 0.5) < 0.02 and abs(u.var() - 1 / 12.0) < 0.01
+    # any split of the index range reproduces the same candidates
+    part = np.vstack([h.generate_candidates(seed, 0, 1234, nu, lower, upper, inc, 0.1),
+                      h.generate_candidates(seed, 1234, M - 1234, nu, lower, upper, inc, 0.1)])
+    np.testing.assert_array_equal(part, got)
+    # fused maximise == argmax of EI over exactly these candidates
+    acq = EI(model)
+    vals = acq.compute(got)
+    x, val, idx = h.maximize_random(seed, 0, M, nu, lower, upper, inc, 0.1, _lib.ACQ_EI, float(model.get_incumbent()[1]), 0.0)
+    assert idx == int(np.argmax(vals)) and val == vals[idx]
+    np.testing.assert_array_equal(x, got[idx])
+    # sharded ranges (what each rank of a multi-GPU run does) merge to the same winner
+    from robo_b200.distributed import merge_best, shard_bounds
+    pairs = []
+    for r in range(3):
+        lo, hi = shard_bounds(M, r, 3)
+        _, v, i = h.maximize_random(seed, lo, hi - lo, nu, lower, upper, inc, 0.1, _lib.ACQ_EI,
+                                    float(model.get_incumbent()[1]), 0.0)
+        pairs.append((v, i))
+    assert merge_best([p[0] for p in pairs], [p[1] for p in pairs])[1] == idx
+    # the maximizer class
+    mx = DeviceRandomSampling(acq, lower, upper, n_samples=2000, rng=np.random.RandomState(3))
+    x1 = mx.maximize()
+    assert x1.shape == (2,) and np.all(x1 >= lower) and np.all(x1 <= upper)
+    cand = h.generate_candidates(mx.last["seed"], 0, 2000, 1400, lower, upper, inc, 0.1)
+    assert mx.last["best_idx"] == int(np.argmax(acq.compute(cand)))
+
+
 # --------------------------------------------------------------------------- larger sizes
 @pytest.mark.parametrize("N,D,M,family", [(1000, 8, 3000, "matern52"), (1536, 16, 1000, "rbf")])
 def test_mid_size_against_oracle(N, D, M, family, loader, monkeypatch):

@@ -67,3 +67,17 @@ def test_var_only_matches_full_cov_path():
     m2, v2 = O.gp_predict_var_only(st, Xs)
     np.testing.assert_allclose(m1, m2, rtol=1e-12)
     np.testing.assert_allclose(v1, v2, rtol=1e-9)
+
+
+def test_philox_known_answer_vectors():
+    """Random123 kat_vectors for philox4x32-10: pins the checker of the device candidate generator."""
+    r = O.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(x[0]) for x in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    r = O.philox4x32_10([f], [f], [f], [f], f, f)
+    assert [int(x[0]) for x in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = O.philox4x32_10([0x243f6a88], [0x85a308d3], [0x13198a2e], [0x03707344], 0xa4093822, 0x299f31d0)
+    assert [int(x[0]) for x in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    c = O.generate_candidates(5, 0, 1000, 700, np.array([-5.0, 0, 1]), np.array([10.0, 15, 2]), np.array([0.0, 1, 1.5]), 0.1)
+    assert c.shape == (1000, 3) and np.all(c >= [-5, 0, 1]) and np.all(c <= [10, 15, 2])
+    assert abs(c[700:, 0].std() - 0.1) < 0.02
