@@ -133,6 +133,14 @@ int gpk_acq(gpk_handle* h, const double* Xs, long m, int acq_kind, double eta, d
 int gpk_acq_dev(gpk_handle* h, const void* d_Xs, long m, int acq_kind, double eta, double par,
                 void* d_out, void* d_mu, void* d_var, void* d_best);
 
+/* Predictive gradients and acquisition gradients.  The reference's
+ * acquisition functions call model.predictive_gradients when derivative=True (ei.py:80-85, pi.py:65-71,
+ * lcb.py:66-69) but none of its models implements it.  Xs: (m, d) raw inputs; mu, var: (m); dmu, dvar:
+ * (m, d) = d mu / d x, d var / d x (chain rules of the input scaling and output transform included).
+ * acq_kind = GPK_ACQ_NONE, or EI / PI / LCB to also get f (m) and df (m, d) = d acquisition / d x. */
+int gpk_predict_grad(gpk_handle* h, const double* Xs, long m, int acq_kind, double eta, double par,
+                     double* mu, double* var, double* dmu, double* dvar, double* f, double* df);
+
 /* RandomSampling.maximize with the candidates generated on the device
  * (robo/maximizers/random_sampling.py:38-50).  Candidate i (global index) is
  *   i < n_uniform : lower + (upper - lower) * U[0,1)^d

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "gpk_predict_cov": [_vp, _dp, C.c_long, _dp, _dp],
     "gpk_acq": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _lp, _lp],
     "gpk_acq_dev": [_vp, _vp, C.c_long, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp],
+    "gpk_predict_grad": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp],
     "gpk_maximize_random": [_vp, C.c_ulonglong, C.c_long, C.c_long, C.c_long, _dp, _dp, _dp, C.c_double, C.c_int,
                             C.c_double, C.c_double, _dp, _dp, _lp],
     "gpk_generate_candidates": [_vp, C.c_ulonglong, C.c_long, C.c_long, C.c_long, C.c_int, _dp, _dp, _dp, C.c_double, _dp],
@@ -226,6 +227,19 @@ class Handle(object):
         self._check(self.lib.gpk_acq_dev(self._h, _vp(d_Xs_ptr), int(m), int(kind), float(eta), float(par),
                                          _vp(d_out_ptr or 0), _vp(d_mu_ptr or 0), _vp(d_var_ptr or 0),
                                          _vp(d_best_ptr or 0)))
+
+    def predict_grad(self, Xs, kind=ACQ_NONE, eta=0.0, par=0.0):
+        """-> dict(mu, var, dmu (m,d), dvar (m,d)[, f, df]) — moments and their input gradients."""
+        Xs = f64(Xs)
+        m, d = Xs.shape
+        mu, var, dmu, dvar = np.empty(m), np.empty(m), np.empty((m, d)), np.empty((m, d))
+        f = np.empty(m) if kind != ACQ_NONE else None
+        df = np.empty((m, d)) if kind != ACQ_NONE else None
+        self._check(self.lib.gpk_predict_grad(self._h, _as_dp(Xs), m, int(kind), float(eta), float(par), _as_dp(mu),
+                                              _as_dp(var), _as_dp(dmu), _as_dp(dvar),
+                                              _as_dp(f) if f is not None else None,
+                                              _as_dp(df) if df is not None else None))
+        return dict(mu=mu, var=var, dmu=dmu, dvar=dvar, f=f, df=df)
 
     def maximize_random(self, seed, first, count, n_uniform, lower, upper, incumbent, scale, kind, eta=0.0, par=0.0):
         """-> (best_x (d,), best_val, best_global_idx) over device-generated candidates [first, first+count)."""

@@ -20,8 +20,11 @@ class EI(BaseAcquisitionFunction):
         Keeps the reference's quirks: a zero predictive std anywhere zeroes the whole batch
         (ei.py:72-74); any negative value raises ValueError (ei.py:86-88)."""
         if derivative:
-            # ei.py:80-85 needs model.predictive_gradients, which no RoBO model implements
-            raise NotImplementedError("derivative=True needs model.predictive_gradients")
+            # ei.py:80-85: df = -dm Phi(z) + ds phi(z); the reference needs model.predictive_gradients,
+            # which none of its models implements — the robo_b200 GaussianProcess does (on the device)
+            if not hasattr(self.model, "score_with_gradient"):
+                raise NotImplementedError("derivative=True needs a model with predictive gradients")
+            return self.model.score_with_gradient(np.asarray(X, dtype=np.float64), "ei", eta=eta, par=self.par)
         if not hasattr(self.model, "score"):
             m, v = self.model.predict(X)
             if (np.sqrt(v) == 0).any():

@@ -12,5 +12,8 @@ class LCB(BaseAcquisitionFunction):
     def compute(self, X, derivative=False, **kwargs):
         """-(m - par sqrt(v)) (lcb.py:62-65); RoBO maximises, so the bound is negated."""
         if derivative:
-            raise NotImplementedError("derivative=True needs model.predictive_gradients")
+            if not hasattr(self.model, "score_with_gradient"):
+                raise NotImplementedError("derivative=True needs a model with predictive gradients")
+            import numpy as np
+            return self.model.score_with_gradient(np.asarray(X, dtype=np.float64), "lcb", par=self.par)
         return self._values(X, None, self.par)[0]

@@ -12,5 +12,8 @@ class PI(BaseAcquisitionFunction):
     def compute(self, X_test, derivative=False, **kwargs):
         """Phi((eta - m - par) / s), eta always the incumbent (pi.py:58-63)."""
         if derivative:
-            raise NotImplementedError("derivative=True needs model.predictive_gradients")
+            if not hasattr(self.model, "score_with_gradient"):
+                raise NotImplementedError("derivative=True needs a model with predictive gradients")
+            import numpy as np
+            return self.model.score_with_gradient(np.asarray(X_test, dtype=np.float64), "pi", par=self.par)
         return self._values(X_test, None, self.par)[0]

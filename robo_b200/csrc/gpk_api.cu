@@ -57,7 +57,9 @@ struct gpk_handle {
 
     // device buffers
     DevBuf Xrow, Xt, y, Kbuf, P, Q, W, lower, upper, logdet_part, scal, status, jobs;
-    DevBuf Kstar2;
+    DevBuf Kstar2, cand2;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> ev_copied, ev_scored;
     DevBuf cand, Kstar, part_mu, part_ssq, out_mu, out_var, out_acq, block_best, best, nneg;
     DevBuf Vt, cov, XsT, tmpjobs, alpha, tmp1, tmp2, tmp3;
     int layout_NP = -1;           // NP the P/Q/W buffers were zeroed for
@@ -432,8 +434,11 @@ int build_linv(gpk_handle* h) {
 }
 
 // Score m candidates resident on the device.  All output pointers are device pointers or NULL.
+// index_offset: global index of dX[0] (arg-max indices and output offsets are global); reset: start a new
+// running arg-max / negative-EI count (false when a host batch is fed in several pieces)
 int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, double par, double* d_out,
-              double* d_mu, double* d_var, BestPair* d_best, unsigned long long* d_nneg) {
+              double* d_mu, double* d_var, BestPair* d_best, unsigned long long* d_nneg,
+              long index_offset = 0, bool reset = true) {
     int rc = build_linv(h);
     if (rc) return rc;
     const long NP = h->NP;
@@ -441,8 +446,10 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
     if ((rc = ensure_score_scratch(h, cap))) return rc;
     if (d_best == nullptr) d_best = ptr<BestPair>(h->best);
     if (d_nneg == nullptr) d_nneg = ptr<unsigned long long>(h->nneg);
-    CK(cudaMemsetAsync(d_best, 0xFF, sizeof(BestPair), h->stream));
-    CK(cudaMemsetAsync(d_nneg, 0, 8, h->stream));
+    if (reset) {
+        CK(cudaMemsetAsync(d_best, 0xFF, sizeof(BestPair), h->stream));
+        CK(cudaMemsetAsync(d_nneg, 0, 8, h->stream));
+    }
     CK(cudaEventRecord(h->ev[6], h->stream));
     const int nchunks = (int)((m + cap - 1) / cap);
     // With more than one chunk, K* of chunk i+1 is built on the low-priority side stream (8 candidates
@@ -520,13 +527,13 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         FinishArgs f;
         memset(&f, 0, sizeof(f));
         f.part_mu = ptr<double>(h->part_mu); f.part_ssq = ptr<double>(h->part_ssq);
-        f.ldpart = cap; f.nparts = h->nb; f.m = mc; f.base = base;
+        f.ldpart = cap; f.nparts = h->nb; f.m = mc; f.base = index_offset + base;
         f.kss = h->spec.amp; f.mean = h->mean;
         f.norm_out = h->norm_out; f.y_mean = h->y_mean; f.y_std = h->y_std;
         f.acq_kind = kind; f.eta = eta; f.par = par;
-        f.out_mu = d_mu ? d_mu + base : nullptr;
-        f.out_var = d_var ? d_var + base : nullptr;
-        f.out_acq = d_out ? d_out + base : nullptr;
+        f.out_mu = d_mu ? d_mu + index_offset + base : nullptr;
+        f.out_var = d_var ? d_var + index_offset + base : nullptr;
+        f.out_acq = d_out ? d_out + index_offset + base : nullptr;
         f.block_best = ptr<BestPair>(h->block_best);
         f.n_negative = d_nneg;
         const int fb = (int)((mc + 255) / 256);
@@ -568,6 +575,7 @@ int gpk_create(gpk_handle** out, int device) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically smallest = highest priority
         if (cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
         if (cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
+        if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
     }
     h->stream = h->own_stream;
     for (int i = 0; i < 16; ++i)
@@ -590,7 +598,7 @@ int gpk_destroy(gpk_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
-                      &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->part_mu, &h->part_ssq, &h->out_mu,
+                      &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
                       &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3};
     for (DevBuf* b : bufs)
@@ -601,6 +609,9 @@ int gpk_destroy(gpk_handle* h) {
     for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_rest) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_cov) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_copied) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_scored) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (cudaEvent_t e : h->ev_gemm) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -912,15 +923,44 @@ int gpk_acq(gpk_handle* h, const double* Xs, long m, int kind, double eta, doubl
     if (!Xs || m <= 0) BAD("gpk_acq: need candidates");
     if (kind < GPK_ACQ_NONE || kind > GPK_ACQ_LCB) BAD("gpk_acq: unknown acquisition %d", kind);
     CK(cudaSetDevice(h->device));
-    if ((rc = ensure(h, h->cand, (size_t)m * h->d * 8))) return rc;
+    if ((rc = ensure(h, h->cand, (size_t)std::min<long>(m, 4 * h->chunk) * h->d * 8))) return rc;
     if (out && (rc = ensure(h, h->out_acq, (size_t)m * 8))) return rc;
     if (mu && (rc = ensure(h, h->out_mu, (size_t)m * 8))) return rc;
     if (var && (rc = ensure(h, h->out_var, (size_t)m * 8))) return rc;
     CK(cudaEventRecord(h->ev[14], h->stream));
-    CK(cudaMemcpyAsync(h->cand.p, Xs, (size_t)m * h->d * 8, cudaMemcpyHostToDevice, h->stream));
-    rc = score_dev(h, ptr<double>(h->cand), m, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,
-                   mu ? ptr<double>(h->out_mu) : nullptr, var ? ptr<double>(h->out_var) : nullptr, nullptr, nullptr);
-    if (rc) return rc;
+    const long piece = 4 * h->chunk;                  // host batch fed in pieces of 4 chunks
+    if (m <= piece) {
+        CK(cudaMemcpyAsync(h->cand.p, Xs, (size_t)m * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+        rc = score_dev(h, ptr<double>(h->cand), m, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,
+                       mu ? ptr<double>(h->out_mu) : nullptr, var ? ptr<double>(h->out_var) : nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    } else {
+        // H2D of piece i+1 (copy stream) overlaps the scoring of piece i; two device staging buffers.
+        const int np = (int)((m + piece - 1) / piece);
+        if ((rc = ensure(h, h->cand2, (size_t)piece * h->d * 8))) return rc;
+        while ((int)h->ev_copied.size() < np) {
+            cudaEvent_t e1, e2;
+            CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            h->ev_copied.push_back(e1);
+            h->ev_scored.push_back(e2);
+        }
+        CK(cudaEventRecord(h->ev_order, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_order, 0));
+        for (int i = 0; i < np; ++i) {
+            const long base = (long)i * piece, mc = std::min(piece, m - base);
+            double* buf = (i & 1) ? ptr<double>(h->cand2) : ptr<double>(h->cand);
+            if (i >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_scored[i - 2], 0));
+            CK(cudaMemcpyAsync(buf, Xs + base * h->d, (size_t)mc * h->d * 8, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaEventRecord(h->ev_copied[i], h->copy_stream));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_copied[i], 0));
+            rc = score_dev(h, buf, mc, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,
+                           mu ? ptr<double>(h->out_mu) : nullptr, var ? ptr<double>(h->out_var) : nullptr, nullptr, nullptr,
+                           base, i == 0);
+            if (rc) return rc;
+            CK(cudaEventRecord(h->ev_scored[i], h->stream));
+        }
+    }
     if (out) CK(cudaMemcpyAsync(out, h->out_acq.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
     if (mu) CK(cudaMemcpyAsync(mu, h->out_mu.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
     if (var) CK(cudaMemcpyAsync(var, h->out_var.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1074,6 +1114,99 @@ int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double*
     CK(cudaMemcpyAsync(mu, h->out_mu.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpy2DAsync(cov, (size_t)m * 8, h->cov.p, (size_t)mp * 8, (size_t)m * 8, (size_t)m, cudaMemcpyDeviceToHost,
                          h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_predict_grad(gpk_handle* h, const double* Xs, long m, int kind, double eta, double par, double* mu, double* var,
+                     double* dmu, double* dvar, double* f, double* df) {
+    int rc = require(h, true, true, true);
+    if (rc) return rc;
+    if (!Xs || m <= 0 || !mu || !var || !dmu || !dvar) BAD("gpk_predict_grad: need Xs, mu, var, dmu, dvar");
+    if (m > 16384) BAD("gpk_predict_grad: m = %ld too large", m);
+    if (kind != GPK_ACQ_NONE && (kind == GPK_ACQ_LOG_EI || kind < GPK_ACQ_NONE || kind > GPK_ACQ_LCB || !f || !df))
+        BAD("gpk_predict_grad: acquisition gradients exist for EI, PI, LCB and need f, df");
+    CK(cudaSetDevice(h->device));
+    if ((rc = build_linv(h))) return rc;
+    const long NP = h->NP, mp = round_up(m, BM);
+    const int nb = h->nb, mb = (int)(mp / BM), d = h->d;
+    if ((rc = ensure(h, h->cand, (size_t)m * d * 8))) return rc;
+    if ((rc = ensure_score_scratch(h, mp))) return rc;
+    bool grew = false;
+    if ((rc = ensure(h, h->Vt, (size_t)mp * NP * 8, &grew))) return rc;
+    if (grew || h->mapVt_rows != mp) {
+        if (h->loader != LOADER_CPASYNC && (rc = make_map(h, &h->mapVt, h->Vt.p, mp, NP, NP))) return rc;
+        h->mapVt_rows = mp;
+    }
+    if ((rc = ensure(h, h->cov, (size_t)mp * NP * 8))) return rc;            // Wt = (K^-1 K*^T)^T
+    if ((rc = ensure(h, h->alpha, (size_t)NP * 8))) return rc;
+    if ((rc = ensure(h, h->out_mu, (size_t)mp * 8))) return rc;
+    if ((rc = ensure(h, h->out_var, (size_t)mp * 8))) return rc;
+    if ((rc = ensure(h, h->tmp1, (size_t)m * d * 8 * 2))) return rc;
+    if ((rc = ensure(h, h->tmp2, (size_t)m * (d + 1) * 8))) return rc;
+    CK(cudaMemcpyAsync(h->cand.p, Xs, (size_t)m * d * 8, cudaMemcpyHostToDevice, h->stream));
+    // moments through the regular scoring path (same numbers as gpk_predict)
+    if ((rc = score_dev(h, ptr<double>(h->cand), m, GPK_ACQ_NONE, 0.0, 0.0, nullptr, ptr<double>(h->out_mu),
+                        ptr<double>(h->out_var), nullptr, nullptr)))
+        return rc;
+    const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
+    const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
+    if ((rc = ensure_score_scratch(h, mp))) return rc;       // score_dev may have sized the K* map for a smaller chunk
+    // K* again into the first buffer (score_dev may have used either), then Vt = (L^-1 K*^T)^T, Wt = (L^-T V)^T
+    gpk_cov_kernel<16><<<dim3((unsigned)(NP / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
+        h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->cand), d, m, lo, up, ptr<double>(h->Kstar), NP, 0);
+    CKL();
+    std::vector<GemmJob> jobs;
+    for (int ib = nb - 1; ib >= 0; --ib)
+        for (int cb = 0; cb < mb; ++cb) jobs.push_back({ib * BM, cb * BM, 0, (ib + 1) * BM, ib * BM, cb * BM, 0, 0});
+    const size_t n1 = jobs.size();
+    for (int jb = 0; jb < nb; ++jb)
+        for (int cb = 0; cb < mb; ++cb) jobs.push_back({cb * BM, jb * BM, jb * BM, (int)NP, cb * BM, jb * BM, 0, 0});
+    if ((rc = ensure(h, h->tmpjobs, jobs.size() * sizeof(GemmJob)))) return rc;
+    CK(cudaMemcpyAsync(h->tmpjobs.p, jobs.data(), jobs.size() * sizeof(GemmJob), cudaMemcpyHostToDevice, h->stream));
+    {
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.A = ptr<double>(h->P); a.lda = NP;
+        a.B = ptr<double>(h->Kstar); a.ldb = NP;
+        a.Ct = ptr<double>(h->Vt); a.ldct = NP;
+        a.alpha = 1.0;
+        a.jobs = ptr<GemmJob>(h->tmpjobs);
+        a.job_mode = JOBS_TABLE;
+        if ((rc = launch_gemm<EPI_STORE>(h, h->mapP, h->mapKs, a, (int)n1))) return rc;
+        GemmArgs b;
+        memset(&b, 0, sizeof(b));
+        b.A = ptr<double>(h->Vt); b.lda = NP;                // Wt[c][j] = sum_{i >= j} Vt[c][i] Q[j][i]
+        b.B = ptr<double>(h->Q); b.ldb = NP;
+        b.C = ptr<double>(h->cov); b.ldc = NP;
+        b.alpha = 1.0;
+        b.jobs = ptr<GemmJob>(h->tmpjobs) + n1;
+        b.job_mode = JOBS_TABLE;
+        if ((rc = launch_gemm<EPI_STORE>(h, h->mapVt, h->mapQ, b, (int)(jobs.size() - n1)))) return rc;
+    }
+    gpk_rowdot_kernel<<<(unsigned)((NP + 7) / 8), 256, 0, h->stream>>>(ptr<double>(h->Q), NP, NP, (int)NP, 1,
+                                                                       ptr<double>(h->Kbuf) + NP * NP,
+                                                                       ptr<double>(h->alpha));
+    CKL();
+    double* d_dmu = ptr<double>(h->tmp1);
+    double* d_dvar = d_dmu + m * d;
+    gpk_predict_grad_kernel<<<(unsigned)m, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->cand), d,
+                                                              lo, up, ptr<double>(h->alpha), ptr<double>(h->cov), NP,
+                                                              h->norm_out, h->y_std, d_dmu, d_dvar);
+    CKL();
+    CK(cudaMemcpyAsync(mu, h->out_mu.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(var, h->out_var.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(dmu, d_dmu, (size_t)m * d * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(dvar, d_dvar, (size_t)m * d * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (kind != GPK_ACQ_NONE) {
+        double* d_f = ptr<double>(h->tmp2);
+        double* d_df = d_f + m;
+        gpk_acq_grad_kernel<<<(unsigned)((m * d + 255) / 256), 256, 0, h->stream>>>(
+            ptr<double>(h->out_mu), ptr<double>(h->out_var), d_dmu, d_dvar, m, d, kind, eta, par, d_f, d_df);
+        CKL();
+        CK(cudaMemcpyAsync(f, d_f, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(df, d_df, (size_t)m * d * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return GPK_OK;
 }

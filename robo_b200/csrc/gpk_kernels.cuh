@@ -879,3 +879,107 @@ __global__ void gpk_candidates_kernel(unsigned long long seed, long first, long 
     out[li * d + a0] = v0;
     if (a1 < d) out[li * d + a1] = v1;
 }
+
+// ---------------------------------------------------------------------------------------
+// Predictive gradients (the API robo/acquisition_functions/ei.py:80-85,
+// pi.py:65-71, lcb.py:66-69 expect from a model but no reference model implements):
+//   d mu / d x*_a   =  sum_j alpha_j        d k(x*, x_j) / d x*_a
+//   d var / d x*_a  = -2 sum_j (K^-1 k*)_j  d k(x*, x_j) / d x*_a          (k** is constant: stationary kernels)
+//   d k / d x*_t    =  k * (dlog f / d r2)(r2_g) * 2 (x*_t - x_jt) / metric_t    per kernel term t (axis a = axis[t])
+// One CTA per candidate, threads stride over the training points, block reduction per term, chain
+// rule of the input scaling (1 / (upper - lower)) and of the output transform applied at the end.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gpk_predict_grad_kernel(const KSpec ks, const double* __restrict__ Xt, long ldx, int n,
+                        const double* __restrict__ cand, int dc,
+                        const double* __restrict__ lower, const double* __restrict__ upper,
+                        const double* __restrict__ alpha, const double* __restrict__ Wt, long ldw,
+                        int norm_out, double y_std, double* __restrict__ dmu, double* __restrict__ dvar)
+{
+    __shared__ double xs[GPK_MAX_TERMS];
+    __shared__ double red[16];
+    const int tid = threadIdx.x, nt = ks.n_terms;
+    const long c = blockIdx.x;
+    for (int t = tid; t < nt; t += 256) {
+        const int a = ks.axis[t];
+        double v = cand[c * dc + a];
+        if (lower != nullptr) v = (v - lower[a]) / (upper[a] - lower[a]);
+        xs[t] = v;
+    }
+    for (int a = tid; a < dc; a += 256) { dmu[c * dc + a] = 0.0; dvar[c * dc + a] = 0.0; }
+    __syncthreads();
+    double gm[GPK_MAX_TERMS], gv[GPK_MAX_TERMS];
+    for (int t = 0; t < nt; ++t) { gm[t] = 0.0; gv[t] = 0.0; }
+    for (int j = tid; j < n; j += 256) {
+        double k = ks.amp, r2 = 0.0;
+        for (int t = 0; t < nt; ++t) {                                  // kernel value
+            const double d = xs[t] - Xt[(long)ks.axis[t] * ldx + j];
+            r2 = fma(d * d, ks.inv_metric[t], r2);
+            if (ks.last[t]) { k *= gpk_radial(ks.family, r2); r2 = 0.0; }
+        }
+        const double ka = k * alpha[j], kw = -2.0 * k * Wt[c * ldw + j];
+        int t0 = 0;
+        while (t0 < nt) {                                               // group by group
+            int t1 = t0;
+            while (!ks.last[t1]) ++t1;
+            r2 = 0.0;
+            for (int t = t0; t <= t1; ++t) {
+                const double d = xs[t] - Xt[(long)ks.axis[t] * ldx + j];
+                r2 = fma(d * d, ks.inv_metric[t], r2);
+            }
+            const double ratio = 2.0 * gpk_radial_dlog(ks.family, r2);
+            for (int t = t0; t <= t1; ++t) {
+                const double d = xs[t] - Xt[(long)ks.axis[t] * ldx + j];
+                const double f = ratio * d * ks.inv_metric[t];
+                gm[t] = fma(ka, f, gm[t]);
+                gv[t] = fma(kw, f, gv[t]);
+            }
+            t0 = t1 + 1;
+        }
+    }
+    for (int t = 0; t < nt; ++t) {
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            double x = pass == 0 ? gm[t] : gv[t];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+            if ((tid & 31) == 0) red[pass * 8 + (tid >> 5)] = x;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double sm = 0.0, sv = 0.0;
+            for (int w = 0; w < 8; ++w) { sm += red[w]; sv += red[8 + w]; }
+            const int a = ks.axis[t];
+            double scale = 1.0;
+            if (lower != nullptr) scale = 1.0 / (upper[a] - lower[a]);
+            if (norm_out) { sm *= y_std; sv *= y_std * y_std; }
+            dmu[c * dc + a] += sm * scale;
+            dvar[c * dc + a] += sv * scale;
+        }
+        __syncthreads();
+    }
+}
+
+// Acquisition value and gradient from moments and their gradients (ei.py:76-85, pi.py:61-71, lcb.py:65-69).
+__global__ void gpk_acq_grad_kernel(const double* __restrict__ mu, const double* __restrict__ var,
+                                    const double* __restrict__ dmu, const double* __restrict__ dvar, long m, int d,
+                                    int kind, double eta, double par, double* __restrict__ f, double* __restrict__ df)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * d) return;
+    const long c = idx / d;
+    const double s = sqrt(var[c]);
+    const double dm = dmu[idx], ds = dvar[idx] / (2.0 * s);
+    double g;
+    if (kind == GPK_ACQ_EI) {
+        const double z = (eta - mu[c] - par) / s;
+        g = -dm * gpk_ndtr(z) + ds * gpk_norm_pdf(z);
+    } else if (kind == GPK_ACQ_PI) {
+        const double z = (eta - mu[c] - par) / s;
+        g = -(gpk_norm_pdf(z) / s) * (dm + ds * z);
+    } else {
+        g = -(dm - par * ds);
+    }
+    df[idx] = g;
+    if (idx == c * d) f[c] = gpk_acq_value(kind, mu[c], var[c], eta, par);
+}

@@ -167,6 +167,11 @@ class DeviceGP(object):
         self._push_cfg()
         return self.handle.predict_cov(Xs)
 
+    def predict_grad(self, Xs, kind=0, eta=0.0, par=0.0):
+        self._restore()
+        self._push_cfg()
+        return self.handle.predict_grad(Xs, kind, eta, par)
+
     def score(self, Xs, kind, eta=0.0, par=0.0, want_values=True, want_moments=False):
         self._restore()
         self._push_cfg()

@@ -186,6 +186,26 @@ class GaussianProcess(BaseModel):
         return self.gp.score(X_test, _lib.ACQ_KIND[kind], eta=float(eta), par=float(par),
                              want_values=want_values)
 
+    def predictive_gradients(self, X_test):
+        """d mu / d x and d var / d x at X_test, shapes (M, D) each.  This is the method the
+        reference's acquisition functions call when ``derivative=True`` (ei.py:80-85, pi.py:65-71,
+        lcb.py:66-69) and that none of its models provides."""
+        if not self.is_trained:
+            raise Exception('Model has to be trained first!')
+        assert len(X_test.shape) == 2
+        r = self.gp.predict_grad(X_test)
+        return r["dmu"], r["dvar"]
+
+    def score_with_gradient(self, X_test, kind, eta=None, par=0.0):
+        """(f (M,), df (M, D)) for 'ei', 'pi', 'lcb' — value and input gradient of the acquisition."""
+        from robo_b200 import _lib
+        if not self.is_trained:
+            raise Exception('Model has to be trained first!')
+        if eta is None:
+            eta = 0.0 if kind == "lcb" else self.get_incumbent()[1]
+        r = self.gp.predict_grad(X_test, _lib.ACQ_KIND[kind], float(eta), float(par))
+        return r["f"], r["df"]
+
     def sample_functions(self, X_test, n_funcs=1):
         """Posterior function samples at X_test (gaussian_process.py:298-332): mean and
         covariance from the device, the multivariate-normal draw with numpy like george."""

@@ -537,6 +537,45 @@ def test_device_candidate_generation_and_fused_maximize():
     assert mx.last["best_idx"] == int(np.argmax(acq.compute(cand)))
 
 
+@pytest.mark.parametrize("name", ["gp_branin_ny1", "gp_prod1d", "gp_rbf_d8"])
+def test_predictive_and_acquisition_gradients(name):
+    """d mu/dx, d var/dx and the EI / PI / LCB input gradients against central differences of the
+    oracle (the reference-faithful CPU predict + closed forms), incl. input scaling and output
+    un-normalisation chain rules."""
+    from robo_b200.acquisition_functions import EI, LCB, PI
+    d, kernel_fn = load_case(name)
+    family, theta = kernel_spec(name)
+    model = product_model(d, family, theta)
+    model.train(d["X"], d["y"], do_optimize=False)
+    st = O.gp_fit(kernel_fn(), d["X"], d["y"], noise=float(d["noise"]), normalize_input=bool(d["normalize_input"]),
+                  normalize_output=bool(d["normalize_output"]), lower=d["lower_"], upper=d["upper_"])
+    Xq = d["Xs"][:7]
+    D = Xq.shape[1]
+    span = 1.0 if d["lower_"] is None else (d["upper_"] - d["lower_"])
+    h = 1e-6 * span
+    dmu, dvar = model.predictive_gradients(Xq)
+    assert dmu.shape == dvar.shape == Xq.shape
+    eta = float(O.gp_get_incumbent(st)[1])
+
+    def fd(fun):
+        g = np.zeros((len(Xq), D))
+        for a in range(D):
+            e = np.zeros(D)
+            e[a] = (h[a] if np.ndim(h) else h)
+            g[:, a] = (fun(Xq + e) - fun(Xq - e)) / (2 * e[a])
+        return g
+    g_mu = fd(lambda X: O.gp_predict(st, X)[0])
+    g_var = fd(lambda X: O.gp_predict(st, X)[1])
+    np.testing.assert_allclose(dmu, g_mu, rtol=2e-5, atol=2e-6 * np.abs(g_mu).max())
+    np.testing.assert_allclose(dvar, g_var, rtol=2e-5, atol=2e-6 * np.abs(g_var).max())
+    for cls, kind in ((EI, "ei"), (PI, "pi"), (LCB, "lcb")):
+        f, df = cls(model).compute(Xq, derivative=True)
+        assert f.shape == (len(Xq),) and df.shape == Xq.shape
+        assert_acq_close(f, O.acquisition(st, Xq, kind), rtol=1e-8, atol=1e-13)
+        g = fd(lambda X: O.acquisition(st, X, kind, eta=None if kind == "lcb" else eta))
+        np.testing.assert_allclose(df, g, rtol=5e-5, atol=5e-6 * max(np.abs(g).max(), 1e-12))
+
+
 # --------------------------------------------------------------------------- larger sizes
 @pytest.mark.parametrize("N,D,M,family", [(1000, 8, 3000, "matern52"), (1536, 16, 1000, "rbf")])
 def test_mid_size_against_oracle(N, D, M, family, loader, monkeypatch):
@@ -558,6 +597,25 @@ def test_mid_size_against_oracle(N, D, M, family, loader, monkeypatch):
     assert r["n_negative"] == 0
     assert r["best_idx"] == int(np.argmax(r["values"]))
     assert ei_ref[r["best_idx"]] >= ei_ref.max() * (1 - 1e-8)
+
+
+def test_piecewise_host_feeding_is_invisible():
+    """gpk_acq feeds host batches larger than 4 chunks in pieces (H2D of piece i+1 overlapped with the
+    scoring of piece i): values, moments, arg-max and negative count must equal the one-shot path."""
+    from robo_b200 import _lib
+    X, y, Xs, theta, noise = O.synthetic_problem(300, 4, 1500, seed_train=3, seed_cand=4)
+    h, _, _, _, _ = _handle_for("matern52", theta, X, y, noise)
+    eta = float(np.min(y))
+    r1 = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
+    h.set_option("chunk", 128)                                  # piece = 512 candidates -> 3 pieces
+    r2 = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
+    for k in ("values", "mu", "var"):
+        np.testing.assert_array_equal(r1[k], r2[k])
+    assert r1["best_idx"] == r2["best_idx"] == int(np.argmax(r1["values"])) and r1["best_val"] == r2["best_val"]
+    r3 = h.acq(Xs, _lib.ACQ_LCB, 0.0, 1.0, want_values=False)
+    h.set_option("chunk", 16384)
+    r4 = h.acq(Xs, _lib.ACQ_LCB, 0.0, 1.0, want_values=True)
+    assert r3["best_idx"] == r4["best_idx"] == int(np.argmax(r4["values"]))
 
 
 def test_full_size_properties():
