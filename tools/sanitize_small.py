@@ -1,0 +1,36 @@
+"""Small end-to-end pass over every kernel (all staging variants) for compute-sanitizer runs."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from robo_b200 import _lib
+from robo_b200 import kernels as K
+
+rng = np.random.RandomState(0)
+N, D, M = 300, 3, 700
+X, y, Xs = rng.rand(N, D), rng.rand(N), rng.rand(M, D)
+f = K.Product(K.ConstantKernel(0.1, ndim=D), K.Matern52Kernel(np.array([0.3, 0.5, 0.8]), ndim=D)).flatten()
+for loader in (2, 1, 0):
+    h = _lib.Handle(0)
+    h.set_option("loader", loader)
+    h.set_option("chunk", 256)
+    h.set_data(X, y)
+    h.set_input_bounds(np.zeros(D), np.ones(D))
+    h.set_output_transform(True, 0.5, 2.0)
+    h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+    print("loader", loader, "fit", h.fit(1e-3 + 1.25e-12, float(y.mean())))
+    r = h.acq(Xs, _lib.ACQ_EI, float(y.min()), 0.0, want_values=True, want_moments=True)
+    print(" acq best", r["best_idx"], r["best_val"], "neg", r["n_negative"])
+    for kind in (_lib.ACQ_LOG_EI, _lib.ACQ_PI, _lib.ACQ_LCB):
+        h.acq(Xs[:300], kind, float(y.min()), 0.1)
+    mu, cov = h.predict_cov(Xs[:150])
+    g = h.nll_grad(1e-3, D)
+    pg = h.predict_grad(Xs[:5], _lib.ACQ_EI, float(y.min()), 0.0)
+    bx, bv, bi = h.maximize_random(7, 0, 1000, 700, np.zeros(D), np.ones(D), X[0], 0.1, _lib.ACQ_EI, float(y.min()), 0.0)
+    km = h.kernel_matrix(Xs[:40], X[:50])
+    print(" cov", cov.shape, "grad", np.round(g, 3), "dmu", pg["dmu"].shape, "max idx", bi, km.shape)
+    h.close()
+h = _lib.moments_handle()
+print(h.acq_moments(rng.randn(100), rng.rand(100) + 0.1, _lib.ACQ_LOG_EI, 0.0, 0.0)[0][:3])
+print(h.reduce_models(rng.rand(4, 50), rng.rand(4, 50))[1][:3])
+print("done")
