@@ -599,6 +599,32 @@ def test_mid_size_against_oracle(N, D, M, family, loader, monkeypatch):
     assert ei_ref[r["best_idx"]] >= ei_ref.max() * (1 - 1e-8)
 
 
+def test_george_shim_call_pattern():
+    """robo_b200.compat.GeorgeGP with george's own call order (targets only at log_likelihood / predict
+    time), as the reference's gaussian_process.py:106-159,280 drives it, against the oracle's george.GP."""
+    from robo_b200 import compat
+    from robo_b200 import kernels as K
+    rng = np.random.RandomState(5)
+    X, Xs = rng.rand(40, 3), rng.rand(25, 3)
+    y = np.sin(X.sum(axis=1))
+    theta = np.array([0.3, -0.5, 0.2, -1.0])
+    ref = G.GP(oracle_kernel("matern52", theta, 3), mean=float(y.mean()))
+    gp = compat.GeorgeGP(product_kernel("matern52", theta, 3), mean=float(y.mean()))
+    for yerr in (0.03, 0.1):
+        ref.compute(X, yerr=yerr)
+        gp.compute(X, yerr=yerr)
+        assert abs(gp.log_likelihood(y, quiet=True) - ref.log_likelihood(y, quiet=True)) <= 1e-10 * abs(ref.log_likelihood(y))
+    mu_ref, cov_ref = ref.predict(y, Xs)
+    mu, cov = gp.predict(y, Xs)
+    assert_mean_close(mu, mu_ref, y)
+    assert np.max(np.abs(cov - np.clip(cov_ref, O.EPS, np.inf))) <= 1e-10 * np.exp(theta[0])
+    y2 = y + 1.0                                             # new targets -> transparent refit
+    ref.compute(X, yerr=0.1)
+    assert abs(gp.log_likelihood(y2) - ref.log_likelihood(y2)) <= 1e-10 * abs(ref.log_likelihood(y2))
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.compute(np.zeros((5, 3)), yerr=0.0)
+
+
 def test_piecewise_host_feeding_is_invisible():
     """gpk_acq feeds host batches larger than 4 chunks in pieces (H2D of piece i+1 overlapped with the
     scoring of piece i): values, moments, arg-max and negative count must equal the one-shot path."""
