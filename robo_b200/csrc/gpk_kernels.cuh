@@ -551,6 +551,230 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
 }
 
 // ---------------------------------------------------------------------------------------
+// Diagonal block, pair-stepped fused version (default).  Same contract and the same cyclic 8 x 8
+// register tiles as gpk_potrf_diag_fused_kernel, but TWO pivots per barrier interval: the owners
+// publish the raw columns j and j+1, every thread factors the 2 x 2 pivot block redundantly
+//   l11 = sqrt(a), l21 = b / l11, l22 = sqrt(c - l21^2)
+// fixes the second column on the fly  l_i2 = (A[i][j+1] - l_i1 l21) / l22  and applies a rank-2 update;
+// the forward substitution L X = I follows one pair behind with the same trick.  64 barrier intervals
+// instead of 128, and finished columns of L leave the register file block by block.
+// ---------------------------------------------------------------------------------------
+template <int JBP>
+__device__ __forceinline__ void diag_pair_x_publish(const double (&X)[8][8], double* rbA, double* rbB, int ty, int tx, int jjm)
+{
+    if (ty == jjm) {
+#pragma unroll
+        for (int b = 0; b <= JBP; ++b) rbA[tx + 16 * b] = X[JBP][b];
+    } else if (ty == jjm + 1) {
+#pragma unroll
+        for (int b = 0; b <= JBP; ++b) rbB[tx + 16 * b] = X[JBP][b];
+    }
+}
+
+template <int JBP>
+__device__ __forceinline__ void diag_pair_x_update(double (&X)[8][8], const double (&lrp1)[8], const double (&lrp2)[8],
+                                                   const double* rbA, const double* rbB, double rs1p, double rs2p,
+                                                   double l21p, int ty, int tx, int jjm)
+{
+    double x1[8], x2[8];
+#pragma unroll
+    for (int b = 0; b <= JBP; ++b) {
+        x1[b] = rbA[tx + 16 * b] * rs1p;
+        x2[b] = fma(-l21p, x1[b], rbB[tx + 16 * b]) * rs2p;
+    }
+    if (ty == jjm) {
+#pragma unroll
+        for (int b = 0; b <= JBP; ++b) X[JBP][b] = x1[b];
+    } else if (ty == jjm + 1) {
+#pragma unroll
+        for (int b = 0; b <= JBP; ++b) X[JBP][b] = x2[b];
+    }
+#pragma unroll
+    for (int a = JBP; a < 8; ++a) {
+        const bool upd = (a > JBP) || (ty > jjm + 1);                    // row i > jm + 1
+#pragma unroll
+        for (int b = 0; b <= JBP; ++b)
+            if (upd) X[a][b] = fma(-lrp2[a], x2[b], fma(-lrp1[a], x1[b], X[a][b]));
+    }
+}
+
+struct DiagPairCarry { double rs1, rs2, l21; };
+
+template <int JB>
+__device__ __forceinline__ void diag_pair_block(double (&A)[8][8], double (&X)[8][8], double (&lrp1)[8], double (&lrp2)[8],
+                                                DiagPairCarry& cy, double* colbuf, double* rowbuf, double* ldiag,
+                                                double* Kt, long ld, int ty, int tx, int tid, int kb, int* s_bad)
+{
+    // X column block JB is first touched in this block: initialise it here (keeps registers free earlier)
+#pragma unroll
+    for (int a = 0; a < 8; ++a) X[a][JB] = (ty + 16 * a == tx + 16 * JB) ? 1.0 : 0.0;
+    for (int jj = 0; jj < 16; jj += 2) {
+        const int j = JB * 16 + jj, p = j >> 1;
+        double* cbA = colbuf + (p & 1) * 256;
+        double* cbB = cbA + 128;
+        double* rbA = rowbuf + ((p + 1) & 1) * 256;       // rows of the previous pair
+        double* rbB = rbA + 128;
+        if (tx == jj) {
+#pragma unroll
+            for (int a = JB; a < 8; ++a) cbA[ty + 16 * a] = A[a][JB];
+        } else if (tx == jj + 1) {
+#pragma unroll
+            for (int a = JB; a < 8; ++a) cbB[ty + 16 * a] = A[a][JB];
+        }
+        if (jj > 0) diag_pair_x_publish<JB>(X, rbA, rbB, ty, tx, jj - 2);
+        else if (JB > 0) diag_pair_x_publish<(JB > 0 ? JB - 1 : 0)>(X, rbA, rbB, ty, tx, 14);
+        __syncthreads();
+        // 2 x 2 pivot block, computed redundantly by every thread
+        double pa = cbA[j], pb = cbA[j + 1], pc = cbB[j + 1];
+        if (!(pa > 0.0) || isinf(pa)) {
+            if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 1;
+            pa = 1.0;
+        }
+        const double rs1 = rsqrt(pa), l11 = pa * rs1, l21 = pb * rs1;
+        double pc2 = fma(-l21, l21, pc);
+        if (!(pc2 > 0.0) || isinf(pc2)) {
+            if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 2;
+            pc2 = 1.0;
+        }
+        const double rs2 = rsqrt(pc2), l22 = pc2 * rs2;
+        if (tid == 0) { ldiag[j] = l11; ldiag[j + 1] = l22; }
+        double lr1[8], lr2[8], lc1[8], lc2[8];
+#pragma unroll
+        for (int a = JB; a < 8; ++a) {
+            lr1[a] = cbA[ty + 16 * a] * rs1;
+            lr2[a] = fma(-lr1[a], l21, cbB[ty + 16 * a]) * rs2;
+        }
+#pragma unroll
+        for (int b = JB; b < 8; ++b) {
+            lc1[b] = cbA[tx + 16 * b] * rs1;
+            lc2[b] = fma(-lc1[b], l21, cbB[tx + 16 * b]) * rs2;
+        }
+        if (tx == jj) {                     // owners keep the finished columns of L
+#pragma unroll
+            for (int a = JB; a < 8; ++a) {
+                const int i = ty + 16 * a;
+                if (i > j) A[a][JB] = lr1[a];
+                else if (i == j) A[a][JB] = l11;
+            }
+        } else if (tx == jj + 1) {
+#pragma unroll
+            for (int a = JB; a < 8; ++a) {
+                const int i = ty + 16 * a;
+                if (i > j + 1) A[a][JB] = lr2[a];
+                else if (i == j + 1) A[a][JB] = l22;
+            }
+        }
+        // forward substitution for the previous pair of rows
+        if (jj > 0) diag_pair_x_update<JB>(X, lrp1, lrp2, rbA, rbB, cy.rs1, cy.rs2, cy.l21, ty, tx, jj - 2);
+        else if (JB > 0) diag_pair_x_update<(JB > 0 ? JB - 1 : 0)>(X, lrp1, lrp2, rbA, rbB, cy.rs1, cy.rs2, cy.l21, ty, tx, 14);
+        // rank-2 update of the trailing part
+#pragma unroll
+        for (int b = JB; b < 8; ++b) {
+            const bool colok = (b > JB) || (tx > jj + 1);                // c > j + 1
+#pragma unroll
+            for (int a = b; a < 8; ++a) {
+                const bool upd = colok && ((a > b) || (ty >= tx));       // c <= i
+                if (upd) A[a][b] = fma(-lr2[a], lc2[b], fma(-lr1[a], lc1[b], A[a][b]));
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) { lrp1[a] = (a >= JB) ? lr1[a] : 0.0; lrp2[a] = (a >= JB) ? lr2[a] : 0.0; }
+        cy.rs1 = rs1; cy.rs2 = rs2; cy.l21 = l21;
+    }
+    // column block JB of L is final: write it out (zeros above the diagonal) and free its registers
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int i = ty + 16 * a, c = tx + 16 * JB;
+        Kt[(long)i * ld + c] = (a >= JB && c <= i) ? A[a][JB] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+gpk_potrf_diag_pair_kernel(double* __restrict__ K, long ld, int kb,
+                           double* __restrict__ P, double* __restrict__ Q, long ldp,
+                           int* __restrict__ status, double* __restrict__ logdet_part)
+{
+    extern __shared__ double dsm[];
+    double (*Ls)[129] = (double (*)[129])dsm;
+    double* colbuf = dsm + 128 * 129;     // 2 x (2 x 128)
+    double* rowbuf = colbuf + 512;        // 2 x (2 x 128)
+    double* ldiag = rowbuf + 512;         // 128
+    __shared__ int s_bad;
+
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    if (*status != 0) return;
+    if (tid == 0) s_bad = 0;
+
+    double* Kt = K + (long)kb * 128 * ld + (long)kb * 128;
+    double A[8][8], X[8][8], lrp1[8], lrp2[8];
+    DiagPairCarry cy;
+    cy.rs1 = 1.0; cy.rs2 = 1.0; cy.l21 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        lrp1[a] = 0.0; lrp2[a] = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int i = ty + 16 * a, c = tx + 16 * b;
+            A[a][b] = (c <= i) ? Kt[(long)i * ld + c] : 0.0;
+        }
+    }
+    __syncthreads();                      // all loads of the tile done before anyone overwrites it
+    diag_pair_block<0>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
+    diag_pair_block<1>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
+    diag_pair_block<2>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
+    diag_pair_block<3>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
+    diag_pair_block<4>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
+    diag_pair_block<5>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
+    diag_pair_block<6>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
+    diag_pair_block<7>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
+    // flush: the last pair of rows (126, 127) of X only needs its 2 x 2 solve
+    {
+        double* rbA = rowbuf + 256;       // buffer ((63 + 2) & 1) = 1: last read in step 62, buffer 0 may still be read
+        double* rbB = rbA + 128;
+        diag_pair_x_publish<7>(X, rbA, rbB, ty, tx, 14);
+        __syncthreads();
+        if (ty == 14 || ty == 15) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double x1 = rbA[tx + 16 * b] * cy.rs1;
+                const double x2 = fma(-cy.l21, x1, rbB[tx + 16 * b]) * cy.rs2;
+                X[7][b] = (ty == 14) ? x1 : x2;
+            }
+        }
+    }
+    // ---------------- log-det, status ----------------
+    if (tid < 32) {
+        double s = 0.0;
+        for (int q = tid; q < 128; q += 32) s += log(ldiag[q]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (tid == 0) {
+            logdet_part[kb] = s;
+            if (s_bad != 0) atomicCAS(status, 0, s_bad);
+        }
+    }
+    // ---------------- publish L^-1 (P lower) and its transpose (Q upper) ----------------
+    double* Pt = P + (long)kb * 128 * ldp + (long)kb * 128;
+    double* Qt = Q + (long)kb * 128 * ldp + (long)kb * 128;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int i = ty + 16 * a, c = tx + 16 * b;
+            const double v = (c <= i) ? X[a][b] : 0.0;
+            Ls[i][c] = v;
+            Pt[(long)i * ldp + c] = v;
+        }
+    __syncthreads();
+    for (int e = tid; e < 128 * 128; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        Qt[(long)r * ldp + c] = (c >= r) ? Ls[c][r] : 0.0;
+    }
+}
+
+constexpr int DIAG3_SMEM = (128 * 129 + 512 + 512 + 128) * 8;
+
+// ---------------------------------------------------------------------------------------
 // Scoring epilogue: sum the per-row-block partials in fixed order, finish mean / variance,
 // apply the output transform + clip (gaussian_process.py:282-294), the acquisition closed form,
 // and a per-block arg-max with numpy.argmax tie-breaking.
