@@ -62,8 +62,8 @@ const char* gpk_version(void);
  *   "loader"    operand staging of the GEMM tile engine: 2 = TMA with a dedicated producer warp and
  *               full/empty mbarriers [default], 1 = TMA issued by a consumer thread, 0 = cp.async (cross-check)
  *   "chunk"     candidates per scoring pass (multiple of 128, default 16384)
- *   "diag"      diagonal-block Cholesky kernel: 2 = fused factor + invert [default], 1 = two-phase
- *               register-tiled, 0 = simple shared-memory version (cross-check)
+ *   "diag"      diagonal-block Cholesky kernel: 2 = register-tiled fused factor + invert [default],
+ *               0 = simple shared-memory version (cross-check)
  *   "lookahead" 1 = trailing updates on a side stream, overlapped with the next diag/panel [default]
  *   "smalltile" 1 = 32-row tiles for the panel solve / next-panel update [default]
  *   "overlap"   1 = build K* of chunk i+1 on the side stream while chunk i contracts [default] */

@@ -43,7 +43,7 @@ struct gpk_handle {
     char err[1024] = {0};
     int loader = LOADER_TMA_WS;
     long chunk = 16384;
-    int diag_kernel = 3;          // 3 = pair-stepped fused, 2 = fused factor+invert, 1 = two-phase register-tiled, 0 = simple
+    int diag_kernel = 2;          // 2 = register-tiled fused factor + invert, 0 = simple shared-memory version (cross-check)
 
     // model
     int n = 0, d = 0, NP = 0, nb = 0;
@@ -207,9 +207,7 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 2)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-    CK(cudaFuncSetAttribute(gpk_potrf_diag_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
-    CK(cudaFuncSetAttribute(gpk_potrf_diag_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG3_SMEM));
     return GPK_OK;
 }
 
@@ -648,7 +646,7 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         return GPK_OK;
     }
     if (!strcmp(key, "diag")) {
-        if (value < 0 || value > 3) BAD("diag must be 0 (shared-memory), 1 (register-tiled), 2 (fused) or 3 (pair-stepped fused)");
+        if (value != 0 && value != 2) BAD("diag must be 2 (register-tiled fused kernel) or 0 (simple shared-memory kernel)");
         h->diag_kernel = (int)value;
         return GPK_OK;
     }
@@ -807,15 +805,9 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
     }
     std::vector<char> rest_recorded(nb, 0);
     for (int k = 0; k < nb; ++k) {
-        if (h->diag_kernel == 3)
-            gpk_potrf_diag_pair_kernel<<<1, 256, DIAG3_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
-                                                                          ptr<int>(h->status), ptr<double>(h->logdet_part));
-        else if (h->diag_kernel == 2)
+        if (h->diag_kernel == 2)
             gpk_potrf_diag_fused_kernel<<<1, 256, DIAG2_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
                                                                            ptr<int>(h->status), ptr<double>(h->logdet_part));
-        else if (h->diag_kernel == 1)
-            gpk_potrf_diag_reg_kernel<<<1, 256, DIAG2_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
-                                                                         ptr<int>(h->status), ptr<double>(h->logdet_part));
         else
             gpk_potrf_diag_kernel<<<1, 256, DIAG_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
                                                                     ptr<int>(h->status), ptr<double>(h->logdet_part));

@@ -197,192 +197,13 @@ gpk_potrf_diag_kernel(double* __restrict__ K, long ld, int kb,
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// Diagonal block, register-tiled version (default).  Same contract as gpk_potrf_diag_kernel.
-// Thread (ty, tx) = (tid / 16, tid % 16) keeps the 8 x 8 cyclic sub-tile A[ty + 16a][tx + 16b] in
-// registers.  Factorisation: per column j the 16 owner threads publish the column through a
-// double-buffered shared vector, everyone scales it by 1/sqrt(pivot) and applies the rank-1
-// update to its registers (1 barrier per column, <= 36 DFMA per thread).  Inversion: right-looking
-// forward substitution L X = I with X in registers, L read from shared memory, row j of X
-// broadcast through a second double-buffered vector (1 barrier per row).
-// ---------------------------------------------------------------------------------------
 constexpr int DIAG2_SMEM = (128 * 129 + 5 * 128) * 8;
 
-// columns 16*JB .. 16*JB+15 of the factorisation (JB is compile-time so A[][] stays in registers)
-template <int JB>
-__device__ __forceinline__ void diag_factor_block(double (&A)[8][8], double* colbuf, double* rdiag, int ty, int tx,
-                                                  int tid, int kb, int* s_bad)
-{
-    for (int jj = 0; jj < 16; ++jj) {
-        const int j = JB * 16 + jj;
-        double* cb = colbuf + (j & 1) * 128;
-        if (tx == jj) {
-#pragma unroll
-            for (int a = JB; a < 8; ++a) cb[ty + 16 * a] = A[a][JB];
-        }
-        __syncthreads();
-        double d = cb[j];
-        if (!(d > 0.0) || isinf(d)) {
-            if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 1;
-            d = 1.0;
-        }
-        // one rsqrt on the critical path instead of sqrt + divide: L_jj = d * rsqrt(d) (<= 2 ulp)
-        const double rs = rsqrt(d);
-        const double sq = d * rs;
-        if (tid == 0) rdiag[j] = rs;      // 1 / L_jj for the inversion below
-        double lr[8], lc[8];
-#pragma unroll
-        for (int a = JB; a < 8; ++a) lr[a] = cb[ty + 16 * a] * rs;
-#pragma unroll
-        for (int b = JB; b < 8; ++b) lc[b] = cb[tx + 16 * b] * rs;
-        if (tx == jj) {           // owners keep the finished column of L
-#pragma unroll
-            for (int a = JB; a < 8; ++a) {
-                const int i = ty + 16 * a;
-                if (i > j) A[a][JB] = lr[a];
-                else if (i == j) A[a][JB] = sq;
-            }
-        }
-#pragma unroll
-        for (int b = JB; b < 8; ++b) {
-            const bool colok = (b > JB) || (tx > jj);                // c > j
-#pragma unroll
-            for (int a = b; a < 8; ++a) {
-                const bool upd = colok && ((a > b) || (ty >= tx));   // c <= i
-                if (upd) A[a][b] = fma(-lr[a], lc[b], A[a][b]);
-            }
-        }
-    }
-}
-
-// rows 16*JB .. 16*JB+15 of the forward substitution L X = I
-template <int JB>
-__device__ __forceinline__ void diag_invert_block(double (&X)[8][8], const double (*Ls)[129], double* rowbuf,
-                                                  const double* rdiag, int ty, int tx)
-{
-    for (int jj = 0; jj < 16; ++jj) {
-        const int j = JB * 16 + jj;
-        double* rb = rowbuf + (j & 1) * 128;
-        const double inv = rdiag[j];
-        if (ty == jj) {           // row owners finish row j of X (entries right of the diagonal are 0)
-#pragma unroll
-            for (int b = 0; b <= JB; ++b) {
-                const double x = X[JB][b] * inv;
-                X[JB][b] = x;
-                rb[tx + 16 * b] = x;
-            }
-        }
-        __syncthreads();
-        double lr[8], xr[8];
-#pragma unroll
-        for (int a = JB; a < 8; ++a) lr[a] = Ls[ty + 16 * a][j];
-#pragma unroll
-        for (int b = 0; b <= JB; ++b) xr[b] = rb[tx + 16 * b];
-#pragma unroll
-        for (int a = JB; a < 8; ++a) {
-            const bool upd = (a > JB) || (ty > jj);                  // i > j
-#pragma unroll
-            for (int b = 0; b <= JB; ++b)
-                if (upd) X[a][b] = fma(-lr[a], xr[b], X[a][b]);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256, 1)
-gpk_potrf_diag_reg_kernel(double* __restrict__ K, long ld, int kb,
-                          double* __restrict__ P, double* __restrict__ Q, long ldp,
-                          int* __restrict__ status, double* __restrict__ logdet_part)
-{
-    extern __shared__ double dsm[];
-    double (*Ls)[129] = (double (*)[129])dsm;
-    double* colbuf = dsm + 128 * 129;     // 2 x 128
-    double* rowbuf = colbuf + 256;        // 2 x 128
-    double* rdiag = rowbuf + 256;         // 128: 1 / L_jj
-    __shared__ int s_bad;
-
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    if (*status != 0) return;
-    if (tid == 0) s_bad = 0;
-
-    double* Kt = K + (long)kb * 128 * ld + (long)kb * 128;
-    double A[8][8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int i = ty + 16 * a, c = tx + 16 * b;
-            A[a][b] = (c <= i) ? Kt[(long)i * ld + c] : 0.0;
-        }
-
-    // ---------------- factorisation ----------------
-    diag_factor_block<0>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<1>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<2>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<3>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<4>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<5>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<6>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
-    diag_factor_block<7>(A, colbuf, rdiag, ty, tx, tid, kb, &s_bad);
-
-    // ---------------- publish L ----------------
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int i = ty + 16 * a, c = tx + 16 * b;
-            const double v = (c <= i) ? A[a][b] : 0.0;
-            Ls[i][c] = v;
-            Kt[(long)i * ld + c] = v;
-        }
-    __syncthreads();
-    if (tid < 32) {
-        double s = 0.0;
-        for (int q = tid; q < 128; q += 32) s += log(Ls[q][q]);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (tid == 0) {
-            logdet_part[kb] = s;
-            if (s_bad != 0) atomicCAS(status, 0, s_bad);
-        }
-    }
-
-    // ---------------- inversion: L X = I ----------------
-    double X[8][8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) X[a][b] = (ty + 16 * a == tx + 16 * b) ? 1.0 : 0.0;
-    diag_invert_block<0>(X, Ls, rowbuf, rdiag, ty, tx);
-    diag_invert_block<1>(X, Ls, rowbuf, rdiag, ty, tx);
-    diag_invert_block<2>(X, Ls, rowbuf, rdiag, ty, tx);
-    diag_invert_block<3>(X, Ls, rowbuf, rdiag, ty, tx);
-    diag_invert_block<4>(X, Ls, rowbuf, rdiag, ty, tx);
-    diag_invert_block<5>(X, Ls, rowbuf, rdiag, ty, tx);
-    diag_invert_block<6>(X, Ls, rowbuf, rdiag, ty, tx);
-    diag_invert_block<7>(X, Ls, rowbuf, rdiag, ty, tx);
-
-    // ---------------- publish L^-1 (P lower) and its transpose (Q upper) ----------------
-    __syncthreads();
-    double* Pt = P + (long)kb * 128 * ldp + (long)kb * 128;
-    double* Qt = Q + (long)kb * 128 * ldp + (long)kb * 128;
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int i = ty + 16 * a, c = tx + 16 * b;
-            const double v = (c <= i) ? X[a][b] : 0.0;
-            Ls[i][c] = v;
-            Pt[(long)i * ldp + c] = v;
-        }
-    __syncthreads();
-    for (int e = tid; e < 128 * 128; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        Qt[(long)r * ldp + c] = (c >= r) ? Ls[c][r] : 0.0;
-    }
-}
-
 // ---------------------------------------------------------------------------------------
-// Diagonal block, fused version: the forward substitution L X = I runs one column behind the
+// Diagonal block, register-tiled fused version (default; same contract as gpk_potrf_diag_kernel).
+// Thread (ty, tx) = (tid / 16, tid % 16) keeps the 8 x 8 cyclic sub-tile A[ty + 16a][tx + 16b] in registers; per
+// column j the 16 owner threads publish the column through a double-buffered shared vector, everyone
+// scales it by rsqrt(pivot) and applies the rank-1 update to its registers.  The forward substitution L X = I runs one column behind the
 // factorisation inside the SAME barrier interval (row j-1 of X and column j of A are published
 // before the one __syncthreads of step j), so the block costs 128 barrier intervals instead of 256.
 // L columns reach the substitution through registers (the scaled column every thread already
@@ -549,230 +370,6 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
         Qt[(long)r * ldp + c] = (c >= r) ? Ls[c][r] : 0.0;
     }
 }
-
-// ---------------------------------------------------------------------------------------
-// Diagonal block, pair-stepped fused version (default).  Same contract and the same cyclic 8 x 8
-// register tiles as gpk_potrf_diag_fused_kernel, but TWO pivots per barrier interval: the owners
-// publish the raw columns j and j+1, every thread factors the 2 x 2 pivot block redundantly
-//   l11 = sqrt(a), l21 = b / l11, l22 = sqrt(c - l21^2)
-// fixes the second column on the fly  l_i2 = (A[i][j+1] - l_i1 l21) / l22  and applies a rank-2 update;
-// the forward substitution L X = I follows one pair behind with the same trick.  64 barrier intervals
-// instead of 128, and finished columns of L leave the register file block by block.
-// ---------------------------------------------------------------------------------------
-template <int JBP>
-__device__ __forceinline__ void diag_pair_x_publish(const double (&X)[8][8], double* rbA, double* rbB, int ty, int tx, int jjm)
-{
-    if (ty == jjm) {
-#pragma unroll
-        for (int b = 0; b <= JBP; ++b) rbA[tx + 16 * b] = X[JBP][b];
-    } else if (ty == jjm + 1) {
-#pragma unroll
-        for (int b = 0; b <= JBP; ++b) rbB[tx + 16 * b] = X[JBP][b];
-    }
-}
-
-template <int JBP>
-__device__ __forceinline__ void diag_pair_x_update(double (&X)[8][8], const double (&lrp1)[8], const double (&lrp2)[8],
-                                                   const double* rbA, const double* rbB, double rs1p, double rs2p,
-                                                   double l21p, int ty, int tx, int jjm)
-{
-    double x1[8], x2[8];
-#pragma unroll
-    for (int b = 0; b <= JBP; ++b) {
-        x1[b] = rbA[tx + 16 * b] * rs1p;
-        x2[b] = fma(-l21p, x1[b], rbB[tx + 16 * b]) * rs2p;
-    }
-    if (ty == jjm) {
-#pragma unroll
-        for (int b = 0; b <= JBP; ++b) X[JBP][b] = x1[b];
-    } else if (ty == jjm + 1) {
-#pragma unroll
-        for (int b = 0; b <= JBP; ++b) X[JBP][b] = x2[b];
-    }
-#pragma unroll
-    for (int a = JBP; a < 8; ++a) {
-        const bool upd = (a > JBP) || (ty > jjm + 1);                    // row i > jm + 1
-#pragma unroll
-        for (int b = 0; b <= JBP; ++b)
-            if (upd) X[a][b] = fma(-lrp2[a], x2[b], fma(-lrp1[a], x1[b], X[a][b]));
-    }
-}
-
-struct DiagPairCarry { double rs1, rs2, l21; };
-
-template <int JB>
-__device__ __forceinline__ void diag_pair_block(double (&A)[8][8], double (&X)[8][8], double (&lrp1)[8], double (&lrp2)[8],
-                                                DiagPairCarry& cy, double* colbuf, double* rowbuf, double* ldiag,
-                                                double* Kt, long ld, int ty, int tx, int tid, int kb, int* s_bad)
-{
-    // X column block JB is first touched in this block: initialise it here (keeps registers free earlier)
-#pragma unroll
-    for (int a = 0; a < 8; ++a) X[a][JB] = (ty + 16 * a == tx + 16 * JB) ? 1.0 : 0.0;
-    for (int jj = 0; jj < 16; jj += 2) {
-        const int j = JB * 16 + jj, p = j >> 1;
-        double* cbA = colbuf + (p & 1) * 256;
-        double* cbB = cbA + 128;
-        double* rbA = rowbuf + ((p + 1) & 1) * 256;       // rows of the previous pair
-        double* rbB = rbA + 128;
-        if (tx == jj) {
-#pragma unroll
-            for (int a = JB; a < 8; ++a) cbA[ty + 16 * a] = A[a][JB];
-        } else if (tx == jj + 1) {
-#pragma unroll
-            for (int a = JB; a < 8; ++a) cbB[ty + 16 * a] = A[a][JB];
-        }
-        if (jj > 0) diag_pair_x_publish<JB>(X, rbA, rbB, ty, tx, jj - 2);
-        else if (JB > 0) diag_pair_x_publish<(JB > 0 ? JB - 1 : 0)>(X, rbA, rbB, ty, tx, 14);
-        __syncthreads();
-        // 2 x 2 pivot block, computed redundantly by every thread
-        double pa = cbA[j], pb = cbA[j + 1], pc = cbB[j + 1];
-        if (!(pa > 0.0) || isinf(pa)) {
-            if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 1;
-            pa = 1.0;
-        }
-        const double rs1 = rsqrt(pa), l11 = pa * rs1, l21 = pb * rs1;
-        double pc2 = fma(-l21, l21, pc);
-        if (!(pc2 > 0.0) || isinf(pc2)) {
-            if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 2;
-            pc2 = 1.0;
-        }
-        const double rs2 = rsqrt(pc2), l22 = pc2 * rs2;
-        if (tid == 0) { ldiag[j] = l11; ldiag[j + 1] = l22; }
-        double lr1[8], lr2[8], lc1[8], lc2[8];
-#pragma unroll
-        for (int a = JB; a < 8; ++a) {
-            lr1[a] = cbA[ty + 16 * a] * rs1;
-            lr2[a] = fma(-lr1[a], l21, cbB[ty + 16 * a]) * rs2;
-        }
-#pragma unroll
-        for (int b = JB; b < 8; ++b) {
-            lc1[b] = cbA[tx + 16 * b] * rs1;
-            lc2[b] = fma(-lc1[b], l21, cbB[tx + 16 * b]) * rs2;
-        }
-        if (tx == jj) {                     // owners keep the finished columns of L
-#pragma unroll
-            for (int a = JB; a < 8; ++a) {
-                const int i = ty + 16 * a;
-                if (i > j) A[a][JB] = lr1[a];
-                else if (i == j) A[a][JB] = l11;
-            }
-        } else if (tx == jj + 1) {
-#pragma unroll
-            for (int a = JB; a < 8; ++a) {
-                const int i = ty + 16 * a;
-                if (i > j + 1) A[a][JB] = lr2[a];
-                else if (i == j + 1) A[a][JB] = l22;
-            }
-        }
-        // forward substitution for the previous pair of rows
-        if (jj > 0) diag_pair_x_update<JB>(X, lrp1, lrp2, rbA, rbB, cy.rs1, cy.rs2, cy.l21, ty, tx, jj - 2);
-        else if (JB > 0) diag_pair_x_update<(JB > 0 ? JB - 1 : 0)>(X, lrp1, lrp2, rbA, rbB, cy.rs1, cy.rs2, cy.l21, ty, tx, 14);
-        // rank-2 update of the trailing part
-#pragma unroll
-        for (int b = JB; b < 8; ++b) {
-            const bool colok = (b > JB) || (tx > jj + 1);                // c > j + 1
-#pragma unroll
-            for (int a = b; a < 8; ++a) {
-                const bool upd = colok && ((a > b) || (ty >= tx));       // c <= i
-                if (upd) A[a][b] = fma(-lr2[a], lc2[b], fma(-lr1[a], lc1[b], A[a][b]));
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 8; ++a) { lrp1[a] = (a >= JB) ? lr1[a] : 0.0; lrp2[a] = (a >= JB) ? lr2[a] : 0.0; }
-        cy.rs1 = rs1; cy.rs2 = rs2; cy.l21 = l21;
-    }
-    // column block JB of L is final: write it out (zeros above the diagonal) and free its registers
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int i = ty + 16 * a, c = tx + 16 * JB;
-        Kt[(long)i * ld + c] = (a >= JB && c <= i) ? A[a][JB] : 0.0;
-    }
-}
-
-__global__ void __launch_bounds__(256, 1)
-gpk_potrf_diag_pair_kernel(double* __restrict__ K, long ld, int kb,
-                           double* __restrict__ P, double* __restrict__ Q, long ldp,
-                           int* __restrict__ status, double* __restrict__ logdet_part)
-{
-    extern __shared__ double dsm[];
-    double (*Ls)[129] = (double (*)[129])dsm;
-    double* colbuf = dsm + 128 * 129;     // 2 x (2 x 128)
-    double* rowbuf = colbuf + 512;        // 2 x (2 x 128)
-    double* ldiag = rowbuf + 512;         // 128
-    __shared__ int s_bad;
-
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    if (*status != 0) return;
-    if (tid == 0) s_bad = 0;
-
-    double* Kt = K + (long)kb * 128 * ld + (long)kb * 128;
-    double A[8][8], X[8][8], lrp1[8], lrp2[8];
-    DiagPairCarry cy;
-    cy.rs1 = 1.0; cy.rs2 = 1.0; cy.l21 = 0.0;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        lrp1[a] = 0.0; lrp2[a] = 0.0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int i = ty + 16 * a, c = tx + 16 * b;
-            A[a][b] = (c <= i) ? Kt[(long)i * ld + c] : 0.0;
-        }
-    }
-    __syncthreads();                      // all loads of the tile done before anyone overwrites it
-    diag_pair_block<0>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
-    diag_pair_block<1>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
-    diag_pair_block<2>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
-    diag_pair_block<3>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
-    diag_pair_block<4>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
-    diag_pair_block<5>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
-    diag_pair_block<6>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
-    diag_pair_block<7>(A, X, lrp1, lrp2, cy, colbuf, rowbuf, ldiag, Kt, ld, ty, tx, tid, kb, &s_bad);
-    // flush: the last pair of rows (126, 127) of X only needs its 2 x 2 solve
-    {
-        double* rbA = rowbuf + 256;       // buffer ((63 + 2) & 1) = 1: last read in step 62, buffer 0 may still be read
-        double* rbB = rbA + 128;
-        diag_pair_x_publish<7>(X, rbA, rbB, ty, tx, 14);
-        __syncthreads();
-        if (ty == 14 || ty == 15) {
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const double x1 = rbA[tx + 16 * b] * cy.rs1;
-                const double x2 = fma(-cy.l21, x1, rbB[tx + 16 * b]) * cy.rs2;
-                X[7][b] = (ty == 14) ? x1 : x2;
-            }
-        }
-    }
-    // ---------------- log-det, status ----------------
-    if (tid < 32) {
-        double s = 0.0;
-        for (int q = tid; q < 128; q += 32) s += log(ldiag[q]);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (tid == 0) {
-            logdet_part[kb] = s;
-            if (s_bad != 0) atomicCAS(status, 0, s_bad);
-        }
-    }
-    // ---------------- publish L^-1 (P lower) and its transpose (Q upper) ----------------
-    double* Pt = P + (long)kb * 128 * ldp + (long)kb * 128;
-    double* Qt = Q + (long)kb * 128 * ldp + (long)kb * 128;
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int i = ty + 16 * a, c = tx + 16 * b;
-            const double v = (c <= i) ? X[a][b] : 0.0;
-            Ls[i][c] = v;
-            Pt[(long)i * ldp + c] = v;
-        }
-    __syncthreads();
-    for (int e = tid; e < 128 * 128; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        Qt[(long)r * ldp + c] = (c >= r) ? Ls[c][r] : 0.0;
-    }
-}
-
-constexpr int DIAG3_SMEM = (128 * 129 + 512 + 512 + 128) * 8;
 
 // ---------------------------------------------------------------------------------------
 // Scoring epilogue: sum the per-row-block partials in fixed order, finish mean / variance,

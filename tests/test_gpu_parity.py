@@ -89,6 +89,30 @@ def test_cholesky_forward_solve_logdet(N, D, loader):
     assert np.abs(np.triu(Linv, 1)).max() == 0.0
 
 
+def test_cholesky_variants_agree():
+    """every implementation switch (diagonal-block kernel, look-ahead, 32-row chain tiles) yields the same
+    factor to rounding"""
+    from robo_b200 import _lib
+    X, y, _, theta, noise = O.synthetic_problem(600, 5, 1, seed_train=11)
+    ref = None
+    for diag, la, st in ((2, 1, 1), (0, 1, 1), (2, 0, 1), (2, 1, 0), (0, 0, 0)):
+        h = _lib.Handle(0)
+        h.set_option("diag", diag)
+        h.set_option("lookahead", la)
+        h.set_option("smalltile", st)
+        h.set_data(X, y)
+        f = product_kernel("matern52", theta, 5).flatten()
+        h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+        logdet, ll = h.fit(1e-3 + G.TINY, float(np.mean(y)))
+        L, Li = h.get_factor(600), h.get_linv(600)
+        if ref is None:
+            ref = (logdet, ll, L, Li)
+        else:
+            assert abs(ll - ref[1]) <= 1e-12 * abs(ref[1]) and abs(logdet - ref[0]) <= 1e-12 * abs(ref[0])
+            np.testing.assert_allclose(L, ref[2], rtol=0, atol=1e-12 * np.abs(ref[2]).max())
+            np.testing.assert_allclose(Li, ref[3], rtol=0, atol=1e-11 * np.abs(ref[3]).max())
+
+
 def test_not_positive_definite_is_linalgerror():
     from robo_b200 import _lib
     X = np.zeros((6, 2))
@@ -622,7 +646,7 @@ def test_george_shim_call_pattern():
     ref.compute(X, yerr=0.1)
     assert abs(gp.log_likelihood(y2) - ref.log_likelihood(y2)) <= 1e-10 * abs(ref.log_likelihood(y2))
     with pytest.raises(np.linalg.LinAlgError):
-        gp.compute(np.zeros((5, 3)), yerr=0.0)
+        gp.compute(np.zeros((5, 3)), yerr=float("nan"))
 
 
 def test_piecewise_host_feeding_is_invisible():
