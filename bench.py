@@ -239,7 +239,7 @@ def run_ours(args, rank, world, local_rank):
     # algorithmic flops per launch: every candidate row of the chunk contracts with the lower
     # triangle of L^-1 (N^2/2 FMA = N^2 flop) plus the mean reduction (2N)   [SURVEY.md 8d: F_ei ~ N^2]
     rows = min(args.chunk, ((M + 127) // 128) * 128)
-    last_rows = M - (M - 1) // rows * rows if M > rows else M
+    last_rows = rows if M > rows else M          # timings() averages the full-size chunk launches of the last step
     gemm_ms = tim["vargemm_ms"]
     flops = float(last_rows) * (N_TRAIN ** 2 + 2 * N_TRAIN)
     achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -301,6 +301,7 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": "datasheet FP64-tensor 37 TF/s (SURVEY 8d P64); MEASURED_PEAKS.json has no fp64 figure",
                      "dgemm_cublas_tflops": dgemm, "frac_of_cublas_dgemm": achieved / dgemm if dgemm > 0 else None,
                      "launch_ms": gemm_ms, "launch_candidates": int(last_rows),
+                     "launches_averaged": int(max(1, (M + rows - 1) // rows - 1)) if M > rows else 1,
                      "traffic": 1.598e9 if last_rows == 16384 else None,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one 16384-candidate "
                                        "launch (profiles/r01_vargemm_ncu_full_raw.csv); algorithmic minimum 0.60e9 "

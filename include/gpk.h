@@ -188,7 +188,8 @@ int gpk_get_linv(gpk_handle* h, double* Linv /* n x n row-major, lower */);
 int gpk_get_z(gpk_handle* h, double* z /* n */);
 /* last fit/score timings measured with CUDA events on the handle's stream, milliseconds:
  * out[0] fit total, [1] K build, [2] Cholesky, [3] L^-1, [4] last score call total,
- * [5] K* build, [6] variance GEMM, [7] epilogue (5-7: last candidate chunk of that call);
+ * [5] K* build and [7] epilogue of the last candidate chunk, [6] variance GEMM averaged over the
+ * full-size chunk launches of that call;
  * out[8] = variance-GEMM launches so far,
  * out[9] = total kernel launches so far. */
 int gpk_get_timings(gpk_handle* h, double* out10);

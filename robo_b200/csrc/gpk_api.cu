@@ -60,6 +60,8 @@ struct gpk_handle {
     DevBuf Kstar2, cand2;
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> ev_copied, ev_scored;
+    std::vector<cudaEvent_t> ev_g0, ev_g1;    // timed pairs around every variance-GEMM launch of the last scoring call
+    int last_nchunks = 0;
     DevBuf cand, Kstar, part_mu, part_ssq, out_mu, out_var, out_acq, block_best, best, nneg;
     DevBuf Vt, cov, XsT, tmpjobs, alpha, tmp1, tmp2, tmp3;
     int layout_NP = -1;           // NP the P/Q/W buffers were zeroed for
@@ -464,6 +466,14 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             h->ev_gemm.push_back(e2);
         }
     }
+    while ((int)h->ev_g0.size() < nchunks) {
+        cudaEvent_t e1, e2;
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventCreate(&e2));
+        h->ev_g0.push_back(e1);
+        h->ev_g1.push_back(e2);
+    }
+    h->last_nchunks = nchunks;
     auto launch_cov = [&](int ci, cudaStream_t st, bool small) -> int {
         const long base = (long)ci * cap;
         const long mc = std::min(cap, m - base);
@@ -518,7 +528,9 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         a.part_ssq = ptr<double>(h->part_ssq);
         a.ldpart = cap;
         if (last) CK(cudaEventRecord(h->ev[10], h->stream));
+        CK(cudaEventRecord(h->ev_g0[ci], h->stream));
         if ((rc = launch_gemm<EPI_COLREDUCE>(h, h->mapP, second ? h->mapKs2 : h->mapKs, a, h->nb * a.mcb))) return rc;
+        CK(cudaEventRecord(h->ev_g1[ci], h->stream));
         if (last) CK(cudaEventRecord(h->ev[11], h->stream));
         if (pipelined) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
         h->launches_var += 1;
@@ -608,6 +620,8 @@ int gpk_destroy(gpk_handle* h) {
     for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_rest) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_cov) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_g0) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_g1) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_copied) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_scored) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1376,7 +1390,14 @@ int gpk_get_timings(gpk_handle* h, double* out) {
     if (h->score_timed) {
         if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) out[4] = ms;
         if (cudaEventElapsedTime(&ms, h->ev[8], h->ev[10]) == cudaSuccess) out[5] = ms;    // K* of the last chunk
-        if (cudaEventElapsedTime(&ms, h->ev[10], h->ev[11]) == cudaSuccess) out[6] = ms;   // variance GEMM, last chunk
+        // variance GEMM: mean over the FULL-SIZE chunk launches of the last scoring call (the last chunk
+        // is included only when it is the only one)
+        double sum = 0.0;
+        int cnt = 0;
+        const int nfull = h->last_nchunks > 1 ? h->last_nchunks - 1 : h->last_nchunks;
+        for (int i = 0; i < nfull && i < (int)h->ev_g0.size(); ++i)
+            if (cudaEventElapsedTime(&ms, h->ev_g0[i], h->ev_g1[i]) == cudaSuccess) { sum += ms; ++cnt; }
+        if (cnt > 0) out[6] = sum / cnt;
         if (cudaEventElapsedTime(&ms, h->ev[11], h->ev[12]) == cudaSuccess) out[7] = ms;   // epilogue, last chunk
     }
     cudaGetLastError();
