@@ -1,14 +1,16 @@
-"""Latin hypercube initial design (robo/initial_design/init_latin_hypercube_sampling.py:5-44)."""
+"""Latin-hypercube initial design with the sampling scheme and random-number consumption of
+robo/initial_design/init_latin_hypercube_sampling.py:5-44 (one uniform draw per stratum and dimension, then
+an independent shuffle of every dimension), so a seeded ``rng`` yields the reference's design."""
 import numpy as np
 
 
 def init_latin_hypercube_sampling(lower, upper, n_points, rng=None):
-    if rng is None:
-        rng = np.random.RandomState(np.random.randint(0, 10000))
+    rng = np.random.RandomState(np.random.randint(0, 10000)) if rng is None else rng
     n_dims = lower.shape[0]
-    s_bounds = np.array([np.linspace(lower[i], upper[i], n_points + 1) for i in range(n_dims)])
-    s_lower, s_upper = s_bounds[:, :-1], s_bounds[:, 1:]
-    samples = s_lower + rng.uniform(0, 1, s_lower.shape) * (s_upper - s_lower)
-    for i in range(n_dims):
-        rng.shuffle(samples[i, :])
-    return samples.T
+    edges = np.stack([np.linspace(lower[d], upper[d], n_points + 1) for d in range(n_dims)])   # (D, n+1)
+    left, width = edges[:, :-1], np.diff(edges, axis=1)
+    design = left + rng.uniform(0, 1, left.shape) * (edges[:, 1:] - left)                       # one point per stratum
+    del width
+    for d in range(n_dims):
+        rng.shuffle(design[d, :])
+    return design.T

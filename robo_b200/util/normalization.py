@@ -1,27 +1,37 @@
-"""Host-side input/output scaling (robo/util/normalization.py:4-32).  Only the *training*
-data passes through these (O(N D) once per train); test inputs and predictive moments are
-scaled inside the CUDA kernels (gpk_set_input_bounds / gpk_set_output_transform)."""
+"""Training-data scaling on the host (the four helpers of robo/util/normalization.py:4-32, same names and
+return conventions because RoBO's callers import them by name).
+
+Only the *training* set passes through here, once per ``train`` (O(N D)).  Test inputs are scaled and
+predictive moments un-scaled inside the CUDA kernels (``gpk_set_input_bounds`` /
+``gpk_set_output_transform``), with the same arithmetic: a true division by ``upper - lower`` and
+``x * std + mean``.
+"""
 import numpy as np
 
 
+def _column_range(X, lower, upper):
+    lo = X.min(axis=0) if lower is None else lower
+    hi = X.max(axis=0) if upper is None else upper
+    return lo, hi
+
+
 def zero_one_normalization(X, lower=None, upper=None):
-    if lower is None:
-        lower = np.min(X, axis=0)
-    if upper is None:
-        upper = np.max(X, axis=0)
-    return np.true_divide((X - lower), (upper - lower)), lower, upper
+    """(X - lower) / (upper - lower); missing bounds default to the column extrema of X and are returned so
+    that test points can be mapped with the same box."""
+    lo, hi = _column_range(X, lower, upper)
+    return np.true_divide(X - lo, hi - lo), lo, hi
 
 
 def zero_one_unnormalization(X_normalized, lower, upper):
-    return lower + (upper - lower) * X_normalized
+    span = upper - lower
+    return lower + span * X_normalized
 
 
 def zero_mean_unit_var_normalization(X, mean=None, std=None):
-    if mean is None:
-        mean = np.mean(X, axis=0)
-    if std is None:
-        std = np.std(X, axis=0)
-    return (X - mean) / std, mean, std
+    """Standardise with the population standard deviation (ddof = 0)."""
+    mu = X.mean(axis=0) if mean is None else mean
+    sd = X.std(axis=0) if std is None else std
+    return (X - mu) / sd, mu, sd
 
 
 def zero_mean_unit_var_unnormalization(X_normalized, mean, std):
