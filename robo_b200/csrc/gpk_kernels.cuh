@@ -240,9 +240,12 @@ __device__ __forceinline__ void diag_x_update(double (&X)[8][8], const double (&
 
 template <int JB>
 __device__ __forceinline__ void diag_fused_block(double (&A)[8][8], double (&X)[8][8], double (&lrp)[8], double& rs_prev,
-                                                 double* colbuf, double* rowbuf, int ty, int tx, int tid, int kb,
-                                                 int* s_bad)
+                                                 double& rs_cur, double* colbuf, double* rowbuf, double* dnext,
+                                                 int ty, int tx, int tid, int kb, int* s_bad)
 {
+    // rs_cur = rsqrt(pivot j) arrives from the previous step: the reciprocal square root of the NEXT pivot
+    // is computed one step ahead from the published diagonal element, so the rsqrt latency (the longest
+    // dependent chain of a step) overlaps the rank-1 updates instead of sitting between two barriers.
     for (int jj = 0; jj < 16; ++jj) {
         const int j = JB * 16 + jj;
         double* cb = colbuf + (j & 1) * 128;
@@ -250,6 +253,12 @@ __device__ __forceinline__ void diag_fused_block(double (&A)[8][8], double (&X)[
         if (tx == jj) {
 #pragma unroll
             for (int a = JB; a < 8; ++a) cb[ty + 16 * a] = A[a][JB];
+        }
+        // the owner of diagonal element j+1 publishes its current value (updated through column j-1)
+        if (jj < 15) {
+            if (ty == jj + 1 && tx == jj + 1) dnext[j & 1] = A[JB][JB];
+        } else if (JB < 7) {
+            if (ty == 0 && tx == 0) dnext[j & 1] = A[JB < 7 ? JB + 1 : 7][JB < 7 ? JB + 1 : 7];
         }
         if (jj > 0) diag_x_publish<JB>(X, rb, rs_prev, ty, tx, jj - 1);
         else if (JB > 0) diag_x_publish<(JB > 0 ? JB - 1 : 0)>(X, rb, rs_prev, ty, tx, 15);
@@ -259,8 +268,15 @@ __device__ __forceinline__ void diag_fused_block(double (&A)[8][8], double (&X)[
             if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 1;
             d = 1.0;
         }
-        const double rs = rsqrt(d);
+        const double rs = rs_cur;            // == rsqrt(d), computed during the previous step
         const double sq = d * rs;
+        // next pivot: d_{j+1} = A[j+1][j+1] - l_{j+1,j}^2, the same fma its owner applies below
+        double rs_next = 1.0;
+        if (j < 127) {
+            const double ln = cb[j + 1] * rs;
+            const double dn = fma(-ln, ln, dnext[j & 1]);
+            rs_next = (dn > 0.0 && !isinf(dn)) ? rsqrt(dn) : 1.0;
+        }
         double lr[8], lc[8];
 #pragma unroll
         for (int a = JB; a < 8; ++a) lr[a] = cb[ty + 16 * a] * rs;
@@ -289,6 +305,7 @@ __device__ __forceinline__ void diag_fused_block(double (&A)[8][8], double (&X)[
 #pragma unroll
         for (int a = 0; a < 8; ++a) lrp[a] = (a >= JB) ? lr[a] : 0.0;
         rs_prev = rs;
+        rs_cur = rs_next;
     }
 }
 
@@ -301,6 +318,7 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
     double (*Ls)[129] = (double (*)[129])dsm;
     double* colbuf = dsm + 128 * 129;     // 2 x 128
     double* rowbuf = colbuf + 256;        // 2 x 128
+    double* dnext = rowbuf + 256;         // 2: diagonal element of the next pivot
     __shared__ int s_bad;
 
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -309,7 +327,7 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
 
     double* Kt = K + (long)kb * 128 * ld + (long)kb * 128;
     double A[8][8], X[8][8], lrp[8];
-    double rs_prev = 1.0;
+    double rs_prev = 1.0, rs_cur = 1.0;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         lrp[a] = 0.0;
@@ -320,14 +338,20 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
             X[a][b] = (i == c) ? 1.0 : 0.0;
         }
     }
-    diag_fused_block<0>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
-    diag_fused_block<1>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
-    diag_fused_block<2>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
-    diag_fused_block<3>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
-    diag_fused_block<4>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
-    diag_fused_block<5>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
-    diag_fused_block<6>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
-    diag_fused_block<7>(A, X, lrp, rs_prev, colbuf, rowbuf, ty, tx, tid, kb, &s_bad);
+    if (tid == 0) dnext[1] = A[0][0];     // first pivot (slot 1: step 0 publishes the next one into slot 0)
+    __syncthreads();
+    {
+        const double d0 = dnext[1];
+        rs_cur = (d0 > 0.0 && !isinf(d0)) ? rsqrt(d0) : 1.0;
+    }
+    diag_fused_block<0>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<1>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<2>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<3>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<4>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<5>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<6>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
+    diag_fused_block<7>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
     // last row of X (row 127) only needs its scaling; nobody reads the broadcast copy
     diag_x_publish<7>(X, rowbuf, rs_prev, ty, tx, 15);
 
