@@ -223,38 +223,42 @@ __device__ __forceinline__ void diag_x_publish(double (&X)[8][8], double* rb, do
 }
 
 template <int JBP>
-__device__ __forceinline__ void diag_x_update(double (&X)[8][8], const double (&lrp)[8], const double* rb,
+__device__ __forceinline__ void diag_x_update(double (&X)[8][8], const double (&lr)[8], const double* rb,
                                               int ty, int tx, int jjp)
 {
-    double xr[8];
+    // X[i][c] -= L[i][jm] X[jm][c] for the rows below jm = 16 JBP + jjp.  No per-element predicates: the rows of
+    // block JBP that are not below jm get a zero multiplier (one select), columns right of jm hold zeros in rb.
+    double xr[8], lx[8];
+    const double* rbc = rb + tx;
 #pragma unroll
-    for (int b = 0; b <= JBP; ++b) xr[b] = rb[tx + 16 * b];
+    for (int b = 0; b <= JBP; ++b) xr[b] = rbc[16 * b];
 #pragma unroll
-    for (int a = JBP; a < 8; ++a) {
-        const bool upd = (a > JBP) || (ty > jjp);                    // i > jm
+    for (int a = JBP; a < 8; ++a) lx[a] = lr[a];
+    lx[JBP] = (ty > jjp) ? lr[JBP] : 0.0;
 #pragma unroll
-        for (int b = 0; b <= JBP; ++b)
-            if (upd) X[a][b] = fma(-lrp[a], xr[b], X[a][b]);
-    }
+    for (int a = JBP; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b <= JBP; ++b) X[a][b] = fma(-lx[a], xr[b], X[a][b]);
 }
 
 template <int JB>
-__device__ __forceinline__ void diag_fused_block(double (&A)[8][8], double (&X)[8][8], double (&lrp)[8], double& rs_prev,
+__device__ __forceinline__ void diag_fused_block(double (&A)[8][8], double (&X)[8][8], double (&lr)[8], double& rs_prev,
                                                  double& rs_cur, double* colbuf, double* rowbuf, double* dnext,
                                                  int ty, int tx, int tid, int kb, int* s_bad)
 {
-    // rs_cur = rsqrt(pivot j) arrives from the previous step: the reciprocal square root of the NEXT pivot
-    // is computed one step ahead from the published diagonal element, so the rsqrt latency (the longest
-    // dependent chain of a step) overlaps the rank-1 updates instead of sitting between two barriers.
+    // Invariants.  lr[] enters holding the scaled column j-1 of L (this thread's rows) and leaves holding column j.
+    // rs_cur = rsqrt(pivot j) was computed during the previous step from the published diagonal element.
+    // Entries above the diagonal inside the diagonal blocks (row < column) are never read by valid entries and
+    // are left to hold garbage (this removes the per-element predicates; the final store masks them).
     for (int jj = 0; jj < 16; ++jj) {
         const int j = JB * 16 + jj;
         double* cb = colbuf + (j & 1) * 128;
         double* rb = rowbuf + ((j + 1) & 1) * 128;       // parity of jm = j - 1
         if (tx == jj) {
+            double* cbw = cb + ty;
 #pragma unroll
-            for (int a = JB; a < 8; ++a) cb[ty + 16 * a] = A[a][JB];
+            for (int a = JB; a < 8; ++a) cbw[16 * a] = A[a][JB];
         }
-        // the owner of diagonal element j+1 publishes its current value (updated through column j-1)
         if (jj < 15) {
             if (ty == jj + 1 && tx == jj + 1) dnext[j & 1] = A[JB][JB];
         } else if (JB < 7) {
@@ -268,42 +272,39 @@ __device__ __forceinline__ void diag_fused_block(double (&A)[8][8], double (&X)[
             if (tid == 0 && *s_bad == 0) *s_bad = kb * 128 + j + 1;
             d = 1.0;
         }
-        const double rs = rs_cur;            // == rsqrt(d), computed during the previous step
+        const double rs = rs_cur;            // == rsqrt(d)
         const double sq = d * rs;
-        // next pivot: d_{j+1} = A[j+1][j+1] - l_{j+1,j}^2, the same fma its owner applies below
         double rs_next = 1.0;
-        if (j < 127) {
+        if (j < 127) {                       // next pivot: the same fma its owner applies below
             const double ln = cb[j + 1] * rs;
             const double dn = fma(-ln, ln, dnext[j & 1]);
             rs_next = (dn > 0.0 && !isinf(dn)) ? rsqrt(dn) : 1.0;
         }
-        double lr[8], lc[8];
+        // forward-substitution step for row j-1, with the previous column of L still in lr[]
+        if (jj > 0) diag_x_update<JB>(X, lr, rb, ty, tx, jj - 1);
+        else if (JB > 0) diag_x_update<(JB > 0 ? JB - 1 : 0)>(X, lr, rb, ty, tx, 15);
+        // column j of L, scaled
+        double lc[8];
+        const double* cbr = cb + ty;
+        const double* cbc = cb + tx;
 #pragma unroll
-        for (int a = JB; a < 8; ++a) lr[a] = cb[ty + 16 * a] * rs;
+        for (int a = JB; a < 8; ++a) lr[a] = cbr[16 * a] * rs;
 #pragma unroll
-        for (int b = JB; b < 8; ++b) lc[b] = cb[tx + 16 * b] * rs;
-        if (tx == jj) {
+        for (int b = JB; b < 8; ++b) lc[b] = cbc[16 * b] * rs;
+        if (tx == jj) {                      // owners keep the finished column (rows above the diagonal: don't care)
 #pragma unroll
-            for (int a = JB; a < 8; ++a) {
-                const int i = ty + 16 * a;
-                if (i > j) A[a][JB] = lr[a];
-                else if (i == j) A[a][JB] = sq;
-            }
+            for (int a = JB + 1; a < 8; ++a) A[a][JB] = lr[a];
+            A[JB][JB] = (ty == jj) ? sq : lr[JB];
         }
-        // substitution step for row jm = j - 1 (uses the column of L scaled in the previous step)
-        if (jj > 0) diag_x_update<JB>(X, lrp, rb, ty, tx, jj - 1);
-        else if (JB > 0) diag_x_update<(JB > 0 ? JB - 1 : 0)>(X, lrp, rb, ty, tx, 15);
+        // rank-1 update; only the column block that contains finished columns needs a predicate
+        if (tx > jj) {
 #pragma unroll
-        for (int b = JB; b < 8; ++b) {
-            const bool colok = (b > JB) || (tx > jj);
-#pragma unroll
-            for (int a = b; a < 8; ++a) {
-                const bool upd = colok && ((a > b) || (ty >= tx));
-                if (upd) A[a][b] = fma(-lr[a], lc[b], A[a][b]);
-            }
+            for (int a = JB; a < 8; ++a) A[a][JB] = fma(-lr[a], lc[JB], A[a][JB]);
         }
 #pragma unroll
-        for (int a = 0; a < 8; ++a) lrp[a] = (a >= JB) ? lr[a] : 0.0;
+        for (int b = JB + 1; b < 8; ++b)
+#pragma unroll
+            for (int a = b; a < 8; ++a) A[a][b] = fma(-lr[a], lc[b], A[a][b]);
         rs_prev = rs;
         rs_cur = rs_next;
     }
@@ -326,7 +327,7 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
     if (tid == 0) s_bad = 0;
 
     double* Kt = K + (long)kb * 128 * ld + (long)kb * 128;
-    double A[8][8], X[8][8], lrp[8];
+    double A[8][8], X[8][8], lrp[8];          // lrp: the scaled column of L of the previous step
     double rs_prev = 1.0, rs_cur = 1.0;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
