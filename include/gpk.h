@@ -182,6 +182,11 @@ int gpk_kernel_matrix(gpk_handle* h, const double* X1, long n1, const double* X2
  * preceding successful gpk_fit with the same parameters.  noise_var = sigma^2. */
 int gpk_nll_grad(gpk_handle* h, double noise_var, double* grad);
 
+/* fp64 issue-rate peaks of this GPU in TFLOP/s, measured with register-resident operands: the DMMA
+ * m8n8k4 tensor pipe (every GEMM of the library) and the DFMA vector pipe (covariance builder).  bench.py
+ * uses the DMMA figure as the roofline denominator (MEASURED_PEAKS.json has no fp64 entry). */
+int gpk_measure_fp64_peaks(gpk_handle* h, double* dmma_tflops, double* dfma_tflops);
+
 /* ---- introspection (tests / debugging) ----------------------------------------------- */
 int gpk_get_factor(gpk_handle* h, double* L /* n x n row-major, lower */);
 int gpk_get_linv(gpk_handle* h, double* Linv /* n x n row-major, lower */);

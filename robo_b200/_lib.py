@@ -49,6 +49,7 @@ _SIGNATURES = {
     "gpk_kernel_matrix": [_vp, _dp, C.c_long, _dp, C.c_long, C.c_int, _dp],
     "gpk_reduce_models": [_vp, _dp, _dp, C.c_int, C.c_long, C.c_int, _dp, _dp],
     "gpk_nll_grad": [_vp, C.c_double, _dp],
+    "gpk_measure_fp64_peaks": [_vp, _dp, _dp],
     "gpk_get_factor": [_vp, _dp],
     "gpk_get_linv": [_vp, _dp],
     "gpk_get_z": [_vp, _dp],
@@ -291,6 +292,12 @@ class Handle(object):
         self._check(self.lib.gpk_kernel_matrix(self._h, _as_dp(X1), X1.shape[0], _as_dp(X2), X2.shape[0],
                                                X1.shape[1], _as_dp(out)))
         return out
+
+    def measure_fp64_peaks(self):
+        """-> (DMMA tensor-pipe TFLOP/s, DFMA vector-pipe TFLOP/s) measured on this GPU."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.gpk_measure_fp64_peaks(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # -- introspection ----------------------------------------------------------------
     def get_factor(self, n):

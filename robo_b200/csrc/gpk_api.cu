@@ -1338,6 +1338,42 @@ int gpk_nll_grad(gpk_handle* h, double noise_var, double* grad) {
     return GPK_OK;
 }
 
+int gpk_measure_fp64_peaks(gpk_handle* h, double* dmma_tflops, double* dfma_tflops) {
+    if (!h) return GPK_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount, warps = 16, threads = warps * 32, iters = 8000;
+    int rc;
+    if ((rc = ensure(h, h->tmp1, 64))) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best_mma = 0.0, best_fma = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        float ms = 0.f;
+        CK(cudaEventRecord(e0, h->stream));
+        gpk_peak_dmma_kernel<<<blocks, threads, 0, h->stream>>>(ptr<double>(h->tmp1), iters);
+        CKL();
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best_mma = std::max(best_mma, 2.0 * 256 * 16 * (double)iters * warps * blocks / (ms * 1e-3) / 1e12);
+        CK(cudaEventRecord(e0, h->stream));
+        gpk_peak_dfma_kernel<<<blocks, threads, 0, h->stream>>>(ptr<double>(h->tmp1), iters);
+        CKL();
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best_fma = std::max(best_fma, 2.0 * 8 * (double)iters * threads * blocks / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (dmma_tflops) *dmma_tflops = best_mma;
+    if (dfma_tflops) *dfma_tflops = best_fma;
+    return GPK_OK;
+}
+
 int gpk_get_factor(gpk_handle* h, double* L) {
     int rc = require(h, true, true, true);
     if (rc) return rc;

@@ -829,3 +829,41 @@ __global__ void gpk_acq_grad_kernel(const double* __restrict__ mu, const double*
     df[idx] = g;
     if (idx == c * d) f[c] = gpk_acq_value(kind, mu[c], var[c], eta, par);
 }
+
+// ---------------------------------------------------------------------------------------
+// fp64 issue-rate peaks of the GPU we run on (register-resident operands, no memory traffic): the
+// denominators of the roofline reported by bench.py.  DMMA m8n8k4 = the tensor pipe every GEMM of this
+// library uses; DFMA = the vector pipe of the covariance builder.
+// ---------------------------------------------------------------------------------------
+__global__ void gpk_peak_dmma_kernel(double* out, int iters)
+{
+    double c[16][2], a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+__global__ void gpk_peak_dfma_kernel(double* out, int iters)
+{
+    double a[8];
+    const double b = 1.0000001, c = 0.9999999;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fma(a[i], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 12345.678) out[0] = s;
+}
