@@ -66,6 +66,7 @@ const char* gpk_version(void);
  *               0 = simple shared-memory version (cross-check)
  *   "lookahead" 1 = trailing updates on a side stream, overlapped with the next diag/panel [default]
  *   "smalltile" 1 = 32-row tiles for the panel solve / next-panel update [default]
+ *   "pdl"       1 = programmatic dependent launch for the kernels of the Cholesky chain [default]
  *   "overlap"   1 = build K* of chunk i+1 on the side stream while chunk i contracts [default] */
 int gpk_set_option(gpk_handle* h, const char* key, long value);
 /* run on an existing CUDA stream (cudaStream_t passed as void*); NULL = the handle's own */

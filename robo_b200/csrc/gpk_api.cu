@@ -40,6 +40,7 @@ struct gpk_handle {
     std::vector<cudaEvent_t> ev_panel, ev_rest;
     int lookahead = 1;
     int smalltile = 1;              // 32-row tiles for the panel solve / next-panel update
+    int pdl = 1;                    // programmatic dependent launch on the Cholesky chain
     char err[1024] = {0};
     int loader = LOADER_TMA_WS;
     long chunk = 16384;
@@ -184,11 +185,35 @@ int make_map(gpk_handle* h, CUtensorMap* map, void* base, long rows, long cols, 
 }
 
 // ---- GEMM launch ---------------------------------------------------------------------------
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel's launch latency and prologue
+// overlap the tail of the previous kernel on the stream; the kernels call cudaGridDependencySynchronize().
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int EPI, int MI = 8>
 int launch_gemm(gpk_handle* h, const CUtensorMap& mA, const CUtensorMap& mB, const GemmArgs& a, int njobs,
-                cudaStream_t stream = nullptr) {
+                cudaStream_t stream = nullptr, bool pdl = false) {
     if (njobs <= 0) return GPK_OK;
     if (stream == nullptr) stream = h->stream;
+    if (pdl && h->pdl && h->loader != LOADER_CPASYNC && MI == 2) {
+        CK(launch_pdl(gpk_gemm_nt_kernel<EPI, LOADER_TMA, MI>, dim3(njobs), dim3(GEMM_THREADS),
+                      (size_t)gemm_smem_bytes(LOADER_TMA, MI), stream, mA, mB, a));
+        h->launches_total += 1;
+        return GPK_OK;
+    }
     if (h->loader == LOADER_TMA_WS && MI == 8)
         gpk_gemm_ws_kernel<EPI><<<njobs, WS_THREADS, GEMM_SMEM_TMA, stream>>>(mA, mB, a);
     else if (h->loader != LOADER_CPASYNC)
@@ -644,6 +669,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->mapVt_rows = 0;
         return GPK_OK;
     }
+    if (!strcmp(key, "pdl")) {
+        if (value != 0 && value != 1) BAD("pdl must be 0 or 1");
+        h->pdl = (int)value;
+        return GPK_OK;
+    }
     if (!strcmp(key, "overlap")) {
         if (value != 0 && value != 1) BAD("overlap must be 0 or 1");
         h->overlap = (int)value;
@@ -819,7 +849,10 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
     }
     std::vector<char> rest_recorded(nb, 0);
     for (int k = 0; k < nb; ++k) {
-        if (h->diag_kernel == 2)
+        if (h->diag_kernel == 2 && h->pdl && k > 0)
+            CK(launch_pdl(gpk_potrf_diag_fused_kernel, dim3(1), dim3(256), (size_t)DIAG2_SMEM, h->stream, K, (long)NP, k,
+                          ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status), ptr<double>(h->logdet_part)));
+        else if (h->diag_kernel == 2)
             gpk_potrf_diag_fused_kernel<<<1, 256, DIAG2_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
                                                                            ptr<int>(h->status), ptr<double>(h->logdet_part));
         else
@@ -836,7 +869,7 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         a.status = ptr<int>(h->status);
         if (h->smalltile) {
             a.jobs = ptr<GemmJob>(h->jobs) + h->trsm32_r[k].off;
-            if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapP, a, h->trsm32_r[k].cnt))) return rc;
+            if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapP, a, h->trsm32_r[k].cnt, nullptr, true))) return rc;
         } else {
             a.jobs = ptr<GemmJob>(h->jobs) + h->trsm_r[k].off;
             if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapP, a, h->trsm_r[k].cnt))) return rc;
@@ -862,7 +895,7 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
             if (k >= 1 && rest_recorded[k - 1]) CK(cudaStreamWaitEvent(h->stream, h->ev_rest[k - 1], 0));
             if (h->smalltile) {
                 s.jobs = ptr<GemmJob>(h->jobs) + h->pu32_r[k].off;
-                if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapK, s, h->pu32_r[k].cnt))) return rc;
+                if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapK, s, h->pu32_r[k].cnt, nullptr, true))) return rc;
             } else {
                 s.jobs = ptr<GemmJob>(h->jobs) + off;
                 if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, npu))) return rc;

@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const GemmArgs g)
 {
+    // Programmatic dependent launch: when launched with the stream-serialization attribute this CTA may
+    // start while the producing kernel drains; nothing is read before the dependency is resolved.
+    cudaGridDependencySynchronize();
     if (g.status != nullptr && *g.status != 0) return;
     static_assert(MI == 8 || MI == 4 || MI == 2, "tile height 128, 64 or 32");
     static_assert(EPI == EPI_STORE || MI == 8, "column-reduce epilogue uses full tiles");

@@ -323,6 +323,7 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
     __shared__ int s_bad;
 
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    cudaGridDependencySynchronize();      // programmatic dependent launch (see gpk_gemm_nt_kernel)
     if (*status != 0) return;
     if (tid == 0) s_bad = 0;
 
