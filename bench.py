@@ -55,7 +55,10 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.lines, self.proc, self.gpu = [], None, gpu_index
+        self.lines, self.proc, self.gpu, self.t_timed = [], None, gpu_index, None
+
+    def mark_timed_region(self):
+        self.t_timed = time.time()
 
     def start(self):
         try:
@@ -68,7 +71,7 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -76,7 +79,8 @@ class ClockSampler(object):
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        timed = [ln for t, ln in self.lines if self.t_timed is None or t >= self.t_timed]
+        for ln in (timed if timed else [ln for _, ln in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -211,15 +215,15 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # started before the warm-up so that samples exist even for short timed regions
     for _ in range(args.warmup):
         step_dev()
     launches0 = h.timings()["launches_total"]
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_timed_region()
     e0.record(stream)
     for _ in range(args.steps):
         step_dev()
