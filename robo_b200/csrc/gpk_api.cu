@@ -821,6 +821,7 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         if (h->spec.axis[t] >= h->d) BAD("gpk_fit: kernel axis %d >= d = %d", h->spec.axis[t], h->d);
     const long NP = h->NP;
     const int nb = h->nb;
+    if (!h->maps_ok && (rc = rebuild_maps(h))) return rc;        // staging mode changed after gpk_set_data
     h->fitted = false;
     h->linv_ready = false;
     h->alpha_ready = false;

@@ -80,3 +80,23 @@ def sharded_argmax(model, acq_kind, X_all, rank, world, eta=None, par=0.0, group
         val, idx = 0.0, -1
     dev = "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cpu"
     return allgather_best(pack_pair(val, idx, dev), group)
+
+
+def sharded_loglik(eval_fn, thetas, rank, world, group=None):
+    """Hyper-parameter vectors are independent too (SURVEY.md section 8e "other shardable axes": MCMC walkers,
+    theta sweeps): rank r evaluates the contiguous slice of ``thetas`` it owns with ``eval_fn(theta_block) ->
+    values`` and one all_gather of the values (8 bytes per theta) gives every rank the full vector."""
+    import torch
+    import torch.distributed as dist
+    thetas = np.asarray(thetas, dtype=np.float64)
+    n = len(thetas)
+    per = (n + world - 1) // world                     # equal-sized slots so that all_gather_into_tensor applies
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    mine = np.full(per, np.nan)
+    if hi > lo:
+        mine[:hi - lo] = np.asarray(eval_fn(thetas[lo:hi]), dtype=np.float64)
+    dev = "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() and dist.get_backend(group) == "nccl" else "cpu"
+    out = torch.empty(per * world, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, torch.from_numpy(mine).to(dev), group=group)
+    host = out.cpu().numpy()
+    return np.concatenate([host[r * per:r * per + max(0, min(per, n - r * per))] for r in range(world)])

@@ -44,6 +44,29 @@ def test_merge_matches_numpy_argmax():
         assert idx == int(np.argmax(vals))
 
 
+def _worker_thetas(rank, world, port, thetas, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from robo_b200.distributed import sharded_loglik
+        vals = sharded_loglik(lambda th: -np.sum(th ** 2, axis=1), thetas, rank, world)
+        out[rank] = vals.tolist()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_theta_evaluation_gloo_world2():
+    thetas = np.random.RandomState(2).randn(7, 3)          # 7 thetas over 2 ranks: uneven split
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_thetas, args=(2, _free_port(), thetas, out), nprocs=2, join=True)
+    ref = -np.sum(thetas ** 2, axis=1)
+    np.testing.assert_allclose(out[0], ref)
+    np.testing.assert_allclose(out[1], ref)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
