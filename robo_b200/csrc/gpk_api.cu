@@ -235,7 +235,6 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
-    CK(cudaFuncSetAttribute(gpk_potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG4_SMEM));
     return GPK_OK;
 }
 
@@ -691,7 +690,7 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         return GPK_OK;
     }
     if (!strcmp(key, "diag")) {
-        if (value != 0 && value != 2 && value != 4) BAD("diag must be 4 (blocked), 2 (register-tiled fused) or 0 (simple shared-memory kernel)");
+        if (value != 0 && value != 2) BAD("diag must be 2 (register-tiled fused kernel) or 0 (simple shared-memory kernel)");
         h->diag_kernel = (int)value;
         return GPK_OK;
     }
@@ -851,13 +850,7 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
     }
     std::vector<char> rest_recorded(nb, 0);
     for (int k = 0; k < nb; ++k) {
-        if (h->diag_kernel == 4 && (!h->pdl || k == 0))
-            gpk_potrf_diag_blocked_kernel<<<1, 256, DIAG4_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
-                                                                             ptr<int>(h->status), ptr<double>(h->logdet_part));
-        else if (h->diag_kernel == 4)
-            CK(launch_pdl(gpk_potrf_diag_blocked_kernel, dim3(1), dim3(256), (size_t)DIAG4_SMEM, h->stream, K, (long)NP, k,
-                          ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status), ptr<double>(h->logdet_part)));
-        else if (h->diag_kernel == 2 && h->pdl && k > 0)
+        if (h->diag_kernel == 2 && h->pdl && k > 0)
             CK(launch_pdl(gpk_potrf_diag_fused_kernel, dim3(1), dim3(256), (size_t)DIAG2_SMEM, h->stream, K, (long)NP, k,
                           ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status), ptr<double>(h->logdet_part)));
         else if (h->diag_kernel == 2)

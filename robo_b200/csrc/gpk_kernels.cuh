@@ -398,250 +398,6 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
 }
 
 // ---------------------------------------------------------------------------------------
-// Diagonal block, blocked version (diag = 4): the 128 x 128 block lives in shared memory and is processed
-// in eight 16-column panels, so that the sequential pivot chain (16 steps per panel) runs inside ONE warp
-// with shuffles (no block barrier per pivot) and everything else is data-parallel:
-//   per panel   (a) warp 0 factors the 16 x 16 diagonal sub-block (registers + shuffles)
-//               (b) one thread per row solves the panel rows against it (16-step substitution)
-//               (c) all threads apply the rank-16 trailing update with 4 x 4 register tiles
-//   then        (d) the eight 16 x 16 sub-block inverses, one warp each
-//               (e) in-place right-looking block inversion  L -> L^-1  (rank-16 updates again)
-// 24 + 16 block barriers instead of 128.  Same contract as gpk_potrf_diag_kernel.
-// ---------------------------------------------------------------------------------------
-constexpr int LDT = 129;
-constexpr int DIAG4_SMEM = (128 * LDT + 16 * 128 + 16 * 17 + 8 * 16 * 17 + 128 + 16 + 16 * 128) * 8;
-
-__device__ __forceinline__ void tri_decode(int q, int& ti, int& tj)      // q -> (ti, tj), tj <= ti
-{
-    int t = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-    while ((t + 1) * (t + 2) / 2 <= q) ++t;
-    while (t * (t + 1) / 2 > q) --t;
-    ti = t;
-    tj = q - t * (t + 1) / 2;
-}
-
-__global__ void __launch_bounds__(256, 1)
-gpk_potrf_diag_blocked_kernel(double* __restrict__ K, long ld, int kb,
-                              double* __restrict__ P, double* __restrict__ Q, long ldp,
-                              int* __restrict__ status, double* __restrict__ logdet_part)
-{
-    extern __shared__ double dsm[];
-    double* T = dsm;                          // [128][LDT]  the block: A -> L -> L^-1
-    double* PanT = T + 128 * LDT;             // [16][128]   current panel, k-major
-    double* L16 = PanT + 16 * 128;            // [16][17]    diagonal sub-block of the current panel
-    double* I16 = L16 + 16 * 17;              // [8][16][17] inverses of the eight diagonal sub-blocks
-    double* ldiag = I16 + 8 * 16 * 17;        // [128]       diagonal of L
-    double* rs16 = ldiag + 128;               // [16]        1 / diag of the current sub-block
-    double* Xrow = rs16 + 16;                 // [16][128]   staging of one row block during the inversion
-    __shared__ int s_bad;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    cudaGridDependencySynchronize();
-    if (*status != 0) return;
-    if (tid == 0) s_bad = 0;
-
-    double* Kt = K + (long)kb * 128 * ld + (long)kb * 128;
-    for (int e = tid; e < 128 * 128; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        T[r * LDT + c] = Kt[(long)r * ld + c];
-    }
-    __syncthreads();
-
-    // ============================ factorisation ============================
-    for (int jb = 0; jb < 8; ++jb) {
-        const int c0 = 16 * jb;
-        // (a) 16 x 16 diagonal sub-block in warp 0: lane r (and its mirror r + 16) holds row r
-        if (warp == 0) {
-            const int r = lane & 15;
-            double a[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) a[k] = (k <= r) ? T[(c0 + r) * LDT + c0 + k] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                double d = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(d > 0.0) || isinf(d)) {
-                    if (lane == 0 && s_bad == 0) s_bad = kb * 128 + c0 + j + 1;
-                    d = 1.0;
-                }
-                const double rs = rsqrt(d);
-                const double lj = (r == j) ? d * rs : a[j] * rs;
-                a[j] = lj;
-                if (lane == j) rs16[j] = rs;
-#pragma unroll
-                for (int c = j + 1; c < 16; ++c) {
-                    const double lc = __shfl_sync(0xffffffffu, lj, c);
-                    if (r >= c) a[c] = fma(-lj, lc, a[c]);
-                }
-            }
-            if (lane < 16) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const double v = (k <= r) ? a[k] : 0.0;
-                    T[(c0 + r) * LDT + c0 + k] = v;
-                    L16[r * 17 + k] = v;
-                }
-                ldiag[c0 + r] = a[r];
-            }
-        }
-        __syncthreads();
-        // (b) panel rows below: x L16^T = a  (one thread per row)
-        {
-            const int i = c0 + 16 + tid;
-            if (i < 128) {
-                double x[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) x[c] = T[i * LDT + c0 + c];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    double sacc = x[c];
-#pragma unroll
-                    for (int k = 0; k < c; ++k) sacc = fma(-x[k], L16[c * 17 + k], sacc);
-                    x[c] = sacc * rs16[c];
-                }
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    T[i * LDT + c0 + c] = x[c];
-                    PanT[c * 128 + i] = x[c];
-                }
-            }
-        }
-        __syncthreads();
-        // (c) rank-16 trailing update, 4 x 4 tiles over the lower triangle of rows/cols >= t0
-        {
-            const int t0 = c0 + 16, nt = (128 - t0) / 4, ntiles = nt * (nt + 1) / 2;
-            for (int q = tid; q < ntiles; q += 256) {
-                int ti, tj;
-                tri_decode(q, ti, tj);
-                const int i0 = t0 + 4 * ti, j0 = t0 + 4 * tj;
-                double acc[4][4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(PanT + k * 128 + i0);
-                    const double2 a23 = *reinterpret_cast<const double2*>(PanT + k * 128 + i0 + 2);
-                    const double2 b01 = *reinterpret_cast<const double2*>(PanT + k * 128 + j0);
-                    const double2 b23 = *reinterpret_cast<const double2*>(PanT + k * 128 + j0 + 2);
-                    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-                    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) T[(i0 + r) * LDT + j0 + c] -= acc[r][c];
-            }
-        }
-        __syncthreads();
-    }
-    // ---- L out (lower, upper zeroed), log-det, status ----
-    for (int e = tid; e < 128 * 128; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        Kt[(long)r * ld + c] = (c <= r) ? T[r * LDT + c] : 0.0;
-    }
-    if (tid < 32) {
-        double sl = 0.0;
-        for (int q = tid; q < 128; q += 32) sl += log(ldiag[q]);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, off);
-        if (tid == 0) {
-            logdet_part[kb] = sl;
-            if (s_bad != 0) atomicCAS(status, 0, s_bad);
-        }
-    }
-    // ============================ inversion ============================
-    // (d) inverses of the eight 16 x 16 diagonal sub-blocks: warp w, lane c < 16 -> column c (forward substitution)
-    if (lane < 16) {
-        const int c0 = 16 * warp, c = lane;
-        double* Iw = I16 + warp * 16 * 17;
-        for (int i = 0; i < c; ++i) Iw[i * 17 + c] = 0.0;
-        Iw[c * 17 + c] = 1.0 / T[(c0 + c) * LDT + c0 + c];
-        for (int i = c + 1; i < 16; ++i) {
-            double sacc = 0.0;
-            for (int k = c; k < i; ++k) sacc = fma(T[(c0 + i) * LDT + c0 + k], Iw[k * 17 + c], sacc);
-            Iw[i * 17 + c] = -sacc / T[(c0 + i) * LDT + c0 + i];
-        }
-    }
-    __syncthreads();
-    // (e) in place, row block by row block:  X[jb][:] = inv16_jb R[jb][:] ;  R[i][:] -= L[i][jb] X[jb][:]  (i > jb)
-    for (int jb = 0; jb < 8; ++jb) {
-        const int c0 = 16 * jb;
-        const double* Ij = I16 + jb * 16 * 17;
-        // (e1) the row block: columns 0 .. c0-1 hold R[jb][:], the diagonal sub-block becomes inv16_jb
-        for (int e = tid; e < 16 * (c0 + 16); e += 256) {
-            const int r = e / (c0 + 16), c = e - r * (c0 + 16);
-            double v;
-            if (c >= c0) {
-                v = (c - c0 <= r) ? Ij[r * 17 + (c - c0)] : 0.0;
-            } else {
-                double sacc = 0.0;
-                for (int k = 0; k <= r; ++k) sacc = fma(Ij[r * 17 + k], T[(c0 + k) * LDT + c], sacc);
-                v = sacc;
-            }
-            Xrow[r * 128 + c] = v;
-        }
-        // panel of L below the row block, k-major, before it is overwritten
-        for (int e = tid; e < 16 * (128 - c0 - 16); e += 256) {
-            const int k = e / (128 - c0 - 16), i = c0 + 16 + (e - k * (128 - c0 - 16));
-            PanT[k * 128 + i] = T[i * LDT + c0 + k];
-        }
-        __syncthreads();
-        for (int e = tid; e < 16 * (c0 + 16); e += 256) {
-            const int r = e / (c0 + 16), c = e - r * (c0 + 16);
-            T[(c0 + r) * LDT + c] = Xrow[r * 128 + c];
-        }
-        // (e2) rows below: T[i][c] = (c < c0 ? T[i][c] : 0) - sum_k L[i][c0+k] X[jb][k][c], c < c0 + 16; 4 x 4 tiles
-        {
-            const int t0 = c0 + 16, nr = (128 - t0) / 4, nc = (c0 + 16) / 4, ntiles = nr * nc;
-            for (int q = tid; q < ntiles; q += 256) {
-                const int ti = q / nc, tj = q - ti * nc;
-                const int i0 = t0 + 4 * ti, j0 = 4 * tj;
-                double acc[4][4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(PanT + k * 128 + i0);
-                    const double2 a23 = *reinterpret_cast<const double2*>(PanT + k * 128 + i0 + 2);
-                    const double2 b01 = *reinterpret_cast<const double2*>(Xrow + k * 128 + j0);
-                    const double2 b23 = *reinterpret_cast<const double2*>(Xrow + k * 128 + j0 + 2);
-                    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-                    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int cc = j0 + c;
-                        const double base = (cc < c0) ? T[(i0 + r) * LDT + cc] : 0.0;
-                        T[(i0 + r) * LDT + cc] = base - acc[r][c];
-                    }
-            }
-        }
-        __syncthreads();
-    }
-    // ---- L^-1 out: P (lower) and Q = P^T (upper) ----
-    double* Pt = P + (long)kb * 128 * ldp + (long)kb * 128;
-    double* Qt = Q + (long)kb * 128 * ldp + (long)kb * 128;
-    for (int e = tid; e < 128 * 128; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        Pt[(long)r * ldp + c] = (c <= r) ? T[r * LDT + c] : 0.0;
-        Qt[(long)r * ldp + c] = (c >= r) ? T[c * LDT + r] : 0.0;
-    }
-}
-
-// ---------------------------------------------------------------------------------------
 // Scoring epilogue: sum the per-row-block partials in fixed order, finish mean / variance,
 // apply the output transform + clip (gaussian_process.py:282-294), the acquisition closed form,
 // and a per-block arg-max with numpy.argmax tie-breaking.
