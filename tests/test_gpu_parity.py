@@ -65,6 +65,37 @@ def test_kernel_matrix_matches_oracle(family, D):
     np.testing.assert_allclose(sym, oracle_kernel(family, theta, D).get_value(X1), rtol=1e-13)
 
 
+def test_matern32_and_isotropic_kernels():
+    """the remaining george kernel shapes RoBO can build: Matern-3/2, and an isotropic metric (one
+    parameter for all axes): values, log-likelihood, posterior and the gradient mapping (the isotropic
+    parameter collects the per-axis terms)."""
+    from robo_b200 import kernels as K
+    from robo_b200.models.gaussian_process import GaussianProcess
+    rng = np.random.RandomState(8)
+    X, Xs = rng.rand(90, 3), rng.rand(40, 3)
+    y = np.cos(4 * X).sum(axis=1)
+    for make_p, make_o in (
+            (lambda: K.Product(K.ConstantKernel(0.4, ndim=3), K.Matern32Kernel(np.array([0.5, 0.2, 1.1]), ndim=3)),
+             lambda: G.Product(G.ConstantKernel(0.4, ndim=3), G.Matern32Kernel(np.array([0.5, 0.2, 1.1]), ndim=3))),
+            (lambda: 1.5 * K.ExpSquaredKernel(0.3, ndim=3), lambda: 1.5 * G.ExpSquaredKernel(0.3, ndim=3)),
+            (lambda: K.Matern52Kernel(0.7, ndim=3), lambda: G.Matern52Kernel(0.7, ndim=3))):
+        kp, ko = make_p(), make_o()
+        np.testing.assert_allclose(kp.get_parameter_vector(), ko.get_parameter_vector())
+        np.testing.assert_allclose(kp.get_value(Xs, X), ko.get_value(Xs, X), rtol=1e-13, atol=1e-300)
+        model = GaussianProcess(kp, noise=1e-3, normalize_input=False)
+        model.train(X, y, do_optimize=False)
+        st = O.gp_fit(ko, X, y, noise=1e-3, normalize_input=False)
+        mu, var = model.predict(Xs)
+        mu_ref, var_ref = O.gp_predict(st, Xs)
+        assert_mean_close(mu, mu_ref, y)
+        assert_var_close(var, var_ref, float(ko.get_value(X[:1])[0, 0]))
+        theta = np.append(kp.get_parameter_vector(), np.log(1e-3))
+        g = model.grad_nll(theta)
+        g_ref = O.gp_grad_nll_correct(st, theta)
+        assert g.shape == g_ref.shape
+        np.testing.assert_allclose(g, g_ref, rtol=1e-8, atol=1e-8 * np.abs(g_ref).max())
+
+
 # --------------------------------------------------------------------------- factorisation
 @pytest.mark.parametrize("N,D", [(10, 2), (127, 3), (128, 3), (129, 4), (300, 8), (700, 16)])
 def test_cholesky_forward_solve_logdet(N, D, loader):
