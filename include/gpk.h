@@ -199,6 +199,10 @@ int gpk_get_z(gpk_handle* h, double* z /* n */);
  * out[8] = variance-GEMM launches so far,
  * out[9] = total kernel launches so far. */
 int gpk_get_timings(gpk_handle* h, double* out10);
+/* diagnostics of the blocked diagonal-block kernel (option "diagprof" = 1): clock64() stamps of the last
+ * launched block: out[0] start, out[1] tiles loaded, out[2+2p] panel p factorised + solved, out[3+2p] panel p's
+ * rank-16 update applied and panel p+1 published, out[33] end. */
+int gpk_get_diag_profile(gpk_handle* h, long long* out34);
 
 #ifdef __cplusplus
 }

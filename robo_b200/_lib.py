@@ -54,6 +54,7 @@ _SIGNATURES = {
     "gpk_get_linv": [_vp, _dp],
     "gpk_get_z": [_vp, _dp],
     "gpk_get_timings": [_vp, _dp],
+    "gpk_get_diag_profile": [_vp, C.POINTER(C.c_longlong)],
 }
 
 _lib = None
@@ -314,6 +315,11 @@ class Handle(object):
         z = np.empty(n)
         self._check(self.lib.gpk_get_z(self._h, _as_dp(z)))
         return z
+
+    def diag_profile(self):
+        t = np.zeros(34, dtype=np.int64)
+        self._check(self.lib.gpk_get_diag_profile(self._h, t.ctypes.data_as(C.POINTER(C.c_longlong))))
+        return t
 
     def timings(self):
         t = np.zeros(10)

@@ -20,6 +20,7 @@
 
 #include "gpk_gemm.cuh"
 #include "gpk_kernels.cuh"
+#include "gpk_diag16.cuh"
 
 namespace {
 
@@ -44,7 +45,9 @@ struct gpk_handle {
     char err[1024] = {0};
     int loader = LOADER_TMA_WS;
     long chunk = 16384;
-    int diag_kernel = 2;          // 2 = register-tiled fused factor + invert, 0 = simple shared-memory version (cross-check)
+    int diag_kernel = 2;          // 3 = blocked 16-column panels, 2 = column-by-column register-tiled, 0 = simple shared-memory version
+    int diag_prof = 0;            // 1: the blocked diagonal kernel records clock64() stamps per phase (diagnostics)
+    DevBuf dprof;
 
     // model
     int n = 0, d = 0, NP = 0, nb = 0;
@@ -235,6 +238,7 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
+    CK(cudaFuncSetAttribute(gpk_potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG3_SMEM));
     return GPK_OK;
 }
 
@@ -689,8 +693,18 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->lookahead = (int)value;
         return GPK_OK;
     }
+    if (!strcmp(key, "diagprof")) {
+        h->diag_prof = value != 0;
+        if (h->diag_prof) {
+            int rc = ensure(h, h->dprof, 64 * 8);
+            if (rc) return rc;
+            CK(cudaMemset(h->dprof.p, 0, 64 * 8));
+        }
+        return GPK_OK;
+    }
     if (!strcmp(key, "diag")) {
-        if (value != 0 && value != 2) BAD("diag must be 2 (register-tiled fused kernel) or 0 (simple shared-memory kernel)");
+        if (value != 0 && value != 2 && value != 3)
+            BAD("diag must be 3 (blocked 16-column panels), 2 (column-by-column register-tiled kernel) or 0 (simple shared-memory kernel)");
         h->diag_kernel = (int)value;
         return GPK_OK;
     }
@@ -850,7 +864,14 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
     }
     std::vector<char> rest_recorded(nb, 0);
     for (int k = 0; k < nb; ++k) {
-        if (h->diag_kernel == 2 && h->pdl && k > 0)
+        long long* dprof = h->diag_prof ? ptr<long long>(h->dprof) : nullptr;
+        if (h->diag_kernel == 3 && h->pdl && k > 0)
+            CK(launch_pdl(gpk_potrf_diag_blocked_kernel, dim3(1), dim3(256), (size_t)DIAG3_SMEM, h->stream, K, (long)NP, k,
+                          ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status), ptr<double>(h->logdet_part), dprof));
+        else if (h->diag_kernel == 3)
+            gpk_potrf_diag_blocked_kernel<<<1, 256, DIAG3_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
+                                                                             ptr<int>(h->status), ptr<double>(h->logdet_part), dprof);
+        else if (h->diag_kernel == 2 && h->pdl && k > 0)
             CK(launch_pdl(gpk_potrf_diag_fused_kernel, dim3(1), dim3(256), (size_t)DIAG2_SMEM, h->stream, K, (long)NP, k,
                           ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status), ptr<double>(h->logdet_part)));
         else if (h->diag_kernel == 2)
@@ -1442,6 +1463,15 @@ int gpk_get_z(gpk_handle* h, double* z) {
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(z, ptr<double>(h->Kbuf) + (long)h->NP * h->NP, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_get_diag_profile(gpk_handle* h, long long* out34) {
+    if (!h || !out34) return GPK_BAD_ARG;
+    if (!h->diag_prof || !h->dprof.p) BAD("gpk_get_diag_profile: set option diagprof = 1 first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out34, h->dprof.p, 34 * 8, cudaMemcpyDeviceToHost));
     return GPK_OK;
 }
 
