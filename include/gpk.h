@@ -33,7 +33,8 @@ typedef enum {
     GPK_NOT_PD = 1,        /* Cholesky pivot <= 0 or NaN: numpy.linalg.LinAlgError in the reference */
     GPK_BAD_ARG = 2,
     GPK_CUDA_ERROR = 3,
-    GPK_NOT_FITTED = 4
+    GPK_NOT_FITTED = 4,
+    GPK_NOT_APPLICABLE = 5 /* gpk_fit_append: preconditions not met, nothing was changed; do a full fit */
 } gpk_status;
 
 /* stationary radial families, george names (oracle/george_oracle.py) */
@@ -110,6 +111,15 @@ int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double*
  * (gaussian_process_mcmc.py:168-202) is served for a half-ensemble of emcee walkers per step. */
 int gpk_fit_begin(gpk_handle* h, double diag_add, double mean);
 int gpk_fit_end(gpk_handle* h, double* logdet, double* loglik);
+
+/* Incremental refit after rows were appended (robo/models/base_model.py:30-45 `update`, and
+ * robo/solver/bayesian_optimization.py:161-167 train(do_optimize=False) when hyper-parameters are frozen).
+ * X (n x d) and y (n) are the full new training set; its first rows must be the ones of the last fit, the kernel
+ * and diag_add unchanged.  Requires a fitted handle whose L^-1 has been built (any predict / acq call) and the new
+ * rows to fall into the last 128-row block of the padded layout; otherwise returns GPK_NOT_APPLICABLE without
+ * touching the model.  O(N^2): only the last block row of the factor and of its inverse is recomputed. */
+int gpk_fit_append(gpk_handle* h, const double* X, const double* y, int n, int d, double diag_add, double mean,
+                   double* logdet, double* loglik);
 
 /* ---- posterior + acquisition over a candidate batch -------------------------------- */
 /* Replaces george GP.predict + np.diag + clip (gaussian_process.py:276-294):
@@ -201,8 +211,8 @@ int gpk_get_z(gpk_handle* h, double* z /* n */);
 int gpk_get_timings(gpk_handle* h, double* out10);
 /* diagnostics of the blocked diagonal-block kernel (option "diagprof" = 1): clock64() stamps of the last
  * launched block: out[0] start, out[1] tiles loaded, out[2+2p] panel p factorised + solved, out[3+2p] panel p's
- * rank-16 update applied and panel p+1 published, out[33] end. */
-int gpk_get_diag_profile(gpk_handle* h, long long* out34);
+ * rank-16 update applied and panel p+1 published, out[33] end, out[34..41] finer stamps inside panel 3. */
+int gpk_get_diag_profile(gpk_handle* h, long long* out64);
 
 #ifdef __cplusplus
 }

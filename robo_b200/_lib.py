@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _build
 
-GPK_OK, GPK_NOT_PD, GPK_BAD_ARG, GPK_CUDA_ERROR, GPK_NOT_FITTED = range(5)
+GPK_OK, GPK_NOT_PD, GPK_BAD_ARG, GPK_CUDA_ERROR, GPK_NOT_FITTED, GPK_NOT_APPLICABLE = range(6)
 MATERN52, EXPSQUARED, MATERN32 = 0, 1, 2
 ACQ_NONE, ACQ_EI, ACQ_LOG_EI, ACQ_PI, ACQ_LCB = range(5)
 ACQ_KIND = {"ei": ACQ_EI, "log_ei": ACQ_LOG_EI, "pi": ACQ_PI, "lcb": ACQ_LCB, "none": ACQ_NONE}
@@ -37,6 +37,7 @@ _SIGNATURES = {
     "gpk_fit": [_vp, C.c_double, C.c_double, _dp, _dp],
     "gpk_fit_begin": [_vp, C.c_double, C.c_double],
     "gpk_fit_end": [_vp, _dp, _dp],
+    "gpk_fit_append": [_vp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp],
     "gpk_predict": [_vp, _dp, C.c_long, _dp, _dp],
     "gpk_predict_cov": [_vp, _dp, C.c_long, _dp, _dp],
     "gpk_acq": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _lp, _lp],
@@ -186,6 +187,19 @@ class Handle(object):
         self._check(self.lib.gpk_fit(self._h, float(diag_add), float(mean), C.byref(logdet), C.byref(ll)))
         return logdet.value, ll.value
 
+    def fit_append(self, X, y, diag_add, mean):
+        """Incremental refit after rows were appended (gpk_fit_append).  Returns (logdet, loglik), or None when the
+        library reports that the shortcut does not apply (the model is untouched: run set_data + fit)."""
+        X, y = f64(X), f64(y)
+        n, d = X.shape
+        logdet, ll = C.c_double(), C.c_double()
+        rc = self.lib.gpk_fit_append(self._h, _as_dp(X), _as_dp(y), n, d, float(diag_add), float(mean),
+                                     C.byref(logdet), C.byref(ll))
+        if rc == GPK_NOT_APPLICABLE:
+            return None
+        self._check(rc)
+        return logdet.value, ll.value
+
     def fit_begin(self, diag_add, mean):
         self._check(self.lib.gpk_fit_begin(self._h, float(diag_add), float(mean)))
 
@@ -317,7 +331,7 @@ class Handle(object):
         return z
 
     def diag_profile(self):
-        t = np.zeros(34, dtype=np.int64)
+        t = np.zeros(64, dtype=np.int64)
         self._check(self.lib.gpk_get_diag_profile(self._h, t.ctypes.data_as(C.POINTER(C.c_longlong))))
         return t
 

@@ -45,7 +45,7 @@ struct gpk_handle {
     char err[1024] = {0};
     int loader = LOADER_TMA_WS;
     long chunk = 16384;
-    int diag_kernel = 2;          // 3 = blocked 16-column panels, 2 = column-by-column register-tiled, 0 = simple shared-memory version
+    int diag_kernel = 3;          // 3 = blocked 16-column panels (default), 2 = column-by-column register-tiled, 0 = simple shared-memory version
     int diag_prof = 0;            // 1: the blocked diagonal kernel records clock64() stamps per phase (diagnostics)
     DevBuf dprof;
 
@@ -74,6 +74,7 @@ struct gpk_handle {
     // job tables
     std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r, trsm32_r, pu32_r;
     Range kinv_r;
+    Range app_row_r, app_syrk_r, app_t_r, app_p_r;      // gpk_fit_append (last block row only)
 
     // tensor maps
     CUtensorMap mapK, mapP, mapQ, mapW, mapKs, mapVt;
@@ -327,6 +328,32 @@ int build_job_tables(gpk_handle* h) {
             jobs.push_back({i * BM, j * BM, i * BM, nb * BM, i * BM, j * BM, 0, 0});
     std::stable_sort(jobs.begin() + h->kinv_r.off, jobs.end(), by_len);
     h->kinv_r.cnt = (int)jobs.size() - h->kinv_r.off;
+    // gpk_fit_append: only block row b = nb-1 changes.  N1 = b*128 leading rows keep their factor L11 and inverse P11.
+    {
+        const int b = nb - 1, N1 = b * BM;
+        // L_row = K[b, 0:N1] P11^T, 32-row tiles (the contraction is up to N1 long: more, shorter CTAs)
+        h->app_row_r.off = (int)jobs.size();
+        for (int j = b - 1; j >= 0; --j)
+            for (int q = 0; q < 4; ++q)
+                jobs.push_back({N1 + 32 * q, j * BM, 0, (j + 1) * BM, N1 + 32 * q, j * BM, 0, 0});
+        h->app_row_r.cnt = (int)jobs.size() - h->app_row_r.off;
+        // partial Gram tiles  T_s = L_row[:, s] L_row[:, s]^T  into the free tiles (s, b) of W; summed in fixed order
+        h->app_syrk_r.off = (int)jobs.size();
+        for (int sblk = 0; sblk < b; ++sblk)
+            jobs.push_back({N1, N1, sblk * BM, (sblk + 1) * BM, sblk * BM, N1, 0, 0});
+        h->app_syrk_r.cnt = (int)jobs.size() - h->app_syrk_r.off;
+        // T = L_row P11 (= L_row Q11^T in NT form), 32-row tiles, stored to P[b, :] and transposed to Q[:, b]
+        h->app_t_r.off = (int)jobs.size();
+        for (int j = 0; j < b; ++j)
+            for (int q = 0; q < 4; ++q)
+                jobs.push_back({N1 + 32 * q, j * BM, j * BM, N1, N1 + 32 * q, j * BM, 0, 0});
+        h->app_t_r.cnt = (int)jobs.size() - h->app_t_r.off;
+        // P[b, j] = -P_bb T[:, j]
+        h->app_p_r.off = (int)jobs.size();
+        for (int j = 0; j < b; ++j)
+            jobs.push_back({N1, j * BM, N1, nb * BM, N1, j * BM, 0, 0});
+        h->app_p_r.cnt = (int)jobs.size() - h->app_p_r.off;
+    }
     if (jobs.empty()) jobs.push_back({0, 0, 0, 0, 0, 0, 0, 0});
     int rc = ensure(h, h->jobs, jobs.size() * sizeof(GemmJob));
     if (rc) return rc;
@@ -419,6 +446,28 @@ __global__ void gpk_mu_finish_kernel(double* __restrict__ mu, long m, double mea
     double v = mu[c] + mean;
     if (norm_out) v = v * y_std + y_mean;
     mu[c] = v;
+}
+
+// gpk_fit_append helpers -------------------------------------------------------------------
+// diagonal of the rows [i0, NP): += diag_add for training rows, unit diagonal on padding rows
+__global__ void gpk_kfix_rows_kernel(double* __restrict__ K, long ld, int n, int NP, double diag_add, int i0) {
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP) return;
+    K[(long)i * ld + i] = (i < n) ? K[(long)i * ld + i] + diag_add : 1.0;
+}
+
+// K[b,b] -= sum_s T_s with T_s = W tile (s, b), s ascending (deterministic); one thread per element
+__global__ void gpk_append_schur_kernel(double* __restrict__ K, const double* __restrict__ W, long ld, int N1, int nparts) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;         // 0 .. 128*128-1
+    const int i = e >> 7, c = e & 127;
+    double acc = 0.0;
+    for (int sblk = 0; sblk < nparts; ++sblk) acc += W[(long)(sblk * 128 + i) * ld + N1 + c];
+    K[(long)(N1 + i) * ld + N1 + c] -= acc;
+}
+
+__global__ void gpk_resid_kernel(const double* __restrict__ y, double mean, int n, int NP, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NP) out[i] = (i < n) ? y[i] - mean : 0.0;
 }
 
 int require(gpk_handle* h, bool data, bool spec, bool fitted) {
@@ -863,6 +912,10 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         h->ev_rest.push_back(e2);
     }
     std::vector<char> rest_recorded(nb, 0);
+    if (h->diag_kernel == 3) {
+        gpk_diag_prezero_kernel<<<nb, 256, 0, h->stream>>>(K, (long)NP);
+        CKL();
+    }
     for (int k = 0; k < nb; ++k) {
         long long* dprof = h->diag_prof ? ptr<long long>(h->dprof) : nullptr;
         if (h->diag_kernel == 3 && h->pdl && k > 0)
@@ -931,6 +984,10 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
             }
         }
     }
+    if (h->diag_kernel == 3) {
+        gpk_diag_qfill_kernel<<<nb, 256, 0, h->stream>>>(ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status));
+        CKL();
+    }
     CK(cudaEventRecord(h->ev[2], h->stream));
     gpk_fit_reduce_kernel<<<1, 256, 0, h->stream>>>(K + NP * NP, h->n, ptr<double>(h->logdet_part), nb,
                                                     ptr<double>(h->scal));
@@ -968,6 +1025,144 @@ int gpk_fit(gpk_handle* h, double diag_add, double mean, double* logdet, double*
     int rc = gpk_fit_begin(h, diag_add, mean);
     if (rc) return rc;
     return gpk_fit_end(h, logdet, loglik);
+}
+
+// ---------------------------------------------------------------------------------------
+// Incremental refit (BaseModel.update / train(do_optimize=False) with frozen hyper-parameters).
+// The rows appended since the last fit live in the last 128-row block b of the padded layout, so the leading factor
+// L11 (N1 = 128 b rows), its inverse P11 and every earlier block of K are unchanged.  With L11^-1 explicit:
+//   L_row = K[b, 0:N1] P11^T                      (one launch, 32-row tiles)
+//   S     = K[b, b] - L_row L_row^T               (b partial Gram tiles + fixed-order sum)
+//   L_bb, P_bb = chol / inverse of S              (the diagonal-block kernel)
+//   P[b, 0:N1] = -P_bb (L_row P11)                (two launches; transposes kept in Q)
+//   z = P (y - mean),  log|K| = 2 sum log diag    (y and the mean change with every new observation)
+// O(N^2) work instead of the O(N^3) factorisation + inversion.  Returns GPK_NOT_APPLICABLE (nothing touched) when
+// the preconditions do not hold; the caller then runs gpk_set_data + gpk_fit.
+// ---------------------------------------------------------------------------------------
+int gpk_fit_append(gpk_handle* h, const double* X, const double* y, int n, int d, double diag_add, double mean,
+                   double* logdet, double* loglik) {
+    if (!h) return GPK_BAD_ARG;
+    if (!X || !y || n <= 0 || d <= 0) BAD("gpk_fit_append: need X, y, n > 0, d > 0");
+    const long NP = h->NP;
+    const int nb = h->nb, b = nb - 1, N1 = b * BM;
+    if (!h->has_data || !h->has_spec || !h->fitted || !h->linv_ready || h->fit_pending || d != h->d || nb < 2 ||
+        round_up(n, BM) != NP || n <= h->n || h->n <= N1 || diag_add != h->diag_add) {
+        set_err(h, "gpk_fit_append: not applicable (needs a fitted model with L^-1 built, the same kernel / "
+                   "diagonal term, new rows inside the last 128-row block)");
+        return GPK_NOT_APPLICABLE;
+    }
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if (!h->maps_ok && (rc = rebuild_maps(h))) return rc;
+    double* K = ptr<double>(h->Kbuf);
+    double* P = ptr<double>(h->P);
+    double* Q = ptr<double>(h->Q);
+    double* W = ptr<double>(h->W);
+    if ((rc = ensure(h, h->tmp1, (size_t)NP * 8))) return rc;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    // inputs (everything is re-uploaded: 8 n (d + 1) bytes; the first h->n rows of X must be the ones already fitted)
+    if ((rc = ensure(h, h->Xrow, (size_t)n * d * 8))) return rc;
+    CK(cudaMemcpyAsync(h->Xrow.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->y.p, 0, (size_t)NP * 8, h->stream));
+    CK(cudaMemcpyAsync(h->y.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    {
+        long total = (long)d * NP;
+        gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->Xrow), n, d, nullptr,
+                                                                                    nullptr, ptr<double>(h->Xt), NP);
+        CKL();
+    }
+    // block row b of K (all columns), diagonal term, padding rows
+    {
+        dim3 cg((unsigned)(NP / 128), 4);
+        gpk_cov_kernel<16><<<cg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, n, ptr<double>(h->Xrow) + (long)N1 * d,
+                                                  d, (long)(n - N1), nullptr, nullptr, K + (long)N1 * NP, NP, 0);
+        CKL();
+        gpk_kfix_rows_kernel<<<1, 128, 0, h->stream>>>(K, NP, n, (int)NP, diag_add, N1);
+        CKL();
+    }
+    CK(cudaMemsetAsync(h->status.p, 0, 4, h->stream));
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    GemmArgs a;
+    // L_row -> W[b, 0:N1]
+    memset(&a, 0, sizeof(a));
+    a.A = K; a.lda = NP; a.B = P; a.ldb = NP; a.C = W; a.ldc = NP;
+    a.alpha = 1.0; a.beta = 0; a.job_mode = JOBS_TABLE;
+    a.jobs = ptr<GemmJob>(h->jobs) + h->app_row_r.off;
+    if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapP, a, h->app_row_r.cnt))) return rc;
+    // partial Gram tiles, then the Schur complement of the last block
+    memset(&a, 0, sizeof(a));
+    a.A = W; a.lda = NP; a.B = W; a.ldb = NP; a.C = W; a.ldc = NP;
+    a.alpha = 1.0; a.beta = 0; a.job_mode = JOBS_TABLE;
+    a.jobs = ptr<GemmJob>(h->jobs) + h->app_syrk_r.off;
+    if ((rc = launch_gemm<EPI_STORE>(h, h->mapW, h->mapW, a, h->app_syrk_r.cnt))) return rc;
+    gpk_append_schur_kernel<<<64, 256, 0, h->stream>>>(K, W, NP, N1, b);
+    CKL();
+    // L_row to its final place (rows N1.. of K, columns 0..N1)
+    CK(cudaMemcpy2DAsync(K + (long)N1 * NP, (size_t)NP * 8, W + (long)N1 * NP, (size_t)NP * 8, (size_t)N1 * 8, BM,
+                         cudaMemcpyDeviceToDevice, h->stream));
+    // factor + invert the last diagonal block
+    if (h->diag_kernel == 3) {
+        gpk_diag_prezero_kernel<<<1, 256, 0, h->stream>>>(K + (long)N1 * NP + N1, (long)NP);
+        CKL();
+        gpk_potrf_diag_blocked_kernel<<<1, 256, DIAG3_SMEM, h->stream>>>(K, NP, b, P, Q, NP, ptr<int>(h->status),
+                                                                         ptr<double>(h->logdet_part), nullptr);
+        CKL();
+        gpk_diag_qfill_kernel<<<1, 256, 0, h->stream>>>(P + (long)N1 * NP + N1, Q + (long)N1 * NP + N1, (long)NP,
+                                                         ptr<int>(h->status));
+    } else if (h->diag_kernel == 2) {
+        gpk_potrf_diag_fused_kernel<<<1, 256, DIAG2_SMEM, h->stream>>>(K, NP, b, P, Q, NP, ptr<int>(h->status),
+                                                                       ptr<double>(h->logdet_part));
+    } else {
+        gpk_potrf_diag_kernel<<<1, 256, DIAG_SMEM, h->stream>>>(K, NP, b, P, Q, NP, ptr<int>(h->status),
+                                                                ptr<double>(h->logdet_part));
+    }
+    CKL();
+    // T = L_row P11 -> P[b, 0:N1], T^T -> Q[0:N1, b]
+    memset(&a, 0, sizeof(a));
+    a.A = K; a.lda = NP; a.B = Q; a.ldb = NP; a.C = P; a.ldc = NP; a.Ct = Q; a.ldct = NP;
+    a.alpha = 1.0; a.beta = 0; a.job_mode = JOBS_TABLE; a.status = ptr<int>(h->status);
+    a.jobs = ptr<GemmJob>(h->jobs) + h->app_t_r.off;
+    if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapQ, a, h->app_t_r.cnt))) return rc;
+    // P[b, 0:N1] = -P_bb T (and its transpose into Q)
+    memset(&a, 0, sizeof(a));
+    a.A = P; a.lda = NP; a.B = Q; a.ldb = NP; a.C = P; a.ldc = NP; a.Ct = Q; a.ldct = NP;
+    a.alpha = -1.0; a.beta = 0; a.job_mode = JOBS_TABLE; a.status = ptr<int>(h->status);
+    a.jobs = ptr<GemmJob>(h->jobs) + h->app_p_r.off;
+    if ((rc = launch_gemm<EPI_STORE>(h, h->mapP, h->mapQ, a, h->app_p_r.cnt))) return rc;
+    // z = P (y - mean) into row NP of K, then z^T z and the log-determinant
+    gpk_resid_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->y), mean, n, (int)NP,
+                                                                          ptr<double>(h->tmp1));
+    CKL();
+    gpk_rowdot_kernel<<<(unsigned)((NP + 7) / 8), 256, 0, h->stream>>>(P, NP, NP, (int)NP, 0, ptr<double>(h->tmp1),
+                                                                       K + NP * NP);
+    CKL();
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    gpk_fit_reduce_kernel<<<1, 256, 0, h->stream>>>(K + NP * NP, n, ptr<double>(h->logdet_part), nb, ptr<double>(h->scal));
+    CKL();
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaMemcpyAsync(h->pin, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin + 2, h->status.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->launches_total += 12;
+    h->fit_timed = true;
+    int st = 0;
+    memcpy(&st, h->pin + 2, 4);
+    if (st != 0) {                      // the block row of K / P is half updated: the model has to be refitted
+        h->fitted = false;
+        h->linv_ready = false;
+        h->alpha_ready = false;
+        h->n = n;
+        set_err(h, "matrix is not positive definite: pivot %d <= 0", st - 1);
+        return GPK_NOT_PD;
+    }
+    h->n = n;
+    h->mean = mean;
+    h->alpha_ready = false;
+    const double ld2 = h->pin[1];
+    const double ll = -0.5 * h->pin[0] - 0.5 * ld2 - 0.5 * (double)n * log(2.0 * M_PI);
+    if (logdet) *logdet = ld2;
+    if (loglik) *loglik = ll;
+    return GPK_OK;
 }
 
 int gpk_acq_dev(gpk_handle* h, const void* d_Xs, long m, int kind, double eta, double par, void* d_out, void* d_mu,
@@ -1466,12 +1661,12 @@ int gpk_get_z(gpk_handle* h, double* z) {
     return GPK_OK;
 }
 
-int gpk_get_diag_profile(gpk_handle* h, long long* out34) {
+int gpk_get_diag_profile(gpk_handle* h, long long* out34) {      // 64 entries
     if (!h || !out34) return GPK_BAD_ARG;
     if (!h->diag_prof || !h->dprof.p) BAD("gpk_get_diag_profile: set option diagprof = 1 first");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(out34, h->dprof.p, 34 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out34, h->dprof.p, 64 * 8, cudaMemcpyDeviceToHost));
     return GPK_OK;
 }
 

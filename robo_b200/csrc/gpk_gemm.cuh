@@ -31,9 +31,12 @@ constexpr int GEMM_SMEM_TMA = RING_TMA + 1024 /*align*/ + 64 /*barriers*/ + 2048
 constexpr int GEMM_SMEM_PAD = RING_PAD + 1024 + 64 + 2048;
 // Tile height is a template parameter: MI = 8 -> 128 rows (throughput tiles), MI = 2 -> 32 rows (the
 // latency-critical panel solve / next-panel update of the Cholesky chain: 4x more CTAs, 1/4 the time each).
+// The 32-row chain tiles contract over K = 128 only (8 k-steps): their ring holds all 8 steps, so every operand
+// load is in flight before the first DMMA instead of trickling through a 4-deep ring (latency, not bandwidth).
+__host__ __device__ constexpr int gemm_nstage(int mi) { return mi == 2 ? 8 : NSTAGE; }
 constexpr int gemm_smem_bytes(int loader, int mi) {
     return mi == 8 ? (loader == LOADER_TMA ? GEMM_SMEM_TMA : GEMM_SMEM_PAD)
-                   : NSTAGE * ((16 * mi + BN) * (loader == LOADER_TMA ? BK : PAD_STRIDE) * 8) + 1024 + 64 + 2048;
+                   : gemm_nstage(mi) * ((16 * mi + BN) * (loader == LOADER_TMA ? BK : PAD_STRIDE) * 8) + 1024 + 64 + 2048;
 }
 
 struct GemmJob {
@@ -150,6 +153,7 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     static_assert(MI == 8 || MI == 4 || MI == 2, "tile height 128, 64 or 32");
     static_assert(EPI == EPI_STORE || MI == 8, "column-reduce epilogue uses full tiles");
     constexpr int TM = 16 * MI;                                          // tile rows (A rows)
+    constexpr int NS = gemm_nstage(MI);                                  // ring depth
     constexpr int HM = TM / 2;                                           // rows per warp row-group
 
     extern __shared__ unsigned char smem_raw[];
@@ -158,7 +162,7 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     constexpr int ROWB = LOADER == LOADER_TMA ? BK * 8 : PAD_STRIDE * 8; // bytes per staged row
     constexpr int A_BYTES = TM * ROWB;
     constexpr int STAGE_BYTES = (TM + BN) * ROWB;
-    constexpr int RING_MIN = NSTAGE * STAGE_BYTES;
+    constexpr int RING_MIN = NS * STAGE_BYTES;
     constexpr int CT_NEED = ((TM * CT_STRIDE * 8 + 1023) / 1024) * 1024;
     constexpr int RING = MI == 8 ? (LOADER == LOADER_TMA ? RING_TMA : RING_PAD)
                                  : RING_MIN;                            // (32/64-row tiles: CT tile fits the ring)
@@ -203,7 +207,7 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (LOADER == LOADER_TMA) {
         if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < NSTAGE; ++s) mbar_init(full_bar + 8 * s, 1);
+            for (int s = 0; s < NS; ++s) mbar_init(full_bar + 8 * s, 1);
             fence_barrier_init();
             fence_proxy_async();
         }
@@ -211,7 +215,7 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
 
     auto issue_load = [&](int kt) {
-        const int s = kt % NSTAGE;
+        const int s = kt % NS;
         const uint32_t st = smem + s * STAGE_BYTES;
         const int kcol = job.k0 + kt * BK;
         if (LOADER == LOADER_TMA) {
@@ -243,7 +247,7 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
     // ---- prologue ----
 #pragma unroll
-    for (int s = 0; s < NSTAGE - 1; ++s) {
+    for (int s = 0; s < NS - 1; ++s) {
         if (s < KT) issue_load(s);
         if (LOADER == LOADER_CPASYNC) cp_async_commit();
     }
@@ -265,15 +269,15 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
     // ---- main loop ----
     for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % NSTAGE;
+        const int s = kt % NS;
         if (LOADER == LOADER_TMA) {
-            const uint32_t parity = (uint32_t)((kt / NSTAGE) & 1);
+            const uint32_t parity = (uint32_t)((kt / NS) & 1);
             while (!mbar_try_wait(full_bar + 8 * s, parity)) { }
         } else {
-            cp_async_wait<NSTAGE - 2>();
+            cp_async_wait<NS - 2>();
         }
         __syncthreads();          // stage s visible to all; everyone is done with stage (kt-1)%NSTAGE
-        if (kt + NSTAGE - 1 < KT) issue_load(kt + NSTAGE - 1);
+        if (kt + NS - 1 < KT) issue_load(kt + NS - 1);
         if (LOADER == LOADER_CPASYNC) cp_async_commit();
 
         const uint32_t st = smem + s * STAGE_BYTES;

@@ -36,6 +36,11 @@ class DeviceGP(object):
         self.computed = False
         self.log_determinant = None
         self._ll = None
+        # incremental refit (gpk_fit_append): what the handle's factorisation was computed for
+        self.incremental = True
+        self._fit_x = None
+        self._fit_sig = None
+        self.n_appends = 0
 
     # ---- handle lifetime: handles do not survive pickling / deepcopy -----------------
     def __getstate__(self):
@@ -46,6 +51,8 @@ class DeviceGP(object):
         was_computed = st["computed"]
         st["computed"] = False
         st["_recompute"] = bool(was_computed)
+        st["_fit_x"] = None
+        st["_fit_sig"] = None
         return st
 
     def __setstate__(self, st):
@@ -57,6 +64,7 @@ class DeviceGP(object):
             self._handle = _lib.Handle(self.device)
             self._data_dirty = True
             self._cfg_dirty = True
+            self._fit_x = None
         return self._handle
 
     def _restore(self):
@@ -104,16 +112,38 @@ class DeviceGP(object):
         if self._x is None or self._y is None:
             raise ValueError("DeviceGP.compute: no training data")
         h = self.handle
+        f = self.kernel.flatten()
+        self._yerr = float(yerr)
+        yerr_tot = np.sqrt(np.float64(self._yerr) ** 2 + np.exp(self.white_noise))
+        diag_add = float(yerr_tot ** 2)
+        sig = (int(f["family"]), float(f["log_amp"]), tuple(int(a) for a in f["axis"]),
+               tuple(int(g) for g in f["group"]), tuple(float(v) for v in np.asarray(f["log_metric"]).ravel()), diag_add)
+        self.computed = False
+        # Rows appended to an already factorised training set with the same kernel and noise (BaseModel.update /
+        # train(do_optimize=False) inside the solver loop): only the last block row of the factor changes.
+        fx = self._fit_x
+        if (self.incremental and self._data_dirty and fx is not None and self._fit_sig == sig
+                and self._x.ndim == 2 and self._x.shape[1] == fx.shape[1] and len(self._x) > len(fx)
+                and np.array_equal(self._x[:len(fx)], fx)):
+            self._push_cfg()
+            self._fit_x = None                       # a failed attempt leaves the handle to be refitted
+            res = h.fit_append(self._x, self._y, diag_add, self.mean)
+            if res is not None:
+                self.log_determinant, self._ll = res
+                self._data_dirty = False
+                self._fit_x = self._x.copy()
+                self.n_appends += 1
+                self.computed = True
+                return
+        self._fit_x = None
         if self._data_dirty:
             h.set_data(self._x, self._y)
             self._data_dirty = False
         self._push_cfg()
-        f = self.kernel.flatten()
         h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
-        self._yerr = float(yerr)
-        yerr_tot = np.sqrt(np.float64(self._yerr) ** 2 + np.exp(self.white_noise))
-        self.computed = False
-        self.log_determinant, self._ll = h.fit(float(yerr_tot ** 2), self.mean)
+        self.log_determinant, self._ll = h.fit(diag_add, self.mean)
+        self._fit_x = self._x.copy()
+        self._fit_sig = sig
         self.computed = True
 
     def log_likelihood(self, y=None, quiet=False):

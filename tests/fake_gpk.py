@@ -23,6 +23,8 @@ class FakeHandle(object):
         self.out = (False, 0.0, 1.0)
         self.fitted = False
         self.n_fits = 0
+        self.n_appends = 0
+        self.linv_built = False
 
     def close(self):
         pass
@@ -54,10 +56,13 @@ class FakeHandle(object):
             sel = group == g
             k = G.Product(k, FAMILIES[int(family)](np.exp(lm[sel]), ndim=D, axes=axis[sel]))
         self.kernel, self.amp, self.fitted = k, float(np.exp(log_amp)), False
+        self.linv_built = False
         self.spec = (int(family), float(log_amp), axis.copy(), group.copy(), lm.copy())
 
     def fit(self, diag_add, mean):
         self.fitted = False
+        self.linv_built = False
+        self.diag_add = diag_add
         self.n_fits += 1
         K = self.kernel.get_value(self.X)
         K[np.diag_indices_from(K)] += diag_add
@@ -71,6 +76,24 @@ class FakeHandle(object):
         ll = -0.5 * self.z @ self.z - 0.5 * logdet - 0.5 * len(self.y) * np.log(2 * np.pi)
         self.fitted = True
         return logdet, ll
+
+    def fit_append(self, X, y, diag_add, mean):
+        """Same preconditions as gpk_fit_append (fitted, L^-1 built by an earlier scoring call, same diagonal term,
+        new rows inside the last 128-row block); the arithmetic is a plain refit."""
+        X, y = np.array(X, dtype=np.float64), np.array(y, dtype=np.float64)
+        n_old, n = len(self.y), len(y)
+        NP = -(-n_old // 128) * 128
+        if (not self.fitted or not self.linv_built or NP < 256 or -(-n // 128) * 128 != NP or n <= n_old
+                or n_old <= NP - 128 or diag_add != self.diag_add):
+            return None
+        assert np.array_equal(X[:n_old], self.X)
+        kernel, amp, spec = self.kernel, self.amp, self.spec
+        self.X, self.y = X, y
+        out = self.fit(diag_add, mean)
+        self.n_fits -= 1
+        self.n_appends += 1
+        self.linv_built = True
+        return out
 
     def fit_begin(self, diag_add, mean):
         try:
@@ -91,6 +114,7 @@ class FakeHandle(object):
     def _moments(self, Xs, full=False):
         if not self.fitted:
             raise RuntimeError("model not fitted")
+        self.linv_built = True
         Xn = self._norm(Xs)
         Ks = self.kernel.get_value(Xn, self.X)
         mu = Ks @ self.alpha + self.mean

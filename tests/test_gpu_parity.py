@@ -126,7 +126,7 @@ def test_cholesky_variants_agree():
     from robo_b200 import _lib
     X, y, _, theta, noise = O.synthetic_problem(600, 5, 1, seed_train=11)
     ref = None
-    for diag, la, st in ((2, 1, 1), (0, 1, 1), (2, 0, 1), (2, 1, 0), (0, 0, 0)):
+    for diag, la, st in ((3, 1, 1), (2, 1, 1), (0, 1, 1), (3, 0, 1), (2, 0, 1), (3, 1, 0), (0, 0, 0)):
         h = _lib.Handle(0)
         h.set_option("diag", diag)
         h.set_option("lookahead", la)
@@ -755,3 +755,91 @@ def test_full_size_properties():
     assert_acq_close(r1["values"][:64], O.acq_ei(mu_ref, var_ref, eta), rtol=1e-8, atol=1e-13)
     ll_ref, logdet_ref = O.gp_loglik_terms(st)
     assert abs(ll - ll_ref) <= 1e-10 * abs(ll_ref) and abs(logdet - logdet_ref) <= 1e-10 * abs(logdet_ref)
+
+
+# --------------------------------------------------------------------------- incremental refit
+@pytest.mark.parametrize("diag", [3, 2])
+def test_fit_append_matches_full_refit_and_oracle(diag):
+    """gpk_fit_append: rows appended inside the last 128-row block.  Against a full refit on the device (factor,
+    inverse, z, log-likelihood) and against the CPU oracle (posterior moments + EI at the north_star tolerances);
+    not-applicable cases leave the model untouched."""
+    from robo_b200 import _lib
+    D = 5
+    X, y, Xs, theta, noise = O.synthetic_problem(700, D, 300, seed_train=21)
+    f = product_kernel("matern52", theta, D).flatten()
+    da = float(np.sqrt(np.float64(np.sqrt(noise)) ** 2 + G.TINY) ** 2)
+
+    def full(n, d_add=da):
+        hh = _lib.Handle(0)
+        hh.set_option("diag", diag)
+        hh.set_data(X[:n], y[:n])
+        hh.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+        return hh, hh.fit(d_add, float(np.mean(y[:n])))
+
+    h, _ = full(650)                                           # NP = 768: rows 640..767 form the last block
+    assert h.fit_append(X[:655], y[:655], da, float(np.mean(y[:655]))) is None      # L^-1 not built yet
+    mu0, var0 = h.predict(Xs)
+    assert h.fit_append(X[:655], y[:655], da * 1.5, float(np.mean(y[:655]))) is None    # other diagonal term
+    assert h.fit_append(X[:650], y[:650], da, float(np.mean(y[:650]))) is None          # nothing appended
+    np.testing.assert_array_equal(h.predict(Xs)[0], mu0)       # untouched by the refusals
+    kss = float(np.exp(theta[0]))
+    for n in (651, 655, 700):                                  # repeated appends; the mean moves every time
+        mean = float(np.mean(y[:n]))
+        res = h.fit_append(X[:n], y[:n], da, mean)
+        assert res is not None
+        hf, (ld_f, ll_f) = full(n)
+        assert abs(res[0] - ld_f) <= 1e-12 * abs(ld_f) and abs(res[1] - ll_f) <= 1e-11 * abs(ll_f)
+        L, Lf = h.get_factor(n), hf.get_factor(n)
+        np.testing.assert_allclose(L, Lf, rtol=0, atol=1e-11 * np.abs(Lf).max())
+        assert np.abs(np.triu(L, 1)).max() == 0.0
+        Li, Lif = h.get_linv(n), hf.get_linv(n)
+        np.testing.assert_allclose(Li, Lif, rtol=0, atol=1e-10 * np.abs(Lif).max())
+        assert np.abs(np.triu(Li, 1)).max() == 0.0
+        np.testing.assert_allclose(h.get_z(n), hf.get_z(n), rtol=0, atol=1e-10 * np.abs(hf.get_z(n)).max())
+        st = O.gp_fit(oracle_kernel("matern52", theta, D), X[:n], y[:n], noise=noise, normalize_input=False)
+        mu_ref, var_ref = O.gp_predict(st, Xs)
+        r = h.acq(Xs, _lib.ACQ_EI, float(np.min(y[:n])), 0.0, want_values=True, want_moments=True)
+        assert_mean_close(r["mu"], mu_ref, y[:n])
+        assert_var_close(r["var"], var_ref, kss)
+        assert_acq_close(r["values"], O.acquisition(st, Xs, "ei"))
+        hf.close()
+    # appended rows that open a new 128-row block: refused, model still the n = 700 one
+    Xb = np.vstack([X, np.random.RandomState(5).rand(100, D)])
+    yb = np.concatenate([y, np.zeros(100)])
+    assert h.fit_append(Xb, yb, da, 0.0) is None
+    assert h.predict(Xs)[0].shape == (300,)
+    # a single block (N <= 128) has nothing to reuse
+    h1, _ = full(100)
+    h1.predict(Xs)
+    assert h1.fit_append(X[:101], y[:101], da, float(np.mean(y[:101]))) is None
+    h1.close()
+    h.close()
+
+
+def test_incremental_refit_through_the_model_classes():
+    """train(do_optimize=False) with appended rows (what the solver does between hyper-parameter refits,
+    solver/bayesian_optimization.py:161-167) takes the shortcut on the device (DeviceGP.n_appends) and agrees with a
+    freshly trained model, output standardisation (a new mean / scale of y at every call) included."""
+    from robo_b200 import kernels as K
+    from robo_b200.models.gaussian_process import GaussianProcess
+    rng = np.random.RandomState(4)
+    X, y, Xs = rng.rand(330, 4), rng.rand(330), rng.rand(50, 4)
+
+    def make():
+        return GaussianProcess(1.3 * K.Matern52Kernel(np.full(4, 0.8), ndim=4), noise=1e-3, lower=np.zeros(4),
+                               upper=np.ones(4), normalize_output=True)
+    model = make()
+    model.train(X[:300], y[:300], do_optimize=False)
+    model.predict(Xs)
+    model.train(X[:301], y[:301], do_optimize=False)
+    model.predict(Xs)
+    model.train(X[:330], y[:330], do_optimize=False)
+    assert model.gp.n_appends == 2
+    ref = make()
+    ref.train(X[:330], y[:330], do_optimize=False)
+    assert ref.gp.n_appends == 0
+    mu, var = model.predict(Xs)
+    mu_r, var_r = ref.predict(Xs)
+    assert_mean_close(mu, mu_r, y[:330])
+    assert_var_close(var, var_r, 1.3)
+    assert abs(model.gp.log_likelihood(model.y) - ref.gp.log_likelihood(ref.y)) <= 1e-11 * abs(ref.gp.log_likelihood(ref.y))

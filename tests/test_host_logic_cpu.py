@@ -149,3 +149,60 @@ def test_device_random_sampling_host_logic(fake):
     rs = RandomSampling(acq, lower, upper, n_samples=100, rng=np.random.RandomState(0))
     xr = rs.maximize()
     assert xr.shape == (2,) and np.all(xr >= lower) and np.all(xr <= upper)
+
+
+def test_incremental_refit_host_logic(fake):
+    """train(do_optimize=False) with rows appended to a factorised training set goes through
+    Handle.fit_append when (and only when) the library's preconditions hold; results equal a fresh model's."""
+    from robo_b200 import kernels as K
+    from robo_b200.models import GaussianProcess
+    rng = np.random.RandomState(3)
+    X, y = rng.rand(400, 3), rng.rand(400)
+    lower, upper = np.zeros(3), np.ones(3)
+    Xt = rng.rand(9, 3)
+
+    def fresh(n, noise=1e-3):
+        m = GaussianProcess(2.0 * K.Matern52Kernel(np.ones(3), ndim=3), noise=noise, lower=lower, upper=upper)
+        m.train(X[:n], y[:n], do_optimize=False)
+        return m
+
+    model = fresh(300)
+    h = model.gp.handle
+    assert (h.n_fits, h.n_appends) == (1, 0)
+    # 1. no scoring call since the fit -> L^-1 not built -> full refit
+    model.train(X[:303], y[:303], do_optimize=False)
+    assert (h.n_fits, h.n_appends, model.gp.n_appends) == (2, 0, 0)
+    # 2. after a predict the appended rows take the shortcut; BaseModel.update goes the same way
+    model.predict(Xt)
+    model.train(X[:310], y[:310], do_optimize=False)
+    assert (h.n_fits, h.n_appends, model.gp.n_appends) == (2, 1, 1)
+    mu, var = model.predict(Xt)
+    mu_f, var_f = fresh(310).predict(Xt)
+    np.testing.assert_allclose(mu, mu_f, rtol=1e-12)
+    np.testing.assert_allclose(var, var_f, rtol=1e-12)
+    assert model.gp.log_likelihood(model.y) == fresh(310).gp.log_likelihood(y[:310])
+    # 3. crossing a 128-row block boundary, changed noise, changed earlier rows, fewer rows: full refits
+    model.train(X[:390], y[:390], do_optimize=False)
+    assert (h.n_fits, h.n_appends) == (3, 1)
+    model.predict(Xt)
+    model.noise = 2e-3
+    model.train(X[:392], y[:392], do_optimize=False)
+    assert (h.n_fits, h.n_appends) == (4, 1)
+    model.predict(Xt)
+    X2 = X[:394].copy()
+    X2[0, 0] += 1e-3
+    model.train(X2, y[:394], do_optimize=False)
+    assert (h.n_fits, h.n_appends) == (5, 1)
+    model.predict(Xt)
+    model.train(X[:391], y[:391], do_optimize=False)
+    assert (h.n_fits, h.n_appends) == (6, 1)
+    # 4. the switch
+    model.predict(Xt)
+    model.gp.incremental = False
+    model.train(X[:393], y[:393], do_optimize=False)
+    assert (h.n_fits, h.n_appends) == (7, 1)
+    # 5. a deep copy (MarginalizationGPMCMC copies models) never appends onto a handle it does not own
+    m2 = copy.deepcopy(fresh(300))
+    m2.predict(Xt)
+    m2.train(X[:305], y[:305], do_optimize=False)
+    np.testing.assert_allclose(m2.predict(Xt)[0], fresh(305).predict(Xt)[0], rtol=1e-12)

@@ -100,5 +100,12 @@ for n in SIZES:
                   % (n, t[33] - t[0], t[1] - t[0]))
             print(ph.T)
             print("sums", ph.sum(axis=0))
+            if t[34]:
+                print("panel 3 fine stamps: S loads %d, pivots 0-3 %d, 4-7 %d, 8-11 %d, 12-15 %d, smem stores %d, barrier %d; "
+                      "U global stores %d, update+publish %d, barrier %d"
+                      % (t[34] - t[7], t[35] - t[34], t[36] - t[35], t[37] - t[36], t[38] - t[37], t[39] - t[38],
+                         t[8] - t[39], t[40] - t[8], t[41] - t[40], t[9] - t[41]))
+                print("panel 3 factorising warp: pivots 0-3 %d, 4-7 %d, 8-11 %d, 12-14 + rsqrt %d cycles"
+                      % (t[42] - t[46], t[43] - t[42], t[44] - t[43], t[45] - t[44]))
             h.close()
 sys.exit(1 if bad else 0)

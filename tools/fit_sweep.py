@@ -19,7 +19,7 @@ theta = np.concatenate(([0.0], np.full(D, np.log(D / 4.0))))
 f = K.Product(K.ConstantKernel(theta[0], ndim=D), K.Matern52Kernel(np.exp(theta[1:]), ndim=D)).flatten()
 da = float(np.sqrt(np.float64(np.sqrt(1e-3)) ** 2 + 1.25e-12) ** 2)
 ref = None
-for diag in (0, 2):
+for diag in (0, 2, 3):
     for la in (0, 1):
         h = _lib.Handle(0)
         h.set_option("diag", diag)

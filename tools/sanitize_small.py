@@ -10,9 +10,10 @@ rng = np.random.RandomState(0)
 N, D, M = 300, 3, 700
 X, y, Xs = rng.rand(N, D), rng.rand(N), rng.rand(M, D)
 f = K.Product(K.ConstantKernel(0.1, ndim=D), K.Matern52Kernel(np.array([0.3, 0.5, 0.8]), ndim=D)).flatten()
-for loader in (2, 1, 0):
+for loader, diag in ((2, 3), (1, 2), (0, 0)):
     h = _lib.Handle(0)
     h.set_option("loader", loader)
+    h.set_option("diag", diag)
     h.set_option("chunk", 256)
     h.set_data(X, y)
     h.set_input_bounds(np.zeros(D), np.ones(D))
