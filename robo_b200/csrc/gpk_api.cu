@@ -45,7 +45,7 @@ struct gpk_handle {
     char err[1024] = {0};
     int loader = LOADER_TMA_WS;
     long chunk = 16384;
-    int diag_kernel = 3;          // 3 = blocked 16-column panels (default), 2 = column-by-column register-tiled, 0 = simple shared-memory version
+    int diag_kernel = 4;          // 4 = blocked 16-column panels, DMMA updates (default); 3 = same with DFMA register tiles, 2 = column-by-column register-tiled, 0 = simple shared-memory version
     int diag_prof = 0;            // 1: the blocked diagonal kernel records clock64() stamps per phase (diagnostics)
     DevBuf dprof;
 
@@ -240,6 +240,7 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG3_SMEM));
+    CK(cudaFuncSetAttribute(gpk_potrf_diag_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG4_SMEM));
     return GPK_OK;
 }
 
@@ -742,18 +743,23 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->lookahead = (int)value;
         return GPK_OK;
     }
-    if (!strcmp(key, "diagprof")) {
+    if (!strcmp(key, "diagprof")) {                 // 1: stamps; 2: stamps + skip the kernel's global stores (timing only)
         h->diag_prof = value != 0;
         if (h->diag_prof) {
             int rc = ensure(h, h->dprof, 64 * 8);
             if (rc) return rc;
             CK(cudaMemset(h->dprof.p, 0, 64 * 8));
+            if (value == 2) {
+                const long long one = 1;
+                CK(cudaMemcpy((char*)h->dprof.p + 63 * 8, &one, 8, cudaMemcpyHostToDevice));
+            }
         }
         return GPK_OK;
     }
     if (!strcmp(key, "diag")) {
-        if (value != 0 && value != 2 && value != 3)
-            BAD("diag must be 3 (blocked 16-column panels), 2 (column-by-column register-tiled kernel) or 0 (simple shared-memory kernel)");
+        if (value != 0 && value != 2 && value != 3 && value != 4)
+            BAD("diag must be 4 (blocked panels, DMMA updates), 3 (blocked panels, DFMA register tiles), 2 (column-by-column "
+                "register-tiled kernel) or 0 (simple shared-memory kernel)");
         h->diag_kernel = (int)value;
         return GPK_OK;
     }
@@ -912,13 +918,19 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         h->ev_rest.push_back(e2);
     }
     std::vector<char> rest_recorded(nb, 0);
-    if (h->diag_kernel == 3) {
-        gpk_diag_prezero_kernel<<<nb, 256, 0, h->stream>>>(K, (long)NP);
+    if (h->diag_kernel >= 3) {
+        gpk_diag_prezero_kernel<<<nb, 256, 0, h->stream>>>(K, (long)NP, ptr<double>(h->P), (long)NP);
         CKL();
     }
     for (int k = 0; k < nb; ++k) {
         long long* dprof = h->diag_prof ? ptr<long long>(h->dprof) : nullptr;
-        if (h->diag_kernel == 3 && h->pdl && k > 0)
+        if (h->diag_kernel == 4 && h->pdl && k > 0)
+            CK(launch_pdl(gpk_potrf_diag_dmma_kernel, dim3(1), dim3(256), (size_t)DIAG4_SMEM, h->stream, K, (long)NP, k,
+                          ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status), ptr<double>(h->logdet_part), dprof));
+        else if (h->diag_kernel == 4)
+            gpk_potrf_diag_dmma_kernel<<<1, 256, DIAG4_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
+                                                                          ptr<int>(h->status), ptr<double>(h->logdet_part), dprof);
+        else if (h->diag_kernel == 3 && h->pdl && k > 0)
             CK(launch_pdl(gpk_potrf_diag_blocked_kernel, dim3(1), dim3(256), (size_t)DIAG3_SMEM, h->stream, K, (long)NP, k,
                           ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status), ptr<double>(h->logdet_part), dprof));
         else if (h->diag_kernel == 3)
@@ -984,7 +996,7 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
             }
         }
     }
-    if (h->diag_kernel == 3) {
+    if (h->diag_kernel >= 3) {
         gpk_diag_qfill_kernel<<<nb, 256, 0, h->stream>>>(ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status));
         CKL();
     }
@@ -1101,11 +1113,15 @@ int gpk_fit_append(gpk_handle* h, const double* X, const double* y, int n, int d
     CK(cudaMemcpy2DAsync(K + (long)N1 * NP, (size_t)NP * 8, W + (long)N1 * NP, (size_t)NP * 8, (size_t)N1 * 8, BM,
                          cudaMemcpyDeviceToDevice, h->stream));
     // factor + invert the last diagonal block
-    if (h->diag_kernel == 3) {
-        gpk_diag_prezero_kernel<<<1, 256, 0, h->stream>>>(K + (long)N1 * NP + N1, (long)NP);
+    if (h->diag_kernel >= 3) {
+        gpk_diag_prezero_kernel<<<1, 256, 0, h->stream>>>(K + (long)N1 * NP + N1, (long)NP, P + (long)N1 * NP + N1, (long)NP);
         CKL();
-        gpk_potrf_diag_blocked_kernel<<<1, 256, DIAG3_SMEM, h->stream>>>(K, NP, b, P, Q, NP, ptr<int>(h->status),
-                                                                         ptr<double>(h->logdet_part), nullptr);
+        if (h->diag_kernel == 4)
+            gpk_potrf_diag_dmma_kernel<<<1, 256, DIAG4_SMEM, h->stream>>>(K, NP, b, P, Q, NP, ptr<int>(h->status),
+                                                                          ptr<double>(h->logdet_part), nullptr);
+        else
+            gpk_potrf_diag_blocked_kernel<<<1, 256, DIAG3_SMEM, h->stream>>>(K, NP, b, P, Q, NP, ptr<int>(h->status),
+                                                                             ptr<double>(h->logdet_part), nullptr);
         CKL();
         gpk_diag_qfill_kernel<<<1, 256, 0, h->stream>>>(P + (long)N1 * NP + N1, Q + (long)N1 * NP + N1, (long)NP,
                                                          ptr<int>(h->status));

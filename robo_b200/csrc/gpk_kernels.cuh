@@ -354,8 +354,9 @@ gpk_potrf_diag_fused_kernel(double* __restrict__ K, long ld, int kb,
     diag_fused_block<5>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
     diag_fused_block<6>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
     diag_fused_block<7>(A, X, lrp, rs_prev, rs_cur, colbuf, rowbuf, dnext, ty, tx, tid, kb, &s_bad);
-    // last row of X (row 127) only needs its scaling; nobody reads the broadcast copy
-    diag_x_publish<7>(X, rowbuf, rs_prev, ty, tx, 15);
+    // last row of X (row 127) only needs its scaling; nobody reads the broadcast copy, but slower threads may still be
+    // reading this buffer for the update of step 127 (racecheck): write the copy to the other parity buffer
+    diag_x_publish<7>(X, rowbuf + 128, rs_prev, ty, tx, 15);
 
     // ---------------- publish L, log-det, status ----------------
 #pragma unroll

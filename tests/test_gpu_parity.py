@@ -126,7 +126,7 @@ def test_cholesky_variants_agree():
     from robo_b200 import _lib
     X, y, _, theta, noise = O.synthetic_problem(600, 5, 1, seed_train=11)
     ref = None
-    for diag, la, st in ((3, 1, 1), (2, 1, 1), (0, 1, 1), (3, 0, 1), (2, 0, 1), (3, 1, 0), (0, 0, 0)):
+    for diag, la, st in ((3, 1, 1), (4, 1, 1), (2, 1, 1), (0, 1, 1), (3, 0, 1), (2, 0, 1), (3, 1, 0), (0, 0, 0)):
         h = _lib.Handle(0)
         h.set_option("diag", diag)
         h.set_option("lookahead", la)
@@ -758,7 +758,7 @@ def test_full_size_properties():
 
 
 # --------------------------------------------------------------------------- incremental refit
-@pytest.mark.parametrize("diag", [3, 2])
+@pytest.mark.parametrize("diag", [3, 4, 2])
 def test_fit_append_matches_full_refit_and_oracle(diag):
     """gpk_fit_append: rows appended inside the last 128-row block.  Against a full refit on the device (factor,
     inverse, z, log-likelihood) and against the CPU oracle (posterior moments + EI at the north_star tolerances);
