@@ -287,6 +287,23 @@ def run_ours(args, rank, world, local_rank):
                "kind": "port", "fit_ms": 1e3 * fit_s,
                "sample": "%d batches of 500 candidates (reference batch size, full M x M covariance), "
                          "N=4096 D=16, oracle port of gaussian_process.py:280-294 + ei.py:65-78" % len(timed)}
+    # incremental refit (gpk_fit_append): the last 8 rows appended to a model fitted on N - 8 rows (extra info, untimed
+    # with respect to the headline; rank 0 only)
+    append_ms = None
+    if rank == 0:
+        try:
+            h2 = _lib.Handle(dev.index or 0)
+            h2.set_data(X[:N_TRAIN - 8], y[:N_TRAIN - 8])
+            h2.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+            h2.fit(diag_add, float(np.mean(y[:N_TRAIN - 8])))
+            h2.predict(Xs[:128])
+            res = h2.fit_append(X, y, diag_add, mean)
+            if res is not None:
+                append_ms = h2.timings()["fit_ms"]
+                assert abs(res[1] - ll) <= 1e-10 * abs(ll), "incremental refit disagrees with the full fit"
+            h2.close()
+        except Exception as e:                                   # noqa: BLE001
+            print("fit_append timing skipped: %r" % (e,), file=sys.stderr)
     line = {
         "metric": METRIC, "value": value, "unit": "EI evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -297,11 +314,11 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "working set per step (L^-1 134 MB + K* chunk %d MB) exceeds the 126 MB L2; no flush needed"
                          % (rows * N_TRAIN * 8 // 2 ** 20)},
         "fit_ms": float(np.median(fit_ms[1:])), "fit_breakdown_ms": {k: t_fit[k] for k in ("kbuild_ms", "potrf_ms", "linv_ms")},
-        "loglik": ll,
+        "loglik": ll, "fit_append_8rows_ms": append_ms,
         "e2e": {"value": e2e_value, "unit": "EI evals/s", "h2d_bytes_per_step": int(M * DIM * 8),
                 "d2h_bytes_per_step": 24, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gpk_gemm_nt_kernel<EPI_COLREDUCE> (L^-1 K*^T contraction, fp64 DMMA)",
+        "roofline": {"bound": "tensor", "kernel": "gpk_gemm_ws_kernel<EPI_COLREDUCE> (L^-1 K*^T contraction, fp64 DMMA, warp-specialised TMA)",
                      "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
                      "peak_source": "measured live on this GPU: register-resident DMMA m8n8k4 issue rate "
                                     "(gpk_measure_fp64_peaks); MEASURED_PEAKS.json has no fp64 figure; datasheet "
@@ -312,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
                      "launches_averaged": int(max(1, (M + rows - 1) // rows - 1)) if M > rows else 1,
                      "traffic": 1.598e9 if last_rows == 16384 else None,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one 16384-candidate "
-                                       "launch (profiles/r01_vargemm_ncu_full_raw.csv); algorithmic minimum 0.60e9 "
+                                       "launch (profiles/r01_vargemm_ws_ncu_full_raw.csv); algorithmic minimum 0.60e9 "
                                        "(L^-1 lower triangle 67 MB + K* 537 MB read once)"},
         "kernel_ms_last_chunk": {k: tim[k] for k in ("kstar_ms", "vargemm_ms", "finish_ms")},
         "cpu_baseline": cpu, "clocks": clocks,

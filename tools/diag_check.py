@@ -88,7 +88,7 @@ for n in SIZES:
         print("time n=%d diag=%d chain=%d  fit_ms median %.3f min %.3f  ll=%.12f  rel.diff vs first %.2e"
               % (n, diag, chain, np.median(ts[2:]), min(ts), ll, rel))
         h.close()
-        if diag in (3, 4):                  # cycle stamps of the last diagonal block (clock64, SM clock)
+        if diag in (3, 4, 5):               # cycle stamps of the last diagonal block (clock64, SM clock)
             h = handle(X, y, f, diag, chain)
             h.set_option("diagprof", int(os.environ.get("DIAGPROF", 1)))
             for _ in range(3):

@@ -24,8 +24,8 @@ if [[ $what == diag || $what == all ]]; then
   # blocked diagonal-block kernel: launch list of three fits and one full capture (block 5 of the second fit)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_fit.csv \
       python tools/fit_only.py > gpurun_out/ncu_fit_list.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gpk_potrf_diag_blocked_kernel -s 37 -c 1 \
-      -f -o gpurun_out/prof_diag_blocked python tools/fit_only.py > gpurun_out/ncu_diag_full.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gpk_potrf_diag_dmma_kernel -s 37 -c 1 \
+      -f -o gpurun_out/prof_diag_dmma python tools/fit_only.py > gpurun_out/ncu_diag_full.log 2>&1
   tail -3 gpurun_out/ncu_diag_full.log
 fi
 if [[ $what == sanitize ]]; then

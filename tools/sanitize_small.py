@@ -10,7 +10,7 @@ rng = np.random.RandomState(0)
 N, D, M = 300, 3, 700
 X, y, Xs = rng.rand(N, D), rng.rand(N), rng.rand(M, D)
 f = K.Product(K.ConstantKernel(0.1, ndim=D), K.Matern52Kernel(np.array([0.3, 0.5, 0.8]), ndim=D)).flatten()
-for loader, diag in ((2, 3), (1, 2), (0, 0)):
+for loader, diag in ((2, 4), (1, 3), (0, 2)):
     h = _lib.Handle(0)
     h.set_option("loader", loader)
     h.set_option("diag", diag)
