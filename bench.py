@@ -182,7 +182,9 @@ def run_ours(args, rank, world, local_rank):
 
     h = _lib.Handle(local_rank)
     # a real (non-default) torch stream: the handle launches on it, and torch.cuda.Event timing sees it
-    stream = torch.cuda.Stream(device=dev)
+    # high priority like the handle's own stream: the single-CTA kernels of the Cholesky chain must not queue behind the
+    # trailing-update tiles the handle launches on its low-priority side stream
+    stream = torch.cuda.Stream(device=dev, priority=-1)
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
     h.set_option("chunk", args.chunk)

@@ -63,14 +63,19 @@ const char* gpk_version(void);
  *   "loader"    operand staging of the GEMM tile engine: 2 = TMA with a dedicated producer warp and
  *               full/empty mbarriers [default], 1 = TMA issued by a consumer thread, 0 = cp.async (cross-check)
  *   "chunk"     candidates per scoring pass (multiple of 128, default 16384)
- *   "diag"      diagonal-block Cholesky kernel: 2 = register-tiled fused factor + invert [default],
- *               0 = simple shared-memory version (cross-check)
+ *   "diag"      diagonal-block Cholesky + inverse kernel: 4 = 16-column panels, square-root-free pivot chain in one warp,
+ *               substitutions in four, rank-16 updates on the fp64 tensor pipe [default]; 3 = the same with DFMA register
+ *               tiles; 2 = column-by-column register-tiled kernel; 0 = simple shared-memory version (cross-checks)
+ *   "diagprof"  1 = the blocked diagonal kernels record clock64() stamps per phase (gpk_get_diag_profile)
  *   "lookahead" 1 = trailing updates on a side stream, overlapped with the next diag/panel [default]
  *   "smalltile" 1 = 32-row tiles for the panel solve / next-panel update [default]
  *   "pdl"       1 = programmatic dependent launch for the kernels of the Cholesky chain [default]
  *   "overlap"   1 = build K* of chunk i+1 on the side stream while chunk i contracts [default] */
 int gpk_set_option(gpk_handle* h, const char* key, long value);
-/* run on an existing CUDA stream (cudaStream_t passed as void*); NULL = the handle's own */
+/* run on an existing CUDA stream (cudaStream_t passed as void*); NULL = the handle's own.  The handle's own stream has
+ * the highest priority and its side stream (trailing updates, K* look-ahead) the lowest: give an external stream a high
+ * priority too, or the single-CTA kernels of the Cholesky chain queue behind the side stream's tiles (fit 2.6 instead of
+ * 2.3 ms at N = 4096). */
 int gpk_set_stream(gpk_handle* h, void* cuda_stream);
 int gpk_synchronize(gpk_handle* h);
 
