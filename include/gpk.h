@@ -68,7 +68,8 @@ const char* gpk_version(void);
  *               tiles; 2 = column-by-column register-tiled kernel; 0 = simple shared-memory version (cross-checks)
  *   "diagprof"  1 = the blocked diagonal kernels record clock64() stamps per phase (gpk_get_diag_profile)
  *   "lookahead" 1 = trailing updates on a side stream, overlapped with the next diag/panel [default]
- *   "smalltile" 1 = 32-row tiles for the panel solve / next-panel update [default]
+ *   "smalltile" 1 = 32-row tiles for the panel solve / next-panel update [default], 2 = 16-row tiles, 0 = 128-row tiles
+ *   "fusechain" 1 = panel solve + next-panel update of a step in one launch (measured neutral; default 0)
  *   "pdl"       1 = programmatic dependent launch for the kernels of the Cholesky chain [default]
  *   "overlap"   1 = build K* of chunk i+1 on the side stream while chunk i contracts [default] */
 int gpk_set_option(gpk_handle* h, const char* key, long value);

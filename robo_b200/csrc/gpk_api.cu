@@ -21,6 +21,7 @@
 #include "gpk_gemm.cuh"
 #include "gpk_kernels.cuh"
 #include "gpk_diag16.cuh"
+#include "gpk_chain.cuh"
 
 namespace {
 
@@ -42,6 +43,8 @@ struct gpk_handle {
     int lookahead = 1;
     int smalltile = 1;              // 32-row tiles for the panel solve / next-panel update
     int pdl = 1;                    // programmatic dependent launch on the Cholesky chain
+    int fusechain = 0;              // 1: panel solve + next-panel update of a step in one launch (gpk_chain.cuh)
+    DevBuf chain_cnt;
     char err[1024] = {0};
     int loader = LOADER_TMA_WS;
     long chunk = 16384;
@@ -72,13 +75,13 @@ struct gpk_handle {
     int jobs_nb = -1;
 
     // job tables
-    std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r, trsm32_r, pu32_r;
+    std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r, trsm32_r, pu32_r, trsm16_r, pu16_r;
     Range kinv_r;
     Range app_row_r, app_syrk_r, app_t_r, app_p_r;      // gpk_fit_append (last block row only)
 
     // tensor maps
     CUtensorMap mapK, mapP, mapQ, mapW, mapKs, mapVt;
-    CUtensorMap mapK32, mapKs2;
+    CUtensorMap mapK32, mapK16, mapKs2;
     long mapKs2_rows = 0;
     std::vector<cudaEvent_t> ev_cov, ev_gemm;
     int overlap = 1;                // build K* of chunk i+1 on the side stream while chunk i contracts            // Kbuf with a 32-row box: A operand of the small-tile chain GEMMs
@@ -93,6 +96,8 @@ struct gpk_handle {
     double launches_total = 0, launches_var = 0;
     long last_chunk_rows = 0;
     double* pin = nullptr;        // pinned host: [0..1] z^T z, logdet ; [2] status (as int) for async fits
+    double* stage[2] = {nullptr, nullptr};    // pinned staging of pageable candidate batches (gpk_acq)
+    size_t stage_cap = 0;
     bool fit_pending = false;
 };
 
@@ -212,7 +217,7 @@ int launch_gemm(gpk_handle* h, const CUtensorMap& mA, const CUtensorMap& mB, con
                 cudaStream_t stream = nullptr, bool pdl = false) {
     if (njobs <= 0) return GPK_OK;
     if (stream == nullptr) stream = h->stream;
-    if (pdl && h->pdl && h->loader != LOADER_CPASYNC && MI == 2) {
+    if (pdl && h->pdl && h->loader != LOADER_CPASYNC && MI <= 2) {
         CK(launch_pdl(gpk_gemm_nt_kernel<EPI, LOADER_TMA, MI>, dim3(njobs), dim3(GEMM_THREADS),
                       (size_t)gemm_smem_bytes(LOADER_TMA, MI), stream, mA, mB, a));
         h->launches_total += 1;
@@ -237,8 +242,11 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_ws_kernel<EPI_COLREDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TMA));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 2)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 1)));
+    CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 1)));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
+    CK(cudaFuncSetAttribute(gpk_chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG3_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG4_SMEM));
     return GPK_OK;
@@ -294,6 +302,26 @@ int build_job_tables(gpk_handle* h) {
                     jobs.push_back({i * BM + 32 * q, (k + 1) * BM, k * BM, (k + 1) * BM, i * BM + 32 * q, (k + 1) * BM, 0, 0});
                 }
         h->pu32_r[k].cnt = (int)jobs.size() - h->pu32_r[k].off;
+    }
+    // 16-row versions (option smalltile = 2): twice the CTAs, half the arithmetic per CTA on the chain
+    h->trsm16_r.assign(nb, Range());
+    h->pu16_r.assign(nb, Range());
+    for (int k = 0; k < nb; ++k) {
+        h->trsm16_r[k].off = (int)jobs.size();
+        for (int i = k + 1; i <= nb; ++i)
+            for (int q = 0; q < 8; ++q) {
+                if (i == nb && q > 0) break;
+                jobs.push_back({i * BM + 16 * q, k * BM, k * BM, (k + 1) * BM, i * BM + 16 * q, k * BM, 0, 0});
+            }
+        h->trsm16_r[k].cnt = (int)jobs.size() - h->trsm16_r[k].off;
+        h->pu16_r[k].off = (int)jobs.size();
+        if (k + 1 < nb)
+            for (int i = k + 1; i <= nb; ++i)
+                for (int q = 0; q < 8; ++q) {
+                    if (i == nb && q > 0) break;
+                    jobs.push_back({i * BM + 16 * q, (k + 1) * BM, k * BM, (k + 1) * BM, i * BM + 16 * q, (k + 1) * BM, 0, 0});
+                }
+        h->pu16_r[k].cnt = (int)jobs.size() - h->pu16_r[k].off;
     }
     std::vector<Node> nodes;
     int hmax = build_nodes(0, nb, nodes);
@@ -370,6 +398,7 @@ int rebuild_maps(gpk_handle* h) {
     int rc;
     if ((rc = make_map(h, &h->mapK, h->Kbuf.p, NP + BM, NP, NP))) return rc;
     if ((rc = make_map(h, &h->mapK32, h->Kbuf.p, NP + BM, NP, NP, 32))) return rc;
+    if ((rc = make_map(h, &h->mapK16, h->Kbuf.p, NP + BM, NP, NP, 16))) return rc;
     if ((rc = make_map(h, &h->mapP, h->P.p, NP, NP, NP))) return rc;
     if ((rc = make_map(h, &h->mapQ, h->Q.p, NP, NP, NP))) return rc;
     if ((rc = make_map(h, &h->mapW, h->W.p, NP, NP, NP))) return rc;
@@ -690,12 +719,14 @@ int gpk_destroy(gpk_handle* h) {
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
                       &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
-                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3};
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->ev_ok)
         for (int i = 0; i < 16; ++i) cudaEventDestroy(h->ev[i]);
     if (h->ev_order) cudaEventDestroy(h->ev_order);
+    for (int i = 0; i < 2; ++i)
+        if (h->stage[i]) cudaFreeHost(h->stage[i]);
     for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_rest) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_cov) cudaEventDestroy(e);
@@ -723,6 +754,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->mapVt_rows = 0;
         return GPK_OK;
     }
+    if (!strcmp(key, "fusechain")) {
+        if (value != 0 && value != 1) BAD("fusechain must be 0 or 1");
+        h->fusechain = (int)value;
+        return GPK_OK;
+    }
     if (!strcmp(key, "pdl")) {
         if (value != 0 && value != 1) BAD("pdl must be 0 or 1");
         h->pdl = (int)value;
@@ -734,7 +770,7 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         return GPK_OK;
     }
     if (!strcmp(key, "smalltile")) {
-        if (value != 0 && value != 1) BAD("smalltile must be 0 or 1");
+        if (value < 0 || value > 2) BAD("smalltile must be 0 (128-row chain tiles), 1 (32 rows) or 2 (16 rows)");
         h->smalltile = (int)value;
         return GPK_OK;
     }
@@ -918,6 +954,11 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         h->ev_rest.push_back(e2);
     }
     std::vector<char> rest_recorded(nb, 0);
+    const bool fuse = h->fusechain && h->smalltile == 1 && h->lookahead;
+    if (fuse) {
+        if ((rc = ensure(h, h->chain_cnt, (size_t)nb * 4))) return rc;
+        CK(cudaMemsetAsync(h->chain_cnt.p, 0, (size_t)nb * 4, h->stream));
+    }
     if (h->diag_kernel >= 3) {
         gpk_diag_prezero_kernel<<<nb, 256, 0, h->stream>>>(K, (long)NP, ptr<double>(h->P), (long)NP);
         CKL();
@@ -946,6 +987,39 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
             gpk_potrf_diag_kernel<<<1, 256, DIAG_SMEM, h->stream>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
                                                                     ptr<int>(h->status), ptr<double>(h->logdet_part));
         CKL();
+        if (fuse) {
+            // one launch for panel solve + next-panel update (gpk_chain.cuh).  Its second pass writes block column
+            // k+1, which the rest of step k-1 (side stream) also updates: wait for that first.
+            const int npu = nb - k;
+            if (k >= 1 && rest_recorded[k - 1]) CK(cudaStreamWaitEvent(h->stream, h->ev_rest[k - 1], 0));
+            ChainArgs c;
+            c.K = K; c.ld = NP; c.P = ptr<double>(h->P); c.ldp = NP;
+            c.solve_jobs = ptr<GemmJob>(h->jobs) + h->trsm32_r[k].off;
+            c.update_jobs = h->pu32_r[k].cnt > 0 ? ptr<GemmJob>(h->jobs) + h->pu32_r[k].off : nullptr;
+            c.counter = ptr<int>(h->chain_cnt) + k;
+            c.status = ptr<int>(h->status);
+            if (h->pdl)
+                CK(launch_pdl(gpk_chain_step_kernel, dim3((unsigned)h->trsm32_r[k].cnt), dim3(GEMM_THREADS), (size_t)CH_SMEM,
+                              h->stream, c));
+            else
+                gpk_chain_step_kernel<<<(unsigned)h->trsm32_r[k].cnt, GEMM_THREADS, CH_SMEM, h->stream>>>(c);
+            CKL();
+            h->launches_total += 1;
+            const int off = h->syrk_r[k].off, cnt = h->syrk_r[k].cnt;
+            if (cnt > npu) {
+                CK(cudaEventRecord(h->ev_panel[k], h->stream));
+                CK(cudaStreamWaitEvent(h->side_stream, h->ev_panel[k], 0));
+                GemmArgs s2;
+                memset(&s2, 0, sizeof(s2));
+                s2.A = K; s2.lda = NP; s2.B = K; s2.ldb = NP; s2.C = K; s2.ldc = NP;
+                s2.alpha = -1.0; s2.beta = 1; s2.job_mode = JOBS_TABLE; s2.status = ptr<int>(h->status);
+                s2.jobs = ptr<GemmJob>(h->jobs) + off + npu;
+                if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s2, cnt - npu, h->side_stream))) return rc;
+                CK(cudaEventRecord(h->ev_rest[k], h->side_stream));
+                rest_recorded[k] = 1;
+            }
+            continue;
+        }
         GemmArgs a;
         memset(&a, 0, sizeof(a));
         a.A = K; a.lda = NP;
@@ -954,7 +1028,10 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         a.alpha = 1.0; a.beta = 0;
         a.job_mode = JOBS_TABLE;
         a.status = ptr<int>(h->status);
-        if (h->smalltile) {
+        if (h->smalltile == 2) {
+            a.jobs = ptr<GemmJob>(h->jobs) + h->trsm16_r[k].off;
+            if ((rc = launch_gemm<EPI_STORE, 1>(h, h->mapK16, h->mapP, a, h->trsm16_r[k].cnt, nullptr, true))) return rc;
+        } else if (h->smalltile) {
             a.jobs = ptr<GemmJob>(h->jobs) + h->trsm32_r[k].off;
             if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapP, a, h->trsm32_r[k].cnt, nullptr, true))) return rc;
         } else {
@@ -980,7 +1057,10 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
             const int npu = nb - k;
             CK(cudaEventRecord(h->ev_panel[k], h->stream));                       // panel k solved
             if (k >= 1 && rest_recorded[k - 1]) CK(cudaStreamWaitEvent(h->stream, h->ev_rest[k - 1], 0));
-            if (h->smalltile) {
+            if (h->smalltile == 2) {
+                s.jobs = ptr<GemmJob>(h->jobs) + h->pu16_r[k].off;
+                if ((rc = launch_gemm<EPI_STORE, 1>(h, h->mapK16, h->mapK, s, h->pu16_r[k].cnt, nullptr, true))) return rc;
+            } else if (h->smalltile) {
                 s.jobs = ptr<GemmJob>(h->jobs) + h->pu32_r[k].off;
                 if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapK, s, h->pu32_r[k].cnt, nullptr, true))) return rc;
             } else {
@@ -1192,6 +1272,28 @@ int gpk_acq_dev(gpk_handle* h, const void* d_Xs, long m, int kind, double eta, d
                      (BestPair*)d_best, nullptr);
 }
 
+// Pageable host memory reaches the device at 1-2 GB/s through cudaMemcpyAsync (the driver stages it synchronously in
+// small pieces): a 2^20 x 8 candidate batch (67 MB, config C3) took 40 ms to copy for 3 ms of scoring.  Large pageable
+// batches are therefore copied by the host into two pinned staging buffers and go out by DMA while the next piece is
+// being staged.  Pinned / registered caller buffers are used in place.
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int ensure_stage(gpk_handle* h, size_t bytes) {
+    if (bytes <= h->stage_cap) return GPK_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (h->stage[i]) CK(cudaFreeHost(h->stage[i]));
+        h->stage[i] = nullptr;
+    }
+    h->stage_cap = 0;
+    for (int i = 0; i < 2; ++i) CK(cudaHostAlloc((void**)&h->stage[i], bytes, cudaHostAllocDefault));
+    h->stage_cap = bytes;
+    return GPK_OK;
+}
+
 int gpk_acq(gpk_handle* h, const double* Xs, long m, int kind, double eta, double par, double* out, double* mu,
             double* var, double* best_val, long* best_idx, long* n_negative) {
     int rc = require(h, true, true, true);
@@ -1205,8 +1307,15 @@ int gpk_acq(gpk_handle* h, const double* Xs, long m, int kind, double eta, doubl
     if (var && (rc = ensure(h, h->out_var, (size_t)m * 8))) return rc;
     CK(cudaEventRecord(h->ev[14], h->stream));
     const long piece = 4 * h->chunk;                  // host batch fed in pieces of 4 chunks
+    const bool staged = (size_t)m * h->d * 8 > ((size_t)1 << 20) && !host_is_pinned(Xs);
+    if (staged && (rc = ensure_stage(h, (size_t)std::min<long>(m, piece) * h->d * 8))) return rc;
     if (m <= piece) {
-        CK(cudaMemcpyAsync(h->cand.p, Xs, (size_t)m * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+        const double* src = Xs;
+        if (staged) {
+            memcpy(h->stage[0], Xs, (size_t)m * h->d * 8);
+            src = h->stage[0];
+        }
+        CK(cudaMemcpyAsync(h->cand.p, src, (size_t)m * h->d * 8, cudaMemcpyHostToDevice, h->stream));
         rc = score_dev(h, ptr<double>(h->cand), m, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,
                        mu ? ptr<double>(h->out_mu) : nullptr, var ? ptr<double>(h->out_var) : nullptr, nullptr, nullptr);
         if (rc) return rc;
@@ -1227,7 +1336,13 @@ int gpk_acq(gpk_handle* h, const double* Xs, long m, int kind, double eta, doubl
             const long base = (long)i * piece, mc = std::min(piece, m - base);
             double* buf = (i & 1) ? ptr<double>(h->cand2) : ptr<double>(h->cand);
             if (i >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_scored[i - 2], 0));
-            CK(cudaMemcpyAsync(buf, Xs + base * h->d, (size_t)mc * h->d * 8, cudaMemcpyHostToDevice, h->copy_stream));
+            const double* src = Xs + base * h->d;
+            if (staged) {
+                if (i >= 2) CK(cudaEventSynchronize(h->ev_copied[i - 2]));      // the DMA out of this staging buffer is done
+                memcpy(h->stage[i & 1], src, (size_t)mc * h->d * 8);
+                src = h->stage[i & 1];
+            }
+            CK(cudaMemcpyAsync(buf, src, (size_t)mc * h->d * 8, cudaMemcpyHostToDevice, h->copy_stream));
             CK(cudaEventRecord(h->ev_copied[i], h->copy_stream));
             CK(cudaStreamWaitEvent(h->stream, h->ev_copied[i], 0));
             rc = score_dev(h, buf, mc, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,

@@ -33,7 +33,7 @@ constexpr int GEMM_SMEM_PAD = RING_PAD + 1024 + 64 + 2048;
 // latency-critical panel solve / next-panel update of the Cholesky chain: 4x more CTAs, 1/4 the time each).
 // The 32-row chain tiles contract over K = 128 only (8 k-steps): their ring holds all 8 steps, so every operand
 // load is in flight before the first DMMA instead of trickling through a 4-deep ring (latency, not bandwidth).
-__host__ __device__ constexpr int gemm_nstage(int mi) { return mi == 2 ? 8 : NSTAGE; }
+__host__ __device__ constexpr int gemm_nstage(int mi) { return mi <= 2 ? 8 : NSTAGE; }
 constexpr int gemm_smem_bytes(int loader, int mi) {
     return mi == 8 ? (loader == LOADER_TMA ? GEMM_SMEM_TMA : GEMM_SMEM_PAD)
                    : gemm_nstage(mi) * ((16 * mi + BN) * (loader == LOADER_TMA ? BK : PAD_STRIDE) * 8) + 1024 + 64 + 2048;
@@ -150,7 +150,7 @@ gpk_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // start while the producing kernel drains; nothing is read before the dependency is resolved.
     cudaGridDependencySynchronize();
     if (g.status != nullptr && *g.status != 0) return;
-    static_assert(MI == 8 || MI == 4 || MI == 2, "tile height 128, 64 or 32");
+    static_assert(MI == 8 || MI == 4 || MI == 2 || MI == 1, "tile height 128, 64, 32 or 16");
     static_assert(EPI == EPI_STORE || MI == 8, "column-reduce epilogue uses full tiles");
     constexpr int TM = 16 * MI;                                          // tile rows (A rows)
     constexpr int NS = gemm_nstage(MI);                                  // ring depth

@@ -126,11 +126,12 @@ def test_cholesky_variants_agree():
     from robo_b200 import _lib
     X, y, _, theta, noise = O.synthetic_problem(600, 5, 1, seed_train=11)
     ref = None
-    for diag, la, st in ((3, 1, 1), (4, 1, 1), (2, 1, 1), (0, 1, 1), (3, 0, 1), (2, 0, 1), (3, 1, 0), (0, 0, 0)):
+    for diag, la, st in ((3, 1, 1), (4, 1, 1), (4, 1, 0), (2, 1, 1), (0, 1, 1), (3, 0, 1), (2, 0, 1), (3, 1, 0), (0, 0, 0)):
         h = _lib.Handle(0)
         h.set_option("diag", diag)
         h.set_option("lookahead", la)
         h.set_option("smalltile", st)
+        h.set_option("fusechain", 1 if (diag, la, st) == (4, 1, 1) else 0)     # fused chain step with the default kernels
         h.set_data(X, y)
         f = product_kernel("matern52", theta, 5).flatten()
         h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
@@ -697,6 +698,29 @@ def test_piecewise_host_feeding_is_invisible():
     h.set_option("chunk", 16384)
     r4 = h.acq(Xs, _lib.ACQ_LCB, 0.0, 1.0, want_values=True)
     assert r3["best_idx"] == r4["best_idx"] == int(np.argmax(r4["values"]))
+
+
+def test_pageable_batches_are_staged_through_pinned_buffers():
+    """host candidate batches above 1 MB that are not page-locked go through the handle's two pinned staging buffers
+    (gpk_acq), one-shot and piecewise; page-locked callers' buffers are used in place: identical results either way."""
+    import torch
+    from robo_b200 import _lib
+    X, y, _, theta, noise = O.synthetic_problem(300, 4, 1, seed_train=3)
+    Xs = np.random.RandomState(9).rand(40000, 4)               # 1.28 MB
+    h, _, _, _, _ = _handle_for("matern52", theta, X, y, noise)
+    eta = float(np.min(y))
+    r1 = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)          # staged, one piece
+    h.set_option("chunk", 1024)                                                          # staged, 10 pieces of 4096
+    r2 = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
+    pinned = torch.from_numpy(Xs).pin_memory()
+    r3 = h.acq(pinned.numpy(), _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)   # used in place
+    for r in (r2, r3):
+        for k in ("values", "mu", "var"):
+            np.testing.assert_array_equal(r1[k], r[k])
+        assert r["best_idx"] == r1["best_idx"] == int(np.argmax(r1["values"]))
+    st = O.gp_fit(oracle_kernel("matern52", theta, 4), X, y, noise=noise, normalize_input=False)
+    assert_acq_close(r1["values"][:2000], O.acquisition(st, Xs[:2000], "ei"))
+    h.close()
 
 
 def test_full_size_properties():

@@ -14,7 +14,8 @@ from robo_b200 import _lib                     # noqa: E402
 from robo_b200 import kernels as K             # noqa: E402
 
 VARIANTS = [tuple(int(x) for x in v.split(":")) for v in
-            os.environ.get("VARIANTS", "2:0,3:0").split(",")]          # diag:chain
+            os.environ.get("VARIANTS", "2:0,3:0").split(",")]          # diag:fusechain
+SMALLTILE = int(os.environ.get("SMALLTILE", 1))                        # 1 = 32-row chain tiles, 2 = 16-row
 SIZES = [int(s) for s in os.environ.get("SIZES", "4096").split(",")]
 TINY = 1.25e-12
 bad = 0
@@ -32,8 +33,9 @@ def problem(n, d, seed=1234):
 def handle(X, y, f, diag, chain):
     h = _lib.Handle(0)
     h.set_option("diag", diag)
+    h.set_option("smalltile", SMALLTILE)
     if chain:
-        h.set_option("chain", chain)
+        h.set_option("fusechain", chain)
     h.set_data(X, y)
     h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
     return h
