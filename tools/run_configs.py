@@ -51,9 +51,11 @@ def c3():
         ts.append(time.perf_counter() - t0)
     t = h.timings()
     return {"config": "C3 batched EI, N=1024 D=8 M=2^20, 1 GPU, host candidates (H2D included)",
-            "wall_ms": 1e3 * min(ts), "ei_per_s": M / min(ts), "device_score_ms": t["score_ms"],
-            "ei_per_s_device": M / (t["score_ms"] * 1e-3), "fit_ms": t["fit_ms"], "best_idx": r["best_idx"],
-            "roofline_tflops": M * (N * N + 2 * N) / (t["score_ms"] * 1e-3) / 1e12}
+            "wall_ms": 1e3 * min(ts), "ei_per_s": M / min(ts), "last_piece_score_ms": t["score_ms"],
+            "fit_ms": t["fit_ms"], "best_idx": r["best_idx"],
+            # the host batch is fed in 16 pieces of 65536 candidates; the handle's score timer covers the last one only,
+            # so the achieved rate is taken over the wall time (copies included)
+            "tflops_over_wall": M * (N * N + N * (3 * D + 40) + 2 * N) / min(ts) / 1e12}
 
 
 def c4():
