@@ -294,16 +294,17 @@ def run_ours(args, rank, world, local_rank):
     append_ms = None
     if rank == 0:
         try:
-            h2 = _lib.Handle(dev.index or 0)
-            h2.set_data(X[:N_TRAIN - 8], y[:N_TRAIN - 8])
-            h2.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
-            h2.fit(diag_add, float(np.mean(y[:N_TRAIN - 8])))
-            h2.predict(Xs[:128])
-            res = h2.fit_append(X, y, diag_add, mean)
-            if res is not None:
-                append_ms = h2.timings()["fit_ms"]
-                assert abs(res[1] - ll) <= 1e-10 * abs(ll), "incremental refit disagrees with the full fit"
-            h2.close()
+            for rep in range(2):                                 # the first pass loads the kernels of this path
+                h2 = _lib.Handle(dev.index or 0)
+                h2.set_data(X[:N_TRAIN - 8], y[:N_TRAIN - 8])
+                h2.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+                h2.fit(diag_add, float(np.mean(y[:N_TRAIN - 8])))
+                h2.predict(Xs[:128])
+                res = h2.fit_append(X, y, diag_add, mean)
+                if res is not None:
+                    append_ms = h2.timings()["fit_ms"]
+                    assert abs(res[1] - ll) <= 1e-10 * abs(ll), "incremental refit disagrees with the full fit"
+                h2.close()
         except Exception as e:                                   # noqa: BLE001
             print("fit_append timing skipped: %r" % (e,), file=sys.stderr)
     line = {

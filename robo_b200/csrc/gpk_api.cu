@@ -829,7 +829,7 @@ int gpk_set_data(gpk_handle* h, const double* X, const double* y, int n, int d) 
     const long NP = round_up(n, BM);
     int rc;
     bool g1, g2, g3, g4;
-    if ((rc = ensure(h, h->Xrow, (size_t)n * d * 8))) return rc;
+    if ((rc = ensure(h, h->Xrow, (size_t)NP * d * 8))) return rc;      // room for the rows gpk_fit_append may add
     if ((rc = ensure(h, h->Xt, (size_t)d * NP * 8))) return rc;
     if ((rc = ensure(h, h->y, (size_t)NP * 8))) return rc;
     if ((rc = ensure(h, h->Kbuf, (size_t)(NP + BM) * NP * 8, &g1))) return rc;
@@ -1153,7 +1153,7 @@ int gpk_fit_append(gpk_handle* h, const double* X, const double* y, int n, int d
     if ((rc = ensure(h, h->tmp1, (size_t)NP * 8))) return rc;
     CK(cudaEventRecord(h->ev[0], h->stream));
     // inputs (everything is re-uploaded: 8 n (d + 1) bytes; the first h->n rows of X must be the ones already fitted)
-    if ((rc = ensure(h, h->Xrow, (size_t)n * d * 8))) return rc;
+    if ((rc = ensure(h, h->Xrow, (size_t)NP * d * 8))) return rc;      // no-op: gpk_set_data sized it for NP rows
     CK(cudaMemcpyAsync(h->Xrow.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->y.p, 0, (size_t)NP * 8, h->stream));
     CK(cudaMemcpyAsync(h->y.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
