@@ -121,17 +121,18 @@ def test_cholesky_forward_solve_logdet(N, D, loader):
 
 
 def test_cholesky_variants_agree():
-    """every implementation switch (diagonal-block kernel, look-ahead, 32-row chain tiles) yields the same
-    factor to rounding"""
+    """every implementation switch (diagonal-block kernel, look-ahead, 128 / 32 / 16-row chain tiles, fused chain
+    step) yields the same factor to rounding"""
     from robo_b200 import _lib
     X, y, _, theta, noise = O.synthetic_problem(600, 5, 1, seed_train=11)
     ref = None
-    for diag, la, st in ((3, 1, 1), (4, 1, 1), (4, 1, 0), (2, 1, 1), (0, 1, 1), (3, 0, 1), (2, 0, 1), (3, 1, 0), (0, 0, 0)):
+    for diag, la, st, fuse in ((3, 1, 1, 0), (4, 1, 1, 0), (4, 1, 1, 1), (4, 1, 0, 0), (4, 1, 2, 0), (2, 1, 1, 0), (0, 1, 1, 0),
+                               (3, 0, 1, 0), (2, 0, 1, 0), (3, 1, 0, 0), (0, 0, 0, 0)):
         h = _lib.Handle(0)
         h.set_option("diag", diag)
         h.set_option("lookahead", la)
         h.set_option("smalltile", st)
-        h.set_option("fusechain", 1 if (diag, la, st) == (4, 1, 1) else 0)     # fused chain step with the default kernels
+        h.set_option("fusechain", fuse)
         h.set_data(X, y)
         f = product_kernel("matern52", theta, 5).flatten()
         h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
