@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""One-off full-size check of config 5 (N=8192, D=32): GPU log-likelihood against the CPU oracle (about a
+"""TEST INFRASTRUCTURE (lives under tests/ because it calls the oracle; not collected by pytest: run by hand on a GPU box).
+One-off full-size check of config 5 (N=8192, D=32): GPU log-likelihood against the CPU oracle (about a
 minute of numpy/LAPACK), GPU gradient against central differences of the GPU nll."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))     # repo root (tests/..)
 sys.path.insert(0, ROOT)
 from robo_b200 import _lib
 from robo_b200 import kernels as K
