@@ -1,12 +1,13 @@
-// Blocked diagonal-block kernel (option diag = 3; same contract as gpk_potrf_diag_fused_kernel):
+// Blocked diagonal-block kernels (option diag = 3: DFMA register tiles, this part of the file; diag = 4, the default:
+// DMMA fragments, second part; same contract as gpk_potrf_diag_fused_kernel):
 //   L_kk = chol(A_kk) and inv(L_kk) of one 128 x 128 diagonal block, one CTA of 256 threads.
 //
 // The column-by-column kernel pays one block-wide barrier per pivot (128 intervals of ~950 cycles; 3/4 of its
 // issued instructions are not arithmetic).  Here the block is processed in 8 panels of 16 columns with two
 // barriers per panel:
 //   S  "factor + solve": warp 0 eliminates the published 16 x 16 diagonal sub-block in registers (lane & 15 = row)
-//      in square-root-free form (L' D L'^T): the serial chain per pivot is mul -> fma -> reciprocal, the raw column is
-//      broadcast with shuffles before its pivot's reciprocal is known, and the 16 rsqrt that give the Cholesky factor
+//      in square-root-free form (L' D L'^T): the serial chain per pivot is mul -> fma -> reciprocal, the raw column goes
+//      through a warp-private shared vector before its pivot's reciprocal is known, and the 16 rsqrt that give the factor
 //      L = L' D^1/2 run in parallel after the last pivot.  Every column of L' is published through shared memory and
 //      signalled with a named barrier (bar.arrive, one id per pivot); warps 1..4 wait on that id (bar.sync) and apply
 //      it to one unit-lower forward substitution per thread -- the 128 - 16(p+1) rows of the panel below the
@@ -127,10 +128,10 @@ __device__ __forceinline__ void d3_update(double (&A)[8][8], D3Smem& sm, int ty,
 
 // ---- coalesced 128-bit stores of what panel kp finished: the factorised sub-block, the solved panel rows below it
 // (final L values) and the row block of the inverse up to its diagonal (what lies right of it is zeroed off the
-// chain by gpk_diag_prezero_kernel).  Executed by threads t = 0..nth-1.  One SM drains global stores at only ~20 B per
-// cycle (130 KB per block = 6.5k cycles): issued by the warps that do the arithmetic they stall those warps on the
-// full store queue (1.4k cycles per panel), so the stores of panel p-1 are issued by the three warps that idle during
-// phase S of panel p and drain behind it.
+// chain by gpk_diag_prezero_kernel).  Executed by threads t = 0..nth-1.  Measured: issued at the start of U by all
+// threads they cost the issuing warps ~1.4k cycles per panel; issued by the three warps that idle during phase S of
+// the NEXT panel the DMMA kernel went from 69.2k to 64.3k cycles per block (a run with the stores disabled takes the
+// same time: they are hidden), while the DFMA kernel got slower (70.8k -> 77.8k) and keeps them at the start of U.
 template <class SM>
 __device__ __forceinline__ void d3_store_panel(const SM& sm, const int kp, const int t, const int nth,
                                                double* __restrict__ Kt, const long ld, double* __restrict__ Pt, const long ldp)
