@@ -330,9 +330,9 @@ def run_ours(args, rank, world, local_rank):
                      "dgemm_cublas_tflops": dgemm, "frac_of_cublas_dgemm": achieved / dgemm if dgemm > 0 else None,
                      "launch_ms": gemm_ms, "launch_candidates": int(last_rows),
                      "launches_averaged": int(max(1, (M + rows - 1) // rows - 1)) if M > rows else 1,
-                     "traffic": 1.598e9 if last_rows == 16384 else None,
+                     "traffic": 1.5977e9 if last_rows == 16384 else None,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one 16384-candidate "
-                                       "launch (profiles/r01_vargemm_ws_ncu_full_raw.csv); algorithmic minimum 0.60e9 "
+                                       "launch (profiles/r01b_vargemm_ws_ncu_full_raw.csv: 1.584 GB read + 13.3 MB written); algorithmic minimum 0.60e9 "
                                        "(L^-1 lower triangle 67 MB + K* 537 MB read once)"},
         "kernel_ms_last_chunk": {k: tim[k] for k in ("kstar_ms", "vargemm_ms", "finish_ms")},
         "cpu_baseline": cpu, "clocks": clocks,
