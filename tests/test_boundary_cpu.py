@@ -104,3 +104,25 @@ def test_model_api_surface_matches_reference():
         m.predict(np.zeros((3, 2)))
     with pytest.raises(AssertionError):
         m.train(np.zeros((3, 2)), np.zeros((4,)))
+
+
+def test_bench_reference_arm_contract_and_loud_failure_without_gpu():
+    """bench.py --impl reference prints the contract's JSON line from the oracle port on the host cores; the product arm
+    must refuse to run without a CUDA device (no CPU fallback)."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "EI evals/s" and line["higher_is_better"] is True
+    assert line["steps"] == 1 and line["n_gpus"] == 1 and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "EI evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    if not torch.cuda.is_available():
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
+                             capture_output=True, text=True, timeout=600, cwd=root)
+        assert out.returncode != 0 and "CUDA" in (out.stderr + out.stdout)
