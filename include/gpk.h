@@ -136,6 +136,11 @@ int gpk_predict(gpk_handle* h, const double* Xs, long m, double* mu, double* var
  * clipped to >= DBL_EPSILON like the reference does. */
 int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double* cov);
 
+/* The same without the clip: the raw posterior covariance K** - K* K^-1 K*^T (negative off-diagonal entries kept,
+ * output transform applied).  This is what george's GP.sample_conditional draws from at gaussian_process.py:324
+ * (sample_functions); only predict() clips (:290-294). */
+int gpk_posterior_cov(gpk_handle* h, const double* Xs, long m, double* mu, double* cov);
+
 /* Fused predict -> acquisition -> argmax.  out (m values) may be NULL when only the argmax
  * is wanted.  best_idx follows numpy.argmax (first maximum; NaN counts as maximum) as used at
  * robo/maximizers/random_sampling.py:50.  n_negative counts EI values < 0 (the reference
@@ -189,10 +194,50 @@ int gpk_acq_moments(gpk_handle* h, const double* mu, const double* var, long m, 
 int gpk_reduce_models(gpk_handle* h, const double* A, const double* B, int n_models, long m, int mode,
                       double* out1, double* out2);
 
+/* One candidate batch against the n_models fitted handles of a GP-MCMC model (all on one device, same input
+ * dimension), reduced over the models ON THE DEVICE: the batch goes H2D once, every model scores it on its own stream
+ * (the small launches overlap), and only the reduced vectors come back.  Xs: (m, d) raw host inputs.
+ *   mode 0: out1 = mean_i acq_i(x)  with eta[i] the incumbent of model i      MarginalizationGPMCMC.compute
+ *           (robo/acquisition_functions/marginalization.py:115-121); best_val/best_idx = numpy.argmax of out1 (may be
+ *           NULL); n_negative = EI values < 0 over all models (ei.py:86-88 raises on any)
+ *   mode 1: out1 = mean_i mu_i, out2 = var_i(mu_i) + mean_i var_i clipped at DBL_EPSILON   GaussianProcessMCMC.predict
+ *           (robo/models/gaussian_process_mcmc.py:235-247); acq_kind / eta / par ignored */
+int gpk_acq_multi(gpk_handle* const* models, int n_models, const double* Xs, long m, int mode, int acq_kind,
+                  const double* eta, double par, double* out1, double* out2, long* n_negative, double* best_val,
+                  long* best_idx);
+
 /* kernel.get_value(X1, X2) (test/test_models/test_gaussian_process.py:44-46) with the
  * handle's current kernel; no input scaling.  out is (n1, n2) row-major. */
 int gpk_kernel_matrix(gpk_handle* h, const double* X1, long n1, const double* X2, long n2,
                       int d, double* out);
+
+/* ---- multi-GPU: candidate shards, one 16-byte exchange per arg-max -------------------- */
+/* One process per GPU, one handle per process.  The fit state is replicated (every rank calls gpk_set_data /
+ * gpk_set_kernel / gpk_fit with the same inputs: zero communication), rank r scores the contiguous slice
+ * gpk_shard_bounds(m, r, world) of the candidate list, and the ranks agree on numpy.argmax of the whole list
+ * (robo/maximizers/random_sampling.py:50: first maximum, NaN first) through ONE ncclAllGather of the 16-byte
+ * {value, global index} pair on the handle's stream followed by a deterministic merge on the device.  NCCL is bound at
+ * run time (dlopen of libnccl.so.2; GPK_NCCL_LIB overrides), so the library itself links cudart only. */
+int gpk_comm_unique_id(void* id128);           /* rank 0: ncclGetUniqueId; ship the 128 bytes to the other ranks */
+int gpk_comm_init(gpk_handle* h, int rank, int world, const void* id128);    /* collective over all ranks */
+int gpk_comm_destroy(gpk_handle* h);
+int gpk_comm_info(gpk_handle* h, int* rank, int* world, int* nccl_version);
+int gpk_shard_bounds(long m, int rank, int world, long* lo, long* hi);       /* sizes differ by at most one */
+/* Xs: the FULL candidate batch (m_total, d), identical host array on every rank; each rank copies and scores only its
+ * slice.  Returns the global arg-max on every rank. */
+int gpk_acq_argmax_sharded(gpk_handle* h, const double* Xs, long m_total, int acq_kind, double eta, double par,
+                           double* best_val, long* best_idx);
+/* Device-resident shard, asynchronous on the handle's stream, no host synchronisation: d_Xs_shard is this rank's
+ * (m_shard, d) slice whose first row has global index first_global (m_shard may be 0); d_best (16 bytes, device)
+ * receives the merged {double value; long long global index}. */
+int gpk_acq_argmax_sharded_dev(gpk_handle* h, const void* d_Xs_shard, long m_shard, long first_global, int acq_kind,
+                               double eta, double par, void* d_best);
+/* gpk_maximize_random over n_total device-generated candidates split across the ranks (Philox keyed by the global
+ * index: the result does not depend on the number of GPUs); best_x is re-created on every rank from the winning index. */
+int gpk_maximize_random_sharded(gpk_handle* h, unsigned long long seed, long n_total, long n_uniform,
+                                const double* lower, const double* upper, const double* incumbent, double scale,
+                                int acq_kind, double eta, double par,
+                                double* best_x, double* best_val, long* best_idx);
 
 /* ---- marginal-likelihood gradient (gaussian_process.py:168-191, corrected noise term) -- */
 /* grad[n_terms + 2] = d(-loglik)/d[log_amp, log_metric_t..., log sigma^2]; requires a

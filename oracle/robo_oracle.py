@@ -150,6 +150,76 @@ def gp_predict_var_only(st, X_test):
     return mu, np.clip(var, EPS, np.inf)
 
 
+def flatten_kernel(kernel):
+    """Product tree of ConstantKernels and radial kernels of ONE family -> the flat description oracle/kmat.c takes
+    (family id, amplitude, per-term axis / metric / group-closing flag)."""
+    fam_id = {G.Matern52Kernel: 0, G.ExpSquaredKernel: 1, G.Matern32Kernel: 2}
+    amp, fams, axis, metric, last = [1.0], set(), [], [], []
+
+    def walk(k):
+        if isinstance(k, G.Product):
+            walk(k.k1)
+            walk(k.k2)
+        elif isinstance(k, G.ConstantKernel):
+            amp[0] = amp[0] * np.exp(k.log_constant)
+        elif type(k) in fam_id:
+            fams.add(fam_id[type(k)])
+            m = k._axis_metric()
+            for a, md in zip(k.axes, m):
+                axis.append(int(a))
+                metric.append(float(md))
+                last.append(0)
+            last[-1] = 1
+        else:
+            raise TypeError("flatten_kernel: unsupported kernel %r" % type(k))
+    walk(kernel)
+    if len(fams) != 1:
+        raise TypeError("flatten_kernel: exactly one radial family expected")
+    return dict(family=fams.pop(), amp=float(amp[0]), axis=np.array(axis, dtype=np.int32),
+                last=np.array(last, dtype=np.int32), metric=np.array(metric, dtype=np.float64))
+
+
+def kmat_fast(kernel, X1, X2):
+    """kernel.get_value(X1, X2) through the threaded C restatement (oracle/kmat.c); equal to the numpy path to a few
+    ulp (tests/test_oracle_golden.py)."""
+    import ctypes as C
+    from oracle import build_c
+    lib = build_c.load()
+    f = flatten_kernel(kernel)
+    X1 = np.ascontiguousarray(X1, dtype=np.float64)
+    X2 = np.ascontiguousarray(X2, dtype=np.float64)
+    out = np.empty((len(X1), len(X2)))
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    lib.oracle_kmat(f["family"], f["amp"], len(f["axis"]), f["axis"].ctypes.data_as(ip), f["last"].ctypes.data_as(ip),
+                    f["metric"].ctypes.data_as(dp), X1.ctypes.data_as(dp), len(X1), X2.ctypes.data_as(dp), len(X2),
+                    X1.shape[1], out.ctypes.data_as(dp))
+    return out
+
+
+def gp_predict_var_only_fast(st, X_test, chunk=8192):
+    """gp_predict_var_only for candidate batches of BASELINE size (2^20): K* from the threaded C restatement, chunked
+    so that the working set stays bounded.  Same formulas, same clip."""
+    X_test = np.asarray(X_test, dtype=np.float64)
+    if st["normalize_input"]:
+        Xs, _, _ = zero_one_normalization(X_test, st["lower"], st["upper"])
+    else:
+        Xs = X_test
+    gp = st["gp"]
+    alpha = gp._compute_alpha(st["y"])
+    U = gp.solver._factor[0]
+    kss = gp.kernel.get_value(Xs[:1], Xs[:1])[0, 0]
+    mu, var = np.empty(len(Xs)), np.empty(len(Xs))
+    for lo in range(0, len(Xs), chunk):
+        Ks = kmat_fast(gp.kernel, Xs[lo:lo + chunk], gp._x)
+        mu[lo:lo + chunk] = Ks @ alpha + st["mean"]
+        V = spla.solve_triangular(U, Ks.T, trans="T", lower=False, check_finite=False)
+        var[lo:lo + chunk] = kss - np.einsum("ij,ij->j", V, V)
+    if st["normalize_output"]:
+        mu = mu * st["y_std"] + st["y_mean"]
+        var = var * st["y_std"] ** 2
+    return mu, np.clip(var, EPS, np.inf)
+
+
 def gp_predict_variance(st, x1, X2):
     """GaussianProcess.predict_variance: gaussian_process.py:221-248."""
     x_ = np.concatenate((x1, X2))
@@ -185,6 +255,31 @@ def gp_grad_nll_correct(st, theta):
     g = 0.5 * np.einsum("ijk,ij", Kg, A)
     g_noise = 0.5 * noise * np.trace(A)
     return -np.append(g, g_noise)
+
+
+def gp_grad_nll_terms_fast(st, theta, recompute=True):
+    """gp_grad_nll_correct for BASELINE-size problems (config 5: N = 8192, D = 32, where the (N, N, H) array of
+    gaussian_process.py:181 would need 18 GB): same formula, the einsum of :186 evaluated by the threaded C restatement
+    without materialising dK/dtheta.  Returns d(-loglik)/d[log amp, log metric per kernel TERM ..., log sigma^2]
+    (one entry per axis of every radial factor: isotropic kernels are the sum of their terms)."""
+    import ctypes as C
+    from oracle import build_c
+    gp = st["gp"]
+    noise = np.exp(theta[-1])
+    if recompute:                       # False: st was fitted with exactly these hyper-parameters (saves a K build)
+        gp.kernel.set_parameter_vector(theta[:-1])
+        gp.compute(st["X"], yerr=np.sqrt(noise))
+    alpha = gp._compute_alpha(st["y"])
+    Kinv = gp.solver.get_inverse()
+    A = np.ascontiguousarray(np.outer(alpha, alpha) - Kinv)
+    f = flatten_kernel(gp.kernel)
+    X = np.ascontiguousarray(gp._x, dtype=np.float64)
+    g = np.zeros(len(f["axis"]) + 1)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    build_c.load().oracle_grad_trace(f["family"], f["amp"], len(f["axis"]), f["axis"].ctypes.data_as(ip),
+                                     f["last"].ctypes.data_as(ip), f["metric"].ctypes.data_as(dp), X.ctypes.data_as(dp),
+                                     len(X), X.shape[1], A.ctypes.data_as(dp), g.ctypes.data_as(dp))
+    return -np.append(0.5 * g, 0.5 * noise * np.trace(A))
 
 
 def gp_grad_nll_reference_compat(st, theta):

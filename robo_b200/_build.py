@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpk.so")
 SOURCES = ["gpk_api.cu"]
-HEADERS = ["gpk_internal.cuh", "gpk_gemm.cuh", "gpk_kernels.cuh", "gpk_diag16.cuh", "gpk_chain.cuh", os.path.join("..", "..", "include", "gpk.h")]
+HEADERS = ["gpk_internal.cuh", "gpk_gemm.cuh", "gpk_kernels.cuh", "gpk_diag16.cuh", "gpk_chain.cuh", "gpk_multi.inl", os.path.join("..", "..", "include", "gpk.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -28,15 +28,32 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile the CUDA library if it is missing or older than its sources."""
+    """Compile the CUDA library if it is missing or older than its sources.  nvcc writes to a temporary file that is
+    renamed over libgpk.so under an exclusive file lock, so concurrent ranks (torchrun) never load a half-written
+    library and only one of them compiles."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():          # another process built it while we waited
+                return LIB
+            tmp = "%s.%d.tmp" % (LIB, os.getpid())
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            try:
+                res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            except OSError as e:
+                raise RuntimeError("nvcc could not be started: %s" % e)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout)
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

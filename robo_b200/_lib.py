@@ -40,6 +40,7 @@ _SIGNATURES = {
     "gpk_fit_append": [_vp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp],
     "gpk_predict": [_vp, _dp, C.c_long, _dp, _dp],
     "gpk_predict_cov": [_vp, _dp, C.c_long, _dp, _dp],
+    "gpk_posterior_cov": [_vp, _dp, C.c_long, _dp, _dp],
     "gpk_acq": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _lp, _lp],
     "gpk_acq_dev": [_vp, _vp, C.c_long, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp],
     "gpk_predict_grad": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp],
@@ -49,6 +50,16 @@ _SIGNATURES = {
     "gpk_acq_moments": [_vp, _dp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _lp],
     "gpk_kernel_matrix": [_vp, _dp, C.c_long, _dp, C.c_long, C.c_int, _dp],
     "gpk_reduce_models": [_vp, _dp, _dp, C.c_int, C.c_long, C.c_int, _dp, _dp],
+    "gpk_acq_multi": [C.POINTER(_vp), C.c_int, _dp, C.c_long, C.c_int, C.c_int, _dp, C.c_double, _dp, _dp, _lp, _dp, _lp],
+    "gpk_comm_unique_id": [_vp],
+    "gpk_comm_init": [_vp, C.c_int, C.c_int, _vp],
+    "gpk_comm_destroy": [_vp],
+    "gpk_comm_info": [_vp, _ip, _ip, _ip],
+    "gpk_shard_bounds": [C.c_long, C.c_int, C.c_int, _lp, _lp],
+    "gpk_acq_argmax_sharded": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _lp],
+    "gpk_acq_argmax_sharded_dev": [_vp, _vp, C.c_long, C.c_long, C.c_int, C.c_double, C.c_double, _vp],
+    "gpk_maximize_random_sharded": [_vp, C.c_ulonglong, C.c_long, C.c_long, _dp, _dp, _dp, C.c_double, C.c_int,
+                                    C.c_double, C.c_double, _dp, _dp, _lp],
     "gpk_nll_grad": [_vp, C.c_double, _dp],
     "gpk_measure_fp64_peaks": [_vp, _dp, _dp],
     "gpk_get_factor": [_vp, _dp],
@@ -74,9 +85,14 @@ def load(build_if_missing=True):
     if build_if_missing and os.environ.get("GPK_NO_BUILD") != "1":
         try:
             _build.build()
-        except Exception:
+        except Exception as e:
             if not os.path.exists(path):
                 raise
+            # sources are newer than the binary and cannot be rebuilt (no nvcc on this box): the binary that travelled
+            # with the tree is used, loudly; the ABI check below still refuses a library that lacks a declared symbol
+            import warnings
+            warnings.warn("libgpk.so is older than its sources and could not be rebuilt (%s); using the existing binary"
+                          % str(e).splitlines()[0])
     if not os.path.exists(path):
         raise RuntimeError("libgpk.so is missing (%s) and could not be built; there is no CPU fallback" % path)
     lib = C.CDLL(path)
@@ -223,6 +239,14 @@ class Handle(object):
         self._check(self.lib.gpk_predict_cov(self._h, _as_dp(Xs), m, _as_dp(mu), _as_dp(cov)))
         return mu, cov
 
+    def posterior_cov(self, Xs):
+        """(mu, cov) with the raw, unclipped posterior covariance (sampling; gpk_posterior_cov)."""
+        Xs = f64(Xs)
+        m = Xs.shape[0]
+        mu, cov = np.empty(m), np.empty((m, m))
+        self._check(self.lib.gpk_posterior_cov(self._h, _as_dp(Xs), m, _as_dp(mu), _as_dp(cov)))
+        return mu, cov
+
     def acq(self, Xs, kind, eta=0.0, par=0.0, want_values=True, want_moments=False):
         """-> dict(values, mu, var, best_val, best_idx, n_negative)"""
         Xs = f64(Xs)
@@ -273,6 +297,41 @@ class Handle(object):
         self._check(self.lib.gpk_generate_candidates(self._h, int(seed), int(first), int(count), int(n_uniform), lo.size,
                                                      _as_dp(lo), _as_dp(up), _as_dp(inc), float(scale), _as_dp(out)))
         return out
+
+    # -- multi-GPU (gpk_comm_*) -----------------------------------------------------------
+    def comm_init(self, rank, world, unique_id=None):
+        """Collective over all ranks.  unique_id: the 128 bytes of comm_unique_id() made on rank 0."""
+        buf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        self._check(self.lib.gpk_comm_init(self._h, int(rank), int(world), C.cast(buf, _vp) if buf is not None else None))
+
+    def comm_destroy(self):
+        self._check(self.lib.gpk_comm_destroy(self._h))
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.gpk_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return dict(rank=r.value, world=w.value, nccl_version=v.value)
+
+    def acq_argmax_sharded(self, Xs_all, kind, eta=0.0, par=0.0):
+        """Xs_all: the full batch, identical on every rank -> (best value, best GLOBAL index) on every rank."""
+        Xs_all = f64(Xs_all)
+        bv, bi = C.c_double(), C.c_long(-1)
+        self._check(self.lib.gpk_acq_argmax_sharded(self._h, _as_dp(Xs_all), Xs_all.shape[0], int(kind), float(eta),
+                                                    float(par), C.byref(bv), C.byref(bi)))
+        return bv.value, bi.value
+
+    def acq_argmax_sharded_dev(self, d_Xs_ptr, m_shard, first_global, kind, eta, par, d_best_ptr=0):
+        self._check(self.lib.gpk_acq_argmax_sharded_dev(self._h, _vp(d_Xs_ptr or 0), int(m_shard), int(first_global),
+                                                        int(kind), float(eta), float(par), _vp(d_best_ptr or 0)))
+
+    def maximize_random_sharded(self, seed, n_total, n_uniform, lower, upper, incumbent, scale, kind, eta=0.0, par=0.0):
+        lo, up, inc = f64(lower).ravel(), f64(upper).ravel(), f64(incumbent).ravel()
+        bx = np.empty(lo.size)
+        bv, bi = C.c_double(), C.c_long(-1)
+        self._check(self.lib.gpk_maximize_random_sharded(self._h, int(seed), int(n_total), int(n_uniform), _as_dp(lo),
+                                                         _as_dp(up), _as_dp(inc), float(scale), int(kind), float(eta),
+                                                         float(par), _as_dp(bx), C.byref(bv), C.byref(bi)))
+        return bx, bv.value, bi.value
 
     def acq_moments(self, mu, var, kind, eta=0.0, par=0.0):
         mu, var = f64(mu).ravel(), f64(var).ravel()
@@ -341,6 +400,43 @@ class Handle(object):
         keys = ["fit_ms", "kbuild_ms", "potrf_ms", "linv_ms", "score_ms", "kstar_ms", "vargemm_ms", "finish_ms",
                 "launches_vargemm", "launches_total"]
         return dict(zip(keys, t.tolist()))
+
+
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 makes it and ships it to the other ranks by any means: file, pipe, MPI, a
+    torch.distributed store ...)."""
+    lib = load()
+    buf = C.create_string_buffer(128)
+    if lib.gpk_comm_unique_id(C.cast(buf, _vp)) != GPK_OK:
+        raise RuntimeError("gpk_comm_unique_id failed: NCCL (libnccl.so.2) is not available")
+    return buf.raw
+
+
+def shard_bounds(m, rank, world):
+    lib = load()
+    lo, hi = C.c_long(), C.c_long()
+    if lib.gpk_shard_bounds(int(m), int(rank), int(world), C.byref(lo), C.byref(hi)) != GPK_OK:
+        raise ValueError("shard_bounds: bad arguments")
+    return lo.value, hi.value
+
+
+def acq_multi(handles, Xs, mode, kind=ACQ_NONE, eta=None, par=0.0, want_argmax=False):
+    """gpk_acq_multi over ``handles`` (all fitted, same device).  mode 0 -> dict(values, n_negative, best_val,
+    best_idx); mode 1 -> dict(mean, var)."""
+    h0 = handles[0]
+    Xs = f64(Xs)
+    m = Xs.shape[0]
+    arr = (_vp * len(handles))(*[h._h for h in handles])
+    out1 = np.empty(m)
+    out2 = np.empty(m) if mode == 1 else None
+    etas = f64(np.zeros(len(handles)) if eta is None else np.broadcast_to(np.asarray(eta, dtype=np.float64), (len(handles),)))
+    nn, bv, bi = C.c_long(0), C.c_double(), C.c_long(-1)
+    h0._check(h0.lib.gpk_acq_multi(arr, len(handles), _as_dp(Xs), m, int(mode), int(kind), _as_dp(etas), float(par),
+                                   _as_dp(out1), _as_dp(out2) if out2 is not None else None, C.byref(nn),
+                                   C.byref(bv) if want_argmax else None, C.byref(bi) if want_argmax else None))
+    if mode == 1:
+        return dict(mean=out1, var=out2)
+    return dict(values=out1, n_negative=nn.value, best_val=bv.value, best_idx=bi.value)
 
 
 _moments_handle = {}

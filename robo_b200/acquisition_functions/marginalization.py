@@ -45,7 +45,45 @@ class MarginalizationGPMCMC(BaseAcquisitionFunction):
 
     def compute(self, X_test, derivative=False):
         n = len(self.model.models)
+        fused = self._fused_spec() if not derivative else None
+        if fused is not None:
+            # marginalization.py:115-121 as ONE call: the batch goes to the device once, the n sub-models score it
+            # concurrently and the mean over models is taken there (gpk_acq_multi mode 0); M doubles come back
+            kind, etas, par, handles = fused
+            r = _lib.acq_multi(handles, np.asarray(X_test, dtype=np.float64), 0, _lib.ACQ_KIND[kind], etas, par)
+            if kind == "ei" and r["n_negative"] > 0:
+                raise ValueError("Expected Improvement is smaller than 0!")      # ei.py:86-88
+            return r["values"]
         acquisition_values = np.zeros([n, X_test.shape[0]])
         for i in range(n):
             acquisition_values[i] = self.estimators[i].compute(X_test, derivative=derivative)
         return _lib.moments_handle().reduce_models(acquisition_values)
+
+    def argmax(self, X_test):
+        """numpy.argmax of compute(X_test) taken on the device when the fused path applies."""
+        fused = self._fused_spec()
+        if fused is None:
+            return int(np.argmax(self.compute(X_test)))
+        kind, etas, par, handles = fused
+        r = _lib.acq_multi(handles, np.asarray(X_test, dtype=np.float64), 0, _lib.ACQ_KIND[kind], etas, par,
+                           want_argmax=True)
+        if kind == "ei" and r["n_negative"] > 0:
+            raise ValueError("Expected Improvement is smaller than 0!")
+        return int(r["best_idx"])
+
+    def _fused_spec(self):
+        """(kind, eta per model, par, handles) when every estimator is a closed-form acquisition on a device GP."""
+        if self.cost_model is not None or len(self.estimators) == 0 or not hasattr(self.model, "sub_model_handles"):
+            return None
+        kinds = set(getattr(e, "kind", None) for e in self.estimators)
+        pars = set(float(getattr(e, "par", 0.0)) for e in self.estimators)
+        if len(kinds) != 1 or len(pars) != 1 or list(kinds)[0] not in ("ei", "log_ei", "pi", "lcb"):
+            return None
+        if any(e.model is not m for e, m in zip(self.estimators, self.model.models)):
+            return None
+        handles = self.model.sub_model_handles()
+        if handles is None or len(handles) != len(self.estimators):
+            return None
+        kind = list(kinds)[0]
+        etas = [0.0 if kind == "lcb" else float(e.model.get_incumbent()[1]) for e in self.estimators]
+        return kind, etas, list(pars)[0], handles

@@ -70,7 +70,7 @@ class GeorgeGP(DeviceGP):
         if return_var or not return_cov:
             mu, var = self.predict_moments(t)
             return (mu, var) if return_var else mu
-        return self.predict_cov(t)
+        return self.posterior_cov(t)          # george returns the raw covariance; the reference clips it itself
 
     def sample_conditional(self, y, t, size=1):
         mu, cov = self.predict(y, t)

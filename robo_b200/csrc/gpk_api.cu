@@ -15,6 +15,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
 
@@ -99,6 +101,14 @@ struct gpk_handle {
     double* stage[2] = {nullptr, nullptr};    // pinned staging of pageable candidate batches (gpk_acq)
     size_t stage_cap = 0;
     bool fit_pending = false;
+
+    // several models, one batch (gpk_acq_multi): buffers owned by the first handle of the call
+    DevBuf multi_cand, multi_A, multi_B, multi_out, multi_bb;
+    cudaEvent_t ev_multi = nullptr;
+    // multi-GPU (gpk_comm_*): NCCL communicator bound at run time, one 16-byte pair per rank
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    DevBuf gather, best_global;
 };
 
 namespace {
@@ -543,11 +553,12 @@ int build_linv(gpk_handle* h) {
 }
 
 // Score m candidates resident on the device.  All output pointers are device pointers or NULL.
-// index_offset: global index of dX[0] (arg-max indices and output offsets are global); reset: start a new
-// running arg-max / negative-EI count (false when a host batch is fed in several pieces)
+// index_offset: position of dX[0] in the caller's batch (offset into the output arrays and into the arg-max index);
+// global_base: added to the arg-max index only (first index of this rank's shard in a sharded batch); reset: start a
+// new running arg-max / negative-EI count (false when a host batch is fed in several pieces)
 int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, double par, double* d_out,
               double* d_mu, double* d_var, BestPair* d_best, unsigned long long* d_nneg,
-              long index_offset = 0, bool reset = true) {
+              long index_offset = 0, bool reset = true, long global_base = 0) {
     int rc = build_linv(h);
     if (rc) return rc;
     const long NP = h->NP;
@@ -646,7 +657,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         FinishArgs f;
         memset(&f, 0, sizeof(f));
         f.part_mu = ptr<double>(h->part_mu); f.part_ssq = ptr<double>(h->part_ssq);
-        f.ldpart = cap; f.nparts = h->nb; f.m = mc; f.base = index_offset + base;
+        f.ldpart = cap; f.nparts = h->nb; f.m = mc; f.base = global_base + index_offset + base;
         f.kss = h->spec.amp; f.mean = h->mean;
         f.norm_out = h->norm_out; f.y_mean = h->y_mean; f.y_std = h->y_std;
         f.acq_kind = kind; f.eta = eta; f.par = par;
@@ -676,7 +687,9 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
 // =============================================================================================
 extern "C" {
 
-const char* gpk_version(void) { return "gpk 0.1 (sm_100a, fp64 DMMA + TMA)"; }
+int gpk_comm_destroy(gpk_handle* h);
+
+const char* gpk_version(void) { return "gpk 0.2 (sm_100a, fp64 DMMA + TMA)"; }
 
 const char* gpk_last_error(gpk_handle* h) { return h ? h->err : "null handle"; }
 
@@ -716,10 +729,13 @@ int gpk_destroy(gpk_handle* h) {
     if (!h) return GPK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    gpk_comm_destroy(h);
+    if (h->ev_multi) cudaEventDestroy(h->ev_multi);
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
                       &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
-                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof};
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof,
+                      &h->multi_cand, &h->multi_A, &h->multi_B, &h->multi_out, &h->multi_bb, &h->gather, &h->best_global};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->ev_ok)
@@ -1423,7 +1439,7 @@ int gpk_predict(gpk_handle* h, const double* Xs, long m, double* mu, double* var
     return gpk_acq(h, Xs, m, GPK_ACQ_NONE, 0.0, 0.0, nullptr, mu, var, nullptr, nullptr, nullptr);
 }
 
-int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double* cov) {
+static int predict_cov_impl(gpk_handle* h, const double* Xs, long m, double* mu, double* cov, int clip) {
     int rc = require(h, true, true, true);
     if (rc) return rc;
     if (!Xs || m <= 0 || !mu || !cov) BAD("gpk_predict_cov: need Xs, mu, cov");
@@ -1500,13 +1516,21 @@ int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double*
         if ((rc = launch_gemm<EPI_STORE>(h, h->mapVt, h->mapVt, a, (int)(jobs.size() - n1)))) return rc;
     }
     gpk_cov_finish_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->cov), mp, m,
-                                                                                 h->norm_out, h->y_std);
+                                                                                 h->norm_out, h->y_std, clip);
     CKL();
     CK(cudaMemcpyAsync(mu, h->out_mu.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpy2DAsync(cov, (size_t)m * 8, h->cov.p, (size_t)mp * 8, (size_t)m * 8, (size_t)m, cudaMemcpyDeviceToHost,
                          h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return GPK_OK;
+}
+
+int gpk_predict_cov(gpk_handle* h, const double* Xs, long m, double* mu, double* cov) {
+    return predict_cov_impl(h, Xs, m, mu, cov, 1);
+}
+
+int gpk_posterior_cov(gpk_handle* h, const double* Xs, long m, double* mu, double* cov) {
+    return predict_cov_impl(h, Xs, m, mu, cov, 0);
 }
 
 int gpk_predict_grad(gpk_handle* h, const double* Xs, long m, int kind, double eta, double par, double* mu, double* var,
@@ -1833,3 +1857,5 @@ int gpk_get_timings(gpk_handle* h, double* out) {
 }
 
 }  // extern "C"
+
+#include "gpk_multi.inl"

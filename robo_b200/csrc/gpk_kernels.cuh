@@ -498,16 +498,18 @@ __global__ void gpk_acq_moments_kernel(const double* __restrict__ mu, const doub
     if (kind == GPK_ACQ_EI && v < 0.0) atomicAdd(n_negative, 1ULL);
 }
 
-// full_cov epilogue: clip every entry to >= eps after the output transform
-// (gaussian_process.py:282-294 applies the clip to the whole matrix).
-__global__ void gpk_cov_finish_kernel(double* __restrict__ cov, long ld, long m, int norm_out, double y_std)
+// full_cov epilogue: output transform, then (clip != 0) every entry clipped to >= eps
+// (gaussian_process.py:282-294 applies the clip to the whole matrix).  clip == 0 keeps the raw posterior
+// covariance, negative off-diagonal entries included: what george's sample_conditional draws from
+// (gaussian_process.py:324; only predict() clips).
+__global__ void gpk_cov_finish_kernel(double* __restrict__ cov, long ld, long m, int norm_out, double y_std, int clip)
 {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= m * m) return;
     long r = idx / m, c = idx - r * m;
     double v = cov[r * ld + c];
     if (norm_out) v *= y_std * y_std;
-    if (v < GPK_EPS) v = GPK_EPS;
+    if (clip && v < GPK_EPS) v = GPK_EPS;
     cov[r * ld + c] = v;
 }
 

@@ -197,6 +197,14 @@ class DeviceGP(object):
         self._push_cfg()
         return self.handle.predict_cov(Xs)
 
+    def posterior_cov(self, Xs):
+        """(mu, cov) with the raw posterior covariance K** - K* K^-1 K*^T: no clip, negative off-diagonal entries
+        kept.  george's GP.predict returns exactly this; the reference clips afterwards in its own predict()
+        (gaussian_process.py:290-294) and samples from the raw matrix (:324)."""
+        self._restore()
+        self._push_cfg()
+        return self.handle.posterior_cov(Xs)
+
     def predict_grad(self, Xs, kind=0, eta=0.0, par=0.0):
         self._restore()
         self._push_cfg()
@@ -208,7 +216,7 @@ class DeviceGP(object):
         return self.handle.acq(Xs, kind, eta, par, want_values, want_moments)
 
     def sample_conditional(self, y, t, size=1):
-        mu, cov = self.predict_cov(t)
+        mu, cov = self.posterior_cov(t)
         if size > 1:
             return np.random.multivariate_normal(mu, cov, size=size)
         return np.random.multivariate_normal(mu, cov)

@@ -2,13 +2,56 @@
 exchange on the path is the arg-max.
 
 NCCL has no MAXLOC, so each rank contributes its 16-byte {value, global index} pair to one
-all_gather (torch.distributed: NCCL on GPUs, gloo on CPU for the host-logic tests) and every
-rank applies the same deterministic merge: numpy.argmax ordering — NaN first, then the larger
-value, then the LOWEST global index (robo/maximizers/random_sampling.py:50 takes the first
-maximum).  Payload is 16 B per rank, so the exchange is latency-bound and candidate throughput
+all-gather and every rank applies the same deterministic merge: numpy.argmax ordering — NaN first,
+then the larger value, then the LOWEST global index (robo/maximizers/random_sampling.py:50 takes the
+first maximum).  Payload is 16 B per rank, so the exchange is latency-bound and candidate throughput
 scales with the number of GPUs.
+
+On GPUs the exchange lives behind the C ABI (include/gpk.h: gpk_comm_init, gpk_acq_argmax_sharded,
+gpk_acq_argmax_sharded_dev, gpk_maximize_random_sharded): ncclAllGather on the handle's stream, merge
+kernel, one 16-byte D2H of the winner — no torch op and no host synchronisation between scoring and
+exchange.  ``init_comm`` only has to get rank 0's 128-byte NCCL id to the other ranks; any launcher
+channel will do (a torch.distributed store under torchrun, a shared file otherwise).  The
+torch.distributed functions below (``allgather_best`` ...) are the same host logic over gloo for the
+CPU tests and for models that are not device GPs.
 """
+import os
+import time
+
 import numpy as np
+
+
+def init_comm(handle, rank, world, group=None, id_file=None, timeout_s=120.0):
+    """gpk_comm_init on ``handle`` (robo_b200._lib.Handle).  The 128-byte id made on rank 0 travels through
+    torch.distributed (object broadcast, when a process group is initialised) or through ``id_file`` (rank 0 writes
+    it atomically, the others poll)."""
+    from robo_b200 import _lib
+    if world <= 1:
+        handle.comm_init(0, 1, None)
+        return
+    uid = _lib.comm_unique_id() if rank == 0 else None
+    if id_file is not None:
+        if rank == 0:
+            tmp = "%s.%d.tmp" % (id_file, os.getpid())
+            with open(tmp, "wb") as f:
+                f.write(uid)
+            os.replace(tmp, id_file)
+        else:
+            t0 = time.time()
+            while not os.path.exists(id_file):
+                if time.time() - t0 > timeout_s:
+                    raise RuntimeError("init_comm: rank 0 never wrote %s" % id_file)
+                time.sleep(0.01)
+            with open(id_file, "rb") as f:
+                uid = f.read()
+    else:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("init_comm: pass id_file=... or initialise torch.distributed (used only to ship the id)")
+        box = [uid]
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = box[0]
+    handle.comm_init(rank, world, uid)
 
 
 def shard_bounds(m, rank, world):
@@ -70,7 +113,17 @@ def pack_pair(value, index, device="cpu"):
 
 def sharded_argmax(model, acq_kind, X_all, rank, world, eta=None, par=0.0, group=None):
     """Score this rank's contiguous shard of X_all (host array, identical on all ranks) with the
-    fused GPU path and agree on the global arg-max.  Returns (best_value, best_global_index)."""
+    fused GPU path and agree on the global arg-max.  Returns (best_value, best_global_index).
+    A device GP whose handle carries a communicator (init_comm) does all of it in one C-ABI call."""
+    gp = getattr(model, "gp", None)
+    handle = getattr(gp, "_handle", None)
+    if handle is not None and hasattr(handle, "comm_info") and handle.comm_info()["world"] == world and world > 1:
+        from robo_b200 import _lib
+        if eta is None:
+            eta = 0.0 if acq_kind == "lcb" else model.get_incumbent()[1]
+        gp._restore()
+        gp._push_cfg()
+        return handle.acq_argmax_sharded(X_all, _lib.ACQ_KIND[acq_kind], float(eta), float(par))
     import torch
     lo, hi = shard_bounds(len(X_all), rank, world)
     if hi > lo:

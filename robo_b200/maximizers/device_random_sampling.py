@@ -35,16 +35,27 @@ class DeviceRandomSampling(BaseMaximizer):
         eta = 0.0 if acq.kind == "lcb" else float(inc_y)
         seed = (self.seed + 0x9E3779B97F4A7C15 * self.calls) & 0xFFFFFFFFFFFFFFFF
         self.calls += 1
+        # random_sampling.py:38-47: int(0.7 n) uniform points followed by int(0.3 n) Gaussian ones (n = 5 gives 3 + 1)
         n_uniform = int(self.n_samples * .7)
-        lo, hi = shard_bounds(self.n_samples, self.rank, self.world)
+        n_total = n_uniform + int(self.n_samples * .3)
         model.gp._restore()
         model.gp._push_cfg()
-        x, val, idx = model.gp.handle.maximize_random(seed, lo, hi - lo, n_uniform, self.lower, self.upper, inc_x, 0.1,
-                                                      kind, eta, acq.par)
-        if self.world > 1:
-            import torch
-            dev = "cuda:%d" % torch.cuda.current_device()
-            val, idx = allgather_best(pack_pair(val, idx, dev), self.group)
-            x = model.gp.handle.generate_candidates(seed, idx, 1, n_uniform, self.lower, self.upper, inc_x, 0.1)[0]
+        handle = model.gp.handle
+        if self.world > 1 and handle.comm_info()["world"] == self.world:
+            # candidates, scoring, exchange and merge behind one C-ABI call (gpk_maximize_random_sharded)
+            x, val, idx = handle.maximize_random_sharded(seed, n_total, n_uniform, self.lower, self.upper, inc_x, 0.1,
+                                                         kind, eta, acq.par)
+        else:
+            lo, hi = shard_bounds(n_total, self.rank, self.world)
+            if hi > lo:
+                x, val, idx = handle.maximize_random(seed, lo, hi - lo, n_uniform, self.lower, self.upper, inc_x, 0.1,
+                                                     kind, eta, acq.par)
+            else:
+                x, val, idx = None, 0.0, -1             # empty shard (world > n_samples): still joins the exchange
+            if self.world > 1:
+                import torch
+                dev = "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cpu"
+                val, idx = allgather_best(pack_pair(val, idx, dev), self.group)
+                x = handle.generate_candidates(seed, idx, 1, n_uniform, self.lower, self.upper, inc_x, 0.1)[0]
         self.last = dict(seed=seed, best_idx=idx, best_val=val)
         return x

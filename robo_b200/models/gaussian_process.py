@@ -211,7 +211,9 @@ class GaussianProcess(BaseModel):
         covariance from the device, the multivariate-normal draw with numpy like george."""
         if not self.is_trained:
             raise Exception('Model has to be trained first!')
-        mu, cov = self.gp.predict_cov(X_test)
+        # the raw (unclipped) posterior covariance, like george's sample_conditional at :324: predict()'s eps clip
+        # would erase every negative posterior correlation
+        mu, cov = self.gp.posterior_cov(X_test)
         funcs = np.random.multivariate_normal(mu, cov, n_funcs) if n_funcs > 1 \
             else np.random.multivariate_normal(mu, cov)
         if len(funcs.shape) == 1:

@@ -185,11 +185,32 @@ class GaussianProcessMCMC(BaseModel):
         fused GPU predict, the reduction over models runs on the GPU too (gpk_reduce_models)."""
         if not self.is_trained:
             raise Exception('Model has to be trained first!')
+        handles = self.sub_model_handles()
+        if handles is not None:
+            # one H2D of X_test, every sub-model scores it on its own stream, the mixture moments are reduced on the
+            # device: 2 M doubles come back instead of 2 n_hypers M (gpk_acq_multi mode 1)
+            r = _lib.acq_multi(handles, np.asarray(X_test, dtype=np.float64), 1)
+            return r["mean"], r["var"]
         mu = np.zeros([len(self.models), X_test.shape[0]])
         var = np.zeros([len(self.models), X_test.shape[0]])
         for i, model in enumerate(self.models):
             mu[i], var[i] = model.predict(X_test)
         return _lib.moments_handle(self.device).reduce_models(mu, var)
+
+    def sub_model_handles(self):
+        """The fitted gpk handles of the hyper-parameter samples (device state restored / configuration pushed), or
+        None when a sub-model is not a device GP (then callers loop over the models like the reference does)."""
+        handles = []
+        for model in self.models:
+            gp = getattr(model, "gp", None)
+            if not isinstance(gp, DeviceGP) or not getattr(model, "is_trained", False):
+                return None
+            gp._restore()
+            if not gp.computed:
+                return None
+            gp._push_cfg()
+            handles.append(gp.handle)
+        return handles if handles else None
 
     def get_incumbent(self):
         """gaussian_process_mcmc.py:251-269."""

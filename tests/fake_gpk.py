@@ -111,7 +111,7 @@ class FakeHandle(object):
         Xs = np.asarray(Xs, dtype=np.float64)
         return Xs if self.bounds is None else (Xs - self.bounds[0]) / (self.bounds[1] - self.bounds[0])
 
-    def _moments(self, Xs, full=False):
+    def _moments(self, Xs, full=False, clip=True):
         if not self.fitted:
             raise RuntimeError("model not fitted")
         self.linv_built = True
@@ -123,7 +123,10 @@ class FakeHandle(object):
         on, ym, ys = self.out
         if on:
             mu, var = mu * ys + ym, var * ys ** 2
-        return mu, np.clip(var, O.EPS, np.inf)
+        return mu, (np.clip(var, O.EPS, np.inf) if clip else var)
+
+    def posterior_cov(self, Xs):
+        return self._moments(Xs, full=True, clip=False)
 
     def predict(self, Xs):
         return self._moments(Xs)
@@ -189,6 +192,9 @@ class FakeHandle(object):
         r = self.acq(C, kind, eta, par)
         return C[r["best_idx"]], r["best_val"], first + r["best_idx"]
 
+    def comm_info(self):
+        return dict(rank=0, world=1, nccl_version=0)
+
     def timings(self):
         return dict(fit_ms=0.0, score_ms=0.0, launches_total=0)
 
@@ -200,6 +206,17 @@ def install(monkeypatch):
 
     def moments_handle(device=0):
         return pool.setdefault(device, FakeHandle(device))
+    def acq_multi(handles, Xs, mode, kind=0, eta=None, par=0.0, want_argmax=False):
+        if mode == 1:
+            mom = [h.predict(Xs) for h in handles]
+            m, v = O.mcmc_mixture_moments(np.array([a for a, _ in mom]), np.array([b for _, b in mom]))
+            return dict(mean=m, var=v)
+        etas = np.broadcast_to(np.zeros(1) if eta is None else np.asarray(eta, float), (len(handles),))
+        rs = [h.acq(Xs, kind, float(e), par) for h, e in zip(handles, etas)]
+        vals = np.mean([r["values"] for r in rs], axis=0)
+        return dict(values=vals, n_negative=sum(r["n_negative"] for r in rs), best_val=float(vals.max()),
+                    best_idx=int(np.argmax(vals)))
+    monkeypatch.setattr(_lib, "acq_multi", acq_multi)
     monkeypatch.setattr(_lib, "Handle", FakeHandle)
     monkeypatch.setattr(_lib, "moments_handle", moments_handle)
     return FakeHandle
