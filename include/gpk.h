@@ -223,6 +223,9 @@ int gpk_comm_init(gpk_handle* h, int rank, int world, const void* id128);    /* 
 int gpk_comm_destroy(gpk_handle* h);
 int gpk_comm_info(gpk_handle* h, int* rank, int* world, int* nccl_version);
 int gpk_shard_bounds(long m, int rank, int world, long* lo, long* hi);       /* sizes differ by at most one */
+/* The exchange alone: this rank's best {value, GLOBAL index} (index < 0: nothing to offer) in, the merged winner out on
+ * every rank.  For callers that scored their shard themselves (e.g. EI.compute on a slice, values wanted on the host). */
+int gpk_comm_argmax_pair(gpk_handle* h, double val, long idx, double* best_val, long* best_idx);
 /* Xs: the FULL candidate batch (m_total, d), identical host array on every rank; each rank copies and scores only its
  * slice.  Returns the global arg-max on every rank. */
 int gpk_acq_argmax_sharded(gpk_handle* h, const double* Xs, long m_total, int acq_kind, double eta, double par,

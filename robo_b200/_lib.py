@@ -56,6 +56,7 @@ _SIGNATURES = {
     "gpk_comm_destroy": [_vp],
     "gpk_comm_info": [_vp, _ip, _ip, _ip],
     "gpk_shard_bounds": [C.c_long, C.c_int, C.c_int, _lp, _lp],
+    "gpk_comm_argmax_pair": [_vp, C.c_double, C.c_long, _dp, _lp],
     "gpk_acq_argmax_sharded": [_vp, _dp, C.c_long, C.c_int, C.c_double, C.c_double, _dp, _lp],
     "gpk_acq_argmax_sharded_dev": [_vp, _vp, C.c_long, C.c_long, C.c_int, C.c_double, C.c_double, _vp],
     "gpk_maximize_random_sharded": [_vp, C.c_ulonglong, C.c_long, C.c_long, _dp, _dp, _dp, C.c_double, C.c_int,
@@ -311,6 +312,12 @@ class Handle(object):
         r, w, v = C.c_int(), C.c_int(), C.c_int()
         self._check(self.lib.gpk_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
         return dict(rank=r.value, world=w.value, nccl_version=v.value)
+
+    def comm_argmax_pair(self, val, idx):
+        """Exchange only: this rank's (value, global index) -> the merged winner on every rank."""
+        bv, bi = C.c_double(), C.c_long(-1)
+        self._check(self.lib.gpk_comm_argmax_pair(self._h, float(val), int(idx), C.byref(bv), C.byref(bi)))
+        return bv.value, bi.value
 
     def acq_argmax_sharded(self, Xs_all, kind, eta=0.0, par=0.0):
         """Xs_all: the full batch, identical on every rank -> (best value, best GLOBAL index) on every rank."""

@@ -50,6 +50,7 @@ struct gpk_handle {
     char err[1024] = {0};
     int loader = LOADER_TMA_WS;
     long chunk = 16384;
+    bool chunk_user = false;        // false: candidates per scoring pass chosen from N (chunk_rows)
     int diag_kernel = 4;          // 4 = blocked 16-column panels, DMMA updates (default); 3 = same with DFMA register tiles, 2 = column-by-column register-tiled, 0 = simple shared-memory version
     int diag_prof = 0;            // 1: the blocked diagonal kernel records clock64() stamps per phase (diagnostics)
     DevBuf dprof;
@@ -552,17 +553,33 @@ int build_linv(gpk_handle* h) {
     return GPK_OK;
 }
 
+// Candidates per scoring pass.  Unless the caller fixed it ("chunk" option) the K* buffer is kept at about 512 MB:
+// 16384 candidates at N = 4096, 65536 at N <= 1024 (fewer, longer launches where a candidate costs only N^2 = 1 MFLOP).
+long chunk_rows(const gpk_handle* h) {
+    if (h->chunk_user) return h->chunk;
+    long c = ((1L << 26) / std::max(h->NP, 128)) / BM * BM;
+    return std::min<long>(65536, std::max<long>(4096, c));
+}
+
+// Host batches are fed to score_dev chunk by chunk: ready(lo, hi, st) makes sure the candidate rows [lo, hi) are on
+// their way to the device buffer and lets stream `st` wait for them (gpk_acq: H2D of chunk i+1, and for pageable memory
+// the host staging copy, overlap the scoring of chunk i inside ONE scoring pass with full K* look-ahead).
+struct Feeder {
+    virtual int ready(long lo, long hi, cudaStream_t st) = 0;
+    virtual ~Feeder() {}
+};
+
 // Score m candidates resident on the device.  All output pointers are device pointers or NULL.
 // index_offset: position of dX[0] in the caller's batch (offset into the output arrays and into the arg-max index);
 // global_base: added to the arg-max index only (first index of this rank's shard in a sharded batch); reset: start a
 // new running arg-max / negative-EI count (false when a host batch is fed in several pieces)
 int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, double par, double* d_out,
               double* d_mu, double* d_var, BestPair* d_best, unsigned long long* d_nneg,
-              long index_offset = 0, bool reset = true, long global_base = 0) {
+              long index_offset = 0, bool reset = true, long global_base = 0, Feeder* feeder = nullptr) {
     int rc = build_linv(h);
     if (rc) return rc;
     const long NP = h->NP;
-    const long cap = std::min<long>(h->chunk, round_up(std::max<long>(m, 1), BM));
+    const long cap = std::min<long>(chunk_rows(h), round_up(std::max<long>(m, 1), BM));
     if ((rc = ensure_score_scratch(h, cap))) return rc;
     if (d_best == nullptr) d_best = ptr<BestPair>(h->best);
     if (d_nneg == nullptr) d_nneg = ptr<unsigned long long>(h->nneg);
@@ -598,6 +615,10 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         const long mc = std::min(cap, m - base);
         const long mcp = round_up(mc, BM);
         double* dst = (pipelined && (ci & 1)) ? ptr<double>(h->Kstar2) : ptr<double>(h->Kstar);
+        if (feeder) {
+            int frc = feeder->ready(base, base + mc, st);
+            if (frc) return frc;
+        }
         const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
         const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
         if (small) {
@@ -816,8 +837,10 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         return GPK_OK;
     }
     if (!strcmp(key, "chunk")) {
-        if (value < BM || value % BM) BAD("chunk must be a positive multiple of 128");
+        if (value == 0) { h->chunk_user = false; return GPK_OK; }          // back to the automatic choice
+        if (value < BM || value % BM) BAD("chunk must be a positive multiple of 128 (0 = automatic)");
         h->chunk = value;
+        h->chunk_user = true;
         return GPK_OK;
     }
     BAD("unknown option '%s'", key);
@@ -1310,6 +1333,44 @@ static int ensure_stage(gpk_handle* h, size_t bytes) {
     return GPK_OK;
 }
 
+namespace {
+// rows of a host batch -> h->cand, piece by piece on the copy stream; pageable memory goes through two pinned staging
+// buffers filled by the host while the previous piece is in flight
+struct HostFeeder : Feeder {
+    gpk_handle* h;
+    const double* Xs;          // first row of the (super-)batch being scored
+    long rows, piece;
+    bool staged;
+    long next = 0;             // rows already enqueued
+    int npieces = 0;
+    int ready(long lo, long hi, cudaStream_t st) override {
+        (void)lo;
+        const long d = h->d;
+        while (next < hi && next < rows) {
+            const int i = npieces;
+            const long mc = std::min(piece, rows - next);
+            while ((int)h->ev_copied.size() <= i) {
+                cudaEvent_t e1;
+                CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+                h->ev_copied.push_back(e1);
+            }
+            const double* src = Xs + next * d;
+            if (staged) {
+                if (i >= 2) CK(cudaEventSynchronize(h->ev_copied[i - 2]));   // the DMA out of this staging buffer is done
+                memcpy(h->stage[i & 1], src, (size_t)mc * d * 8);
+                src = h->stage[i & 1];
+            }
+            CK(cudaMemcpyAsync(ptr<double>(h->cand) + next * d, src, (size_t)mc * d * 8, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaEventRecord(h->ev_copied[i], h->copy_stream));
+            next += mc;
+            ++npieces;
+        }
+        if (npieces > 0) CK(cudaStreamWaitEvent(st, h->ev_copied[npieces - 1], 0));
+        return GPK_OK;
+    }
+};
+}  // namespace
+
 int gpk_acq(gpk_handle* h, const double* Xs, long m, int kind, double eta, double par, double* out, double* mu,
             double* var, double* best_val, long* best_idx, long* n_negative) {
     int rc = require(h, true, true, true);
@@ -1317,55 +1378,36 @@ int gpk_acq(gpk_handle* h, const double* Xs, long m, int kind, double eta, doubl
     if (!Xs || m <= 0) BAD("gpk_acq: need candidates");
     if (kind < GPK_ACQ_NONE || kind > GPK_ACQ_LCB) BAD("gpk_acq: unknown acquisition %d", kind);
     CK(cudaSetDevice(h->device));
-    if ((rc = ensure(h, h->cand, (size_t)std::min<long>(m, 4 * h->chunk) * h->d * 8))) return rc;
+    const long d = h->d;
+    // the device copy of the batch: whole batches up to 1 GiB, larger ones in super-batches of that size
+    const long super = std::max<long>(BM, (((long)1 << 30) / (d * 8)) / BM * BM);
+    if ((rc = ensure(h, h->cand, (size_t)std::min<long>(m, super) * d * 8))) return rc;
     if (out && (rc = ensure(h, h->out_acq, (size_t)m * 8))) return rc;
     if (mu && (rc = ensure(h, h->out_mu, (size_t)m * 8))) return rc;
     if (var && (rc = ensure(h, h->out_var, (size_t)m * 8))) return rc;
     CK(cudaEventRecord(h->ev[14], h->stream));
-    const long piece = 4 * h->chunk;                  // host batch fed in pieces of 4 chunks
-    const bool staged = (size_t)m * h->d * 8 > ((size_t)1 << 20) && !host_is_pinned(Xs);
-    if (staged && (rc = ensure_stage(h, (size_t)std::min<long>(m, piece) * h->d * 8))) return rc;
-    if (m <= piece) {
-        const double* src = Xs;
-        if (staged) {
-            memcpy(h->stage[0], Xs, (size_t)m * h->d * 8);
-            src = h->stage[0];
-        }
-        CK(cudaMemcpyAsync(h->cand.p, src, (size_t)m * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    const long piece = std::min<long>(chunk_rows(h), round_up(m, BM));       // one H2D piece per scoring chunk
+    const bool small = (size_t)m * d * 8 <= ((size_t)1 << 20);
+    const bool staged = !small && !host_is_pinned(Xs);
+    if (staged && (rc = ensure_stage(h, (size_t)piece * d * 8))) return rc;
+    if (small) {
+        CK(cudaMemcpyAsync(h->cand.p, Xs, (size_t)m * d * 8, cudaMemcpyHostToDevice, h->stream));
         rc = score_dev(h, ptr<double>(h->cand), m, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,
                        mu ? ptr<double>(h->out_mu) : nullptr, var ? ptr<double>(h->out_var) : nullptr, nullptr, nullptr);
         if (rc) return rc;
     } else {
-        // H2D of piece i+1 (copy stream) overlaps the scoring of piece i; two device staging buffers.
-        const int np = (int)((m + piece - 1) / piece);
-        if ((rc = ensure(h, h->cand2, (size_t)piece * h->d * 8))) return rc;
-        while ((int)h->ev_copied.size() < np) {
-            cudaEvent_t e1, e2;
-            CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-            h->ev_copied.push_back(e1);
-            h->ev_scored.push_back(e2);
-        }
-        CK(cudaEventRecord(h->ev_order, h->stream));
-        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_order, 0));
-        for (int i = 0; i < np; ++i) {
-            const long base = (long)i * piece, mc = std::min(piece, m - base);
-            double* buf = (i & 1) ? ptr<double>(h->cand2) : ptr<double>(h->cand);
-            if (i >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_scored[i - 2], 0));
-            const double* src = Xs + base * h->d;
-            if (staged) {
-                if (i >= 2) CK(cudaEventSynchronize(h->ev_copied[i - 2]));      // the DMA out of this staging buffer is done
-                memcpy(h->stage[i & 1], src, (size_t)mc * h->d * 8);
-                src = h->stage[i & 1];
-            }
-            CK(cudaMemcpyAsync(buf, src, (size_t)mc * h->d * 8, cudaMemcpyHostToDevice, h->copy_stream));
-            CK(cudaEventRecord(h->ev_copied[i], h->copy_stream));
-            CK(cudaStreamWaitEvent(h->stream, h->ev_copied[i], 0));
-            rc = score_dev(h, buf, mc, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,
+        for (long base = 0; base < m; base += super) {
+            const long rows = std::min(super, m - base);
+            // the copy stream starts after everything already queued on the scoring stream (earlier users of h->cand)
+            CK(cudaEventRecord(h->ev_order, h->stream));
+            CK(cudaStreamWaitEvent(h->copy_stream, h->ev_order, 0));
+            if (base > 0) CK(cudaStreamSynchronize(h->copy_stream));     // staging buffers and h->cand are reused
+            HostFeeder feeder;
+            feeder.h = h; feeder.Xs = Xs + base * d; feeder.rows = rows; feeder.piece = piece; feeder.staged = staged;
+            rc = score_dev(h, ptr<double>(h->cand), rows, kind, eta, par, out ? ptr<double>(h->out_acq) : nullptr,
                            mu ? ptr<double>(h->out_mu) : nullptr, var ? ptr<double>(h->out_var) : nullptr, nullptr, nullptr,
-                           base, i == 0);
+                           base, base == 0, 0, &feeder);
             if (rc) return rc;
-            CK(cudaEventRecord(h->ev_scored[i], h->stream));
         }
     }
     if (out) CK(cudaMemcpyAsync(out, h->out_acq.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));

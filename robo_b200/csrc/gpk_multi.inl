@@ -291,6 +291,24 @@ extern "C" int gpk_shard_bounds(long m, int rank, int world, long* lo, long* hi)
     return GPK_OK;
 }
 
+extern "C" int gpk_comm_argmax_pair(gpk_handle* h, double val, long idx, double* best_val, long* best_idx) {
+    if (!h) return GPK_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure(h, h->best, sizeof(BestPair)))) return rc;
+    if ((rc = ensure(h, h->best_global, sizeof(BestPair)))) return rc;
+    BestPair in;
+    in.val = val; in.idx = idx;
+    CK(cudaMemcpyAsync(h->best.p, &in, sizeof(in), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = exchange_best(h, ptr<BestPair>(h->best), ptr<BestPair>(h->best_global)))) return rc;
+    BestPair bp;
+    CK(cudaMemcpyAsync(&bp, h->best_global.p, sizeof(bp), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (best_val) *best_val = bp.val;
+    if (best_idx) *best_idx = (long)bp.idx;
+    return GPK_OK;
+}
+
 extern "C" int gpk_acq_argmax_sharded_dev(gpk_handle* h, const void* d_Xs_shard, long m_shard, long first_global, int kind,
                                double eta, double par, void* d_best) {
     int rc = require(h, true, true, true);

@@ -68,9 +68,17 @@ def test_gp_mcmc_model_and_marginalisation(fake):
     for cls in (EI, LogEI, PI, LCB):
         acq = MarginalizationGPMCMC(cls(model))
         acq.update(model)
+        assert acq._fused_spec() is not None          # device sub-models: ONE multi-model call (gpk_acq_multi)
         a = acq.compute(Xt)
         assert a.shape == (7,)
         np.testing.assert_allclose(a, np.mean([cls(s).compute(Xt) for s in model.models], axis=0))
+        assert acq.argmax(Xt) == int(np.argmax(a))
+        # a cost model, or estimators with different parameters, fall back to the reference's loop over estimators
+        acq.estimators[0].par = 0.25
+        assert acq._fused_spec() is None
+        b = acq.compute(Xt)
+        assert b.shape == (7,)
+        acq.estimators[0].par = acq.estimators[1].par
     clone = copy.deepcopy(model)
     np.testing.assert_allclose(clone.predict(Xt)[0], m)
     model.train(X, y, do_optimize=False)
@@ -146,6 +154,11 @@ def test_device_random_sampling_host_logic(fake):
     assert np.array_equal(x, cand[int(np.argmax(acq.compute(cand)))])
     x2 = mx.maximize()
     assert mx.calls == 2 and not np.array_equal(x, x2)
+    # candidate count of the reference: int(0.7 n) + int(0.3 n)  (n = 5 -> 3 + 1), random_sampling.py:38-47
+    mx5 = DeviceRandomSampling(acq, lower, upper, n_samples=5, rng=np.random.RandomState(2))
+    x5 = mx5.maximize()
+    cand5 = O.generate_candidates(mx5.last["seed"], 0, 4, 3, lower, upper, model.get_incumbent()[0], 0.1)
+    assert np.array_equal(x5, cand5[int(np.argmax(acq.compute(cand5)))])
     rs = RandomSampling(acq, lower, upper, n_samples=100, rng=np.random.RandomState(0))
     xr = rs.maximize()
     assert xr.shape == (2,) and np.all(xr >= lower) and np.all(xr <= upper)

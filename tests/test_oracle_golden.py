@@ -81,3 +81,60 @@ def test_philox_known_answer_vectors():
     c = O.generate_candidates(5, 0, 1000, 700, np.array([-5.0, 0, 1]), np.array([10.0, 15, 2]), np.array([0.0, 1, 1.5]), 0.1)
     assert c.shape == (1000, 3) and np.all(c >= [-5, 0, 1]) and np.all(c <= [10, 15, 2])
     assert abs(c[700:, 0].std() - 0.1) < 0.02
+
+
+# ----------------------------------------------------------------------------------------------
+# threaded C restatement (oracle/kmat.c) used for the BASELINE-size checks: pinned to the numpy oracle
+# ----------------------------------------------------------------------------------------------
+def _prod1d(theta, D, cls):
+    k = G.ConstantKernel(theta[0], ndim=D)
+    for d in range(D):
+        k = G.Product(k, cls(np.exp(theta[1 + d:2 + d]), ndim=D, axes=d))
+    return k
+
+
+@pytest.mark.parametrize("case", ["ard_matern52", "ard_rbf", "ard_matern32", "prod1d_matern52", "iso_matern52"])
+def test_c_kernel_matrix_matches_numpy_oracle(case):
+    rng = np.random.RandomState(7)
+    D = 5
+    X1, X2 = rng.rand(37, D) * 3 - 1, rng.rand(53, D) * 3 - 1
+    theta = np.concatenate(([0.3], rng.uniform(-2, 1, D)))
+    if case == "ard_matern52":
+        k = O.make_kernel("matern52", D, theta)
+    elif case == "ard_rbf":
+        k = O.make_kernel("rbf", D, theta)
+    elif case == "ard_matern32":
+        k = G.Product(G.ConstantKernel(theta[0], ndim=D), G.Matern32Kernel(np.exp(theta[1:]), ndim=D))
+    elif case == "prod1d_matern52":
+        k = _prod1d(theta, D, G.Matern52Kernel)
+    else:
+        k = 2.0 * G.Matern52Kernel(0.7, ndim=D)
+    ref = k.get_value(X1, X2)
+    got = O.kmat_fast(k, X1, X2)
+    assert np.max(np.abs(got - ref) / ref) <= 8 * np.finfo(float).eps      # libm exp vs numpy exp, a few ulp
+    f = O.flatten_kernel(k)
+    assert len(f["axis"]) == D and f["last"][-1] == 1
+
+
+def test_fast_oracle_paths_match_reference_faithful_oracle():
+    """gp_predict_var_only_fast (BASELINE-size candidate batches) and gp_grad_nll_terms_fast (config 5) against the
+    reference-faithful restatements they accelerate."""
+    X, y, Xs, theta, noise = O.synthetic_problem(200, 4, 700)
+    st = O.gp_fit(O.make_kernel("matern52", 4, theta), X, y, noise=noise, normalize_input=True, normalize_output=True,
+                  lower=np.zeros(4) - 0.1, upper=np.ones(4) + 0.2)
+    mu, var = O.gp_predict(st, Xs)
+    mu2, var2 = O.gp_predict_var_only_fast(st, Xs, chunk=256)
+    np.testing.assert_allclose(mu2, mu, rtol=0, atol=1e-11 * np.abs(mu).max())
+    np.testing.assert_allclose(var2, var, rtol=1e-9, atol=1e-13)
+    th = np.append(theta, np.log(noise)) + 0.05
+    g = O.gp_grad_nll_correct(st, th)
+    g2 = O.gp_grad_nll_terms_fast(st, th)
+    np.testing.assert_allclose(g2, g, rtol=1e-10, atol=1e-10)
+    # product of 1-D kernels: one entry per term, george parameter order
+    t3 = np.array([0.2, -0.5, 0.1, -1.0])
+    k = _prod1d(t3, 3, G.Matern52Kernel)
+    X3 = np.random.RandomState(1).rand(150, 3)
+    y3 = np.sin(X3.sum(axis=1))
+    st3 = O.gp_fit(k, X3, y3, noise=1e-3, normalize_input=False)
+    th3 = np.append(t3, np.log(1e-3))
+    np.testing.assert_allclose(O.gp_grad_nll_terms_fast(st3, th3), O.gp_grad_nll_correct(st3, th3), rtol=1e-10, atol=1e-10)
