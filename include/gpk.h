@@ -62,7 +62,12 @@ const char* gpk_version(void);
 /* key in
  *   "loader"    operand staging of the GEMM tile engine: 2 = TMA with a dedicated producer warp and
  *               full/empty mbarriers [default], 1 = TMA issued by a consumer thread, 0 = cp.async (cross-check)
- *   "chunk"     candidates per scoring pass (multiple of 128, default 16384)
+ *   "chunk"     candidates per scoring pass (multiple of 128); 0 = automatic [default]: the K* buffer is kept near
+ *               512 MB (16384 candidates at N = 4096, 65536 at N <= 1024)
+ *   "cov"       covariance builder: 2 = TMA-staged, pre-scaled term-major operands [default], 1 = round-1 kernel
+ *   "chainsplit" 1 = split Cholesky chain [default]: diag(k+1) waits only for block row k+1 of step k (one launch on
+ *               four 32-row tiles), the rows below run on a second high-priority stream, trailing update with
+ *               look-ahead 2; 0 = plain look-ahead schedule (bit-identical factor)
  *   "diag"      diagonal-block Cholesky + inverse kernel: 4 = 16-column panels, square-root-free pivot chain in one warp,
  *               substitutions in four, rank-16 updates on the fp64 tensor pipe [default]; 3 = the same with DFMA register
  *               tiles; 2 = column-by-column register-tiled kernel; 0 = simple shared-memory version (cross-checks)

@@ -42,6 +42,9 @@ struct gpk_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t side_stream = nullptr;     // trailing updates of the look-ahead Cholesky
     std::vector<cudaEvent_t> ev_panel, ev_rest;
+    cudaStream_t panel_stream = nullptr;    // split chain: panel solve / next-panel update of the rows below block row k+1
+    std::vector<cudaEvent_t> ev_cs;         // split chain: 5 events per step (diag, X, trsm', pu', rest_a)
+    int chainsplit = 1;             // 1: diag(k+1) waits only for block row k+1 of step k (gpk_chain_step_kernel on 4 CTAs)
     int lookahead = 1;
     int smalltile = 1;              // 32-row tiles for the panel solve / next-panel update
     int pdl = 1;                    // programmatic dependent launch on the Cholesky chain
@@ -68,6 +71,8 @@ struct gpk_handle {
     // device buffers
     DevBuf Xrow, Xt, y, Kbuf, P, Q, W, lower, upper, logdet_part, scal, status, jobs;
     DevBuf Kstar2, cand2;
+    DevBuf Xts;                     // training inputs, term-major and pre-scaled (operand of gpk_cov_tma_kernel)
+    int cov_kernel = 2;             // 2 = TMA-staged, pre-scaled operands [default]; 1 = the round-1 kernel (cross-check)
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> ev_copied, ev_scored;
     std::vector<cudaEvent_t> ev_g0, ev_g1;    // timed pairs around every variance-GEMM launch of the last scoring call
@@ -204,6 +209,71 @@ int make_map(gpk_handle* h, CUtensorMap* map, void* base, long rows, long cols, 
     return GPK_OK;
 }
 
+// term-major operand [n_terms][ld] of the covariance builder: box = n_terms rows x 128 columns, no swizzle
+int make_cov_map(gpk_handle* h, CUtensorMap* map, void* base, int n_terms, long ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_err(h, "cuTensorMapEncodeTiled entry point not available");
+        return GPK_CUDA_ERROR;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)n_terms};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {128u, (cuuint32_t)n_terms};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_err(h, "cuTensorMapEncodeTiled (covariance operand) failed with CUresult %d (terms=%d ld=%ld)", (int)r, n_terms, ld);
+        return GPK_CUDA_ERROR;
+    }
+    return GPK_OK;
+}
+
+inline bool cov_tma(const gpk_handle* h) { return h->cov_kernel == 2 && h->loader != LOADER_CPASYNC; }
+
+// "Transposed" operand of the covariance builder for n points X (row-major, n x d) into dst with ld columns:
+// term-major + pre-scaled for the TMA kernel (dst needs n_terms x ld doubles), axis-major for the round-1 kernel
+// (d x ld doubles).  lo / up: input bounds to apply first (NULL: none).
+int build_cov_operand(gpk_handle* h, cudaStream_t st, const double* X, long n, int d, const double* lo, const double* up,
+                      double* dst, long ld) {
+    if (cov_tma(h)) {
+        const long total = (long)h->spec.n_terms * ld;
+        gpk_termmajor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->spec, X, n, d, lo, up, dst, ld);
+    } else {
+        const long total = (long)d * ld;
+        gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, n, d, lo, up, dst, ld);
+    }
+    CKL();
+    return GPK_OK;
+}
+inline size_t cov_operand_rows(const gpk_handle* h, int d) { return (size_t)std::max(d, h->spec.n_terms); }
+
+// out[c][j] = k(cand_c, point_j) for m candidates (row-major raw inputs, bounds lo / up applied on the fly) against
+// the n points of `operand` (built by build_cov_operand, ld = ldx columns); out has ldo columns and at least
+// round_up(m, tile) rows.  small: the 128 x 16 tile variant that fits next to a resident variance-GEMM CTA.
+int launch_cov_tiles(gpk_handle* h, cudaStream_t st, const double* operand, long ldx, int n, const double* cand, int dc,
+                     long m, long m_padded, const double* lo, const double* up, double* out, long ldo, int tri, bool small) {
+    const unsigned gx = (unsigned)(ldx / 128);
+    if (cov_tma(h)) {
+        CUtensorMap map;
+        int rc = make_cov_map(h, &map, (void*)operand, h->spec.n_terms, ldx);
+        if (rc) return rc;
+        if (small)
+            gpk_cov_tma_kernel<4><<<dim3(gx, (unsigned)(m_padded / 16)), 256, cov_tma_smem_bytes(h->spec.n_terms, 4), st>>>(
+                map, h->spec, n, cand, dc, m, lo, up, out, ldo, tri);
+        else
+            gpk_cov_tma_kernel<8><<<dim3(gx, (unsigned)(m_padded / 32)), 256, cov_tma_smem_bytes(h->spec.n_terms, 8), st>>>(
+                map, h->spec, n, cand, dc, m, lo, up, out, ldo, tri);
+    } else if (small) {
+        gpk_cov_kernel<8><<<dim3(gx, (unsigned)(m_padded / 16)), 256, 0, st>>>(h->spec, operand, ldx, n, cand, dc, m, lo, up, out, ldo, tri);
+    } else {
+        gpk_cov_kernel<16><<<dim3(gx, (unsigned)(m_padded / 32)), 256, 0, st>>>(h->spec, operand, ldx, n, cand, dc, m, lo, up, out, ldo, tri);
+    }
+    CKL();
+    return GPK_OK;
+}
+inline const double* train_operand(const gpk_handle* h) { return cov_tma(h) ? ptr<double>(h->Xts) : ptr<double>(h->Xt); }
+
 // ---- GEMM launch ---------------------------------------------------------------------------
 // Launch with the programmatic-stream-serialization attribute (PDL): the kernel's launch latency and prologue
 // overlap the tail of the previous kernel on the stream; the kernels call cudaGridDependencySynchronize().
@@ -255,6 +325,8 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 1)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 1)));
+    CK(cudaFuncSetAttribute(gpk_cov_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_tma_smem_bytes(GPK_MAX_TERMS, 8)));
+    CK(cudaFuncSetAttribute(gpk_cov_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_tma_smem_bytes(GPK_MAX_TERMS, 4)));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
     CK(cudaFuncSetAttribute(gpk_chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
@@ -621,17 +693,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         }
         const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
         const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
-        if (small) {
-            dim3 cg((unsigned)(NP / 128), (unsigned)(mcp / 16));
-            gpk_cov_kernel<8><<<cg, 256, 0, st>>>(h->spec, ptr<double>(h->Xt), NP, h->n, dX + base * h->d, h->d, mc, lo, up,
-                                                  dst, NP, 0);
-        } else {
-            dim3 cg((unsigned)(NP / 128), (unsigned)(mcp / 32));
-            gpk_cov_kernel<16><<<cg, 256, 0, st>>>(h->spec, ptr<double>(h->Xt), NP, h->n, dX + base * h->d, h->d, mc, lo, up,
-                                                   dst, NP, 0);
-        }
-        CKL();
-        return GPK_OK;
+        return launch_cov_tiles(h, st, train_operand(h), NP, h->n, dX + base * h->d, h->d, mc, mcp, lo, up, dst, NP, 0, small);
     };
     if (pipelined) {
         CK(cudaEventRecord(h->ev_order, h->stream));          // side stream starts after all prior work
@@ -729,6 +791,7 @@ int gpk_create(gpk_handle** out, int device) {
         if (cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
         if (cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
         if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
+        if (cudaStreamCreateWithPriority(&h->panel_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return GPK_CUDA_ERROR; }
     }
     h->stream = h->own_stream;
     for (int i = 0; i < 16; ++i)
@@ -755,7 +818,7 @@ int gpk_destroy(gpk_handle* h) {
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
                       &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
-                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof,
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts,
                       &h->multi_cand, &h->multi_A, &h->multi_B, &h->multi_out, &h->multi_bb, &h->gather, &h->best_global};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -764,6 +827,8 @@ int gpk_destroy(gpk_handle* h) {
     if (h->ev_order) cudaEventDestroy(h->ev_order);
     for (int i = 0; i < 2; ++i)
         if (h->stage[i]) cudaFreeHost(h->stage[i]);
+    for (cudaEvent_t e : h->ev_cs) cudaEventDestroy(e);
+    if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
     for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_rest) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_cov) cudaEventDestroy(e);
@@ -789,6 +854,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->maps_ok = false;
         h->mapKs_rows = 0;
         h->mapVt_rows = 0;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "chainsplit")) {
+        if (value != 0 && value != 1) BAD("chainsplit must be 0 or 1");
+        h->chainsplit = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "fusechain")) {
@@ -834,6 +904,13 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
             BAD("diag must be 4 (blocked panels, DMMA updates), 3 (blocked panels, DFMA register tiles), 2 (column-by-column "
                 "register-tiled kernel) or 0 (simple shared-memory kernel)");
         h->diag_kernel = (int)value;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "cov")) {
+        if (value != 1 && value != 2) BAD("cov must be 2 (TMA-staged covariance builder, pre-scaled operands) or 1 (round-1 kernel)");
+        h->cov_kernel = (int)value;
+        h->fitted = false;
+        h->linv_ready = false;
         return GPK_OK;
     }
     if (!strcmp(key, "chunk")) {
@@ -944,6 +1021,7 @@ int gpk_set_kernel(gpk_handle* h, int family, double log_amp, int n_terms, const
         if (t > 0 && (group[t] < group[t - 1] || group[t] > group[t - 1] + 1)) BAD("gpk_set_kernel: groups must be contiguous");
         s.axis[t] = axis[t];
         s.inv_metric[t] = 1.0 / exp(log_metric[t]);
+        s.scale[t] = sqrt((family == GPK_MATERN52 ? 5.0 : family == GPK_MATERN32 ? 3.0 : 0.5) * s.inv_metric[t]);
         s.last[t] = (t == n_terms - 1) || (group[t + 1] != group[t]);
     }
     if (group[0] != 0) BAD("gpk_set_kernel: groups must start at 0");
@@ -975,10 +1053,14 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
 
     CK(cudaEventRecord(h->ev[0], h->stream));
     {
-        dim3 cg((unsigned)(NP / 128), (unsigned)(NP / 32));
-        gpk_cov_kernel<16><<<cg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->Xrow), h->d,
-                                                  (long)h->n, nullptr, nullptr, K, NP, 1);
-        CKL();
+        if (cov_tma(h)) {               // the pre-scaled operand depends on the hyper-parameters: rebuilt per fit (n_terms x NP)
+            if ((rc = ensure(h, h->Xts, (size_t)GPK_MAX_TERMS * NP * 8))) return rc;
+            if ((rc = build_cov_operand(h, h->stream, ptr<double>(h->Xrow), h->n, h->d, nullptr, nullptr, ptr<double>(h->Xts), NP)))
+                return rc;
+        }
+        if ((rc = launch_cov_tiles(h, h->stream, train_operand(h), NP, h->n, ptr<double>(h->Xrow), h->d, (long)h->n, NP,
+                                   nullptr, nullptr, K, NP, 1, false)))
+            return rc;
         gpk_kfix_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, h->stream>>>(K, NP, h->n, (int)NP, diag_add,
                                                                             ptr<double>(h->y), mean);
         CKL();
@@ -998,11 +1080,123 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         if ((rc = ensure(h, h->chain_cnt, (size_t)nb * 4))) return rc;
         CK(cudaMemsetAsync(h->chain_cnt.p, 0, (size_t)nb * 4, h->stream));
     }
-    if (h->diag_kernel >= 3) {
+    // ---- split chain (default): only block row k+1 of step k stays between diag(k) and diag(k+1) ----------------
+    // Step k of the right-looking factorisation used to put diag(k) -> panel solve (all rows) -> update of block column
+    // k+1 (all rows) on the critical chain.  diag(k+1) only needs A[k+1,k+1] -= L[k+1,k] L[k+1,k]^T with
+    // L[k+1,k] = A[k+1,k] inv(L_kk)^T: one launch of gpk_chain_step_kernel on the four 32-row tiles of block row k+1
+    // ("X(k)").  The rows below go to a second high-priority stream and overlap diag(k+1); the trailing update is cut
+    // in two (block column k+2 first) so that the chain waits for one column, not for the whole update (look-ahead 2).
+    // Every tile still receives its panels in increasing order: the factor is bit-identical to the other schedules.
+    //   C (h->stream)     diag(k) . X(k) . diag(k+1) ...
+    //   P (panel_stream)  solve'(k) [rows > k+1] . update'(k) [block column k+1, rows > k+1]
+    //   R (side_stream)   rest_a(k) [block column k+2] . rest_b(k) [block columns >= k+3]
+    const bool split = h->chainsplit && h->smalltile == 1 && h->lookahead && !fuse && h->diag_kernel >= 3 &&
+                       h->loader != LOADER_CPASYNC && nb >= 3;
+    if (split) {
+        if ((rc = ensure(h, h->chain_cnt, (size_t)nb * 4))) return rc;
+        CK(cudaMemsetAsync(h->chain_cnt.p, 0, (size_t)nb * 4, h->stream));
+        while ((int)h->ev_cs.size() < 5 * nb) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->ev_cs.push_back(e);
+        }
+        auto evD = [&](int k) { return h->ev_cs[5 * k]; };
+        auto evX = [&](int k) { return h->ev_cs[5 * k + 1]; };
+        auto evT = [&](int k) { return h->ev_cs[5 * k + 2]; };
+        auto evPU = [&](int k) { return h->ev_cs[5 * k + 3]; };
+        auto evRA = [&](int k) { return h->ev_cs[5 * k + 4]; };
+        std::vector<char> haveX(nb, 0), havePU(nb, 0), haveRA(nb, 0);
+        cudaStream_t C = h->stream, Pst = h->panel_stream, R = h->side_stream;
+        CK(cudaEventRecord(h->ev_order, C));                       // K is built: the other streams may start
+        CK(cudaStreamWaitEvent(Pst, h->ev_order, 0));
+        CK(cudaStreamWaitEvent(R, h->ev_order, 0));
+        gpk_diag_prezero_kernel<<<nb, 256, 0, C>>>(K, (long)NP, ptr<double>(h->P), (long)NP);
+        CKL();
+        for (int k = 0; k < nb; ++k) {
+            long long* dprof = h->diag_prof ? ptr<long long>(h->dprof) : nullptr;
+            // ---- C: diag(k)
+            if (h->diag_kernel == 4)
+                gpk_potrf_diag_dmma_kernel<<<1, 256, DIAG4_SMEM, C>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
+                                                                     ptr<int>(h->status), ptr<double>(h->logdet_part), dprof);
+            else
+                gpk_potrf_diag_blocked_kernel<<<1, 256, DIAG3_SMEM, C>>>(K, NP, k, ptr<double>(h->P), ptr<double>(h->Q), NP,
+                                                                        ptr<int>(h->status), ptr<double>(h->logdet_part), dprof);
+            CKL();
+            CK(cudaEventRecord(evD(k), C));
+            const int nsolve = h->trsm32_r[k].cnt, nupd = h->pu32_r[k].cnt;
+            const bool hasX = (k + 1 < nb);                              // block row k+1 exists: 4 solve + 4 update tiles
+            // ---- C: X(k)
+            if (hasX) {
+                if (k >= 1 && havePU[k - 1]) CK(cudaStreamWaitEvent(C, evPU(k - 1), 0));     // A[k+1,k] carries panel k-1
+                if (k >= 1 && haveRA[k - 1]) CK(cudaStreamWaitEvent(C, evRA(k - 1), 0));     // A[k+1,k+1] carries panel k-1
+                ChainArgs c;
+                c.K = K; c.ld = NP; c.P = ptr<double>(h->P); c.ldp = NP;
+                c.solve_jobs = ptr<GemmJob>(h->jobs) + h->trsm32_r[k].off;
+                c.update_jobs = ptr<GemmJob>(h->jobs) + h->pu32_r[k].off;
+                c.counter = ptr<int>(h->chain_cnt) + k;
+                c.status = ptr<int>(h->status);
+                gpk_chain_step_kernel<<<4, GEMM_THREADS, CH_SMEM, C>>>(c);
+                CKL();
+                CK(cudaEventRecord(evX(k), C));
+                haveX[k] = 1;
+            }
+            // ---- P: the rest of the panel (rows below block row k+1, and the right-hand-side row)
+            const int skip = hasX ? 4 : 0;
+            GemmArgs a;
+            memset(&a, 0, sizeof(a));
+            a.A = K; a.lda = NP; a.B = ptr<double>(h->P); a.ldb = NP; a.C = K; a.ldc = NP;
+            a.alpha = 1.0; a.beta = 0; a.job_mode = JOBS_TABLE; a.status = ptr<int>(h->status);
+            a.jobs = ptr<GemmJob>(h->jobs) + h->trsm32_r[k].off + skip;
+            CK(cudaStreamWaitEvent(Pst, evD(k), 0));
+            if (nsolve - skip > 0) {
+                if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapP, a, nsolve - skip, Pst))) return rc;
+            }
+            CK(cudaEventRecord(evT(k), Pst));
+            if (hasX && nupd - 4 > 0) {
+                GemmArgs u;
+                memset(&u, 0, sizeof(u));
+                u.A = K; u.lda = NP; u.B = K; u.ldb = NP; u.C = K; u.ldc = NP;
+                u.alpha = -1.0; u.beta = 1; u.job_mode = JOBS_TABLE; u.status = ptr<int>(h->status);
+                u.jobs = ptr<GemmJob>(h->jobs) + h->pu32_r[k].off + 4;
+                CK(cudaStreamWaitEvent(Pst, evX(k), 0));                                       // L[k+1,k] is the B operand
+                if (k >= 1 && haveRA[k - 1]) CK(cudaStreamWaitEvent(Pst, evRA(k - 1), 0));    // column k+1 carries panel k-1
+                if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapK, u, nupd - 4, Pst))) return rc;
+                CK(cudaEventRecord(evPU(k), Pst));
+                havePU[k] = 1;
+            }
+            // ---- R: trailing update beyond block column k+1: column k+2 first (what step k+1 waits for), then the rest
+            const int off = h->syrk_r[k].off, cnt = h->syrk_r[k].cnt, npu = nb - k;       // first npu jobs: block column k+1
+            if (cnt > npu) {
+                const int na = nb - k - 1;                                                // block column k+2: rows k+2 .. nb
+                GemmArgs s2;
+                memset(&s2, 0, sizeof(s2));
+                s2.A = K; s2.lda = NP; s2.B = K; s2.ldb = NP; s2.C = K; s2.ldc = NP;
+                s2.alpha = -1.0; s2.beta = 1; s2.job_mode = JOBS_TABLE; s2.status = ptr<int>(h->status);
+                CK(cudaStreamWaitEvent(R, evT(k), 0));
+                if (hasX) CK(cudaStreamWaitEvent(R, evX(k), 0));
+                s2.jobs = ptr<GemmJob>(h->jobs) + off + npu;
+                if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s2, std::min(na, cnt - npu), R))) return rc;
+                CK(cudaEventRecord(evRA(k), R));
+                haveRA[k] = 1;
+                if (cnt - npu - na > 0) {
+                    s2.jobs = ptr<GemmJob>(h->jobs) + off + npu + na;
+                    if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s2, cnt - npu - na, R))) return rc;
+                }
+            }
+        }
+        // join: everything the factor consists of is complete once P and R have drained
+        CK(cudaEventRecord(h->ev_order, Pst));
+        CK(cudaStreamWaitEvent(C, h->ev_order, 0));
+        CK(cudaEventRecord(h->ev_panel[0], R));
+        CK(cudaStreamWaitEvent(C, h->ev_panel[0], 0));
+        gpk_diag_qfill_kernel<<<nb, 256, 0, C>>>(ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status));
+        CKL();
+    }
+    if (!split && h->diag_kernel >= 3) {
         gpk_diag_prezero_kernel<<<nb, 256, 0, h->stream>>>(K, (long)NP, ptr<double>(h->P), (long)NP);
         CKL();
     }
-    for (int k = 0; k < nb; ++k) {
+    for (int k = 0; k < nb && !split; ++k) {
         long long* dprof = h->diag_prof ? ptr<long long>(h->dprof) : nullptr;
         if (h->diag_kernel == 4 && h->pdl && k > 0)
             CK(launch_pdl(gpk_potrf_diag_dmma_kernel, dim3(1), dim3(256), (size_t)DIAG4_SMEM, h->stream, K, (long)NP, k,
@@ -1115,7 +1309,7 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
             }
         }
     }
-    if (h->diag_kernel >= 3) {
+    if (!split && h->diag_kernel >= 3) {
         gpk_diag_qfill_kernel<<<nb, 256, 0, h->stream>>>(ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status));
         CKL();
     }
@@ -1204,10 +1398,14 @@ int gpk_fit_append(gpk_handle* h, const double* X, const double* y, int n, int d
     }
     // block row b of K (all columns), diagonal term, padding rows
     {
-        dim3 cg((unsigned)(NP / 128), 4);
-        gpk_cov_kernel<16><<<cg, 256, 0, h->stream>>>(h->spec, ptr<double>(h->Xt), NP, n, ptr<double>(h->Xrow) + (long)N1 * d,
-                                                  d, (long)(n - N1), nullptr, nullptr, K + (long)N1 * NP, NP, 0);
-        CKL();
+        if (cov_tma(h)) {
+            if ((rc = ensure(h, h->Xts, (size_t)GPK_MAX_TERMS * NP * 8))) return rc;
+            if ((rc = build_cov_operand(h, h->stream, ptr<double>(h->Xrow), n, d, nullptr, nullptr, ptr<double>(h->Xts), NP)))
+                return rc;
+        }
+        if ((rc = launch_cov_tiles(h, h->stream, train_operand(h), NP, n, ptr<double>(h->Xrow) + (long)N1 * d, d,
+                                   (long)(n - N1), BM, nullptr, nullptr, K + (long)N1 * NP, NP, 0, false)))
+            return rc;
         gpk_kfix_rows_kernel<<<1, 128, 0, h->stream>>>(K, NP, n, (int)NP, diag_add, N1);
         CKL();
     }
@@ -1499,25 +1697,20 @@ static int predict_cov_impl(gpk_handle* h, const double* Xs, long m, double* mu,
         h->mapVt_rows = mp;
     }
     if ((rc = ensure(h, h->cov, (size_t)mp * mp * 8))) return rc;
-    if ((rc = ensure(h, h->XsT, (size_t)h->d * mp * 8))) return rc;
+    if ((rc = ensure(h, h->XsT, cov_operand_rows(h, h->d) * mp * 8))) return rc;
     if ((rc = ensure(h, h->out_mu, (size_t)mp * 8))) return rc;
     CK(cudaMemcpyAsync(h->cand.p, Xs, (size_t)m * h->d * 8, cudaMemcpyHostToDevice, h->stream));
     const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
     const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
     // K* (mp x NP)
-    gpk_cov_kernel<16><<<dim3((unsigned)(NP / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
-        h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->cand), h->d, m, lo, up, ptr<double>(h->Kstar), NP, 0);
-    CKL();
-    // K** (mp x mp): candidates against (scaled, transposed) candidates
-    {
-        long total = (long)h->d * mp;
-        gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->cand), m, h->d, lo,
-                                                                                    up, ptr<double>(h->XsT), mp);
-        CKL();
-        gpk_cov_kernel<16><<<dim3((unsigned)(mp / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
-            h->spec, ptr<double>(h->XsT), mp, (int)m, ptr<double>(h->cand), h->d, m, lo, up, ptr<double>(h->cov), mp, 0);
-        CKL();
-    }
+    if ((rc = launch_cov_tiles(h, h->stream, train_operand(h), NP, h->n, ptr<double>(h->cand), h->d, m, mp, lo, up,
+                               ptr<double>(h->Kstar), NP, 0, false)))
+        return rc;
+    // K** (mp x mp): candidates against the (scaled, transposed) candidates
+    if ((rc = build_cov_operand(h, h->stream, ptr<double>(h->cand), m, h->d, lo, up, ptr<double>(h->XsT), mp))) return rc;
+    if ((rc = launch_cov_tiles(h, h->stream, ptr<double>(h->XsT), mp, (int)m, ptr<double>(h->cand), h->d, m, mp, lo, up,
+                               ptr<double>(h->cov), mp, 0, false)))
+        return rc;
     // V^T = (L^-1 K*^T)^T  ->  Vt[cand][i]
     std::vector<GemmJob> jobs;
     for (int ib = nb - 1; ib >= 0; --ib)
@@ -1610,9 +1803,9 @@ int gpk_predict_grad(gpk_handle* h, const double* Xs, long m, int kind, double e
     const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
     if ((rc = ensure_score_scratch(h, mp))) return rc;       // score_dev may have sized the K* map for a smaller chunk
     // K* again into the first buffer (score_dev may have used either), then Vt = (L^-1 K*^T)^T, Wt = (L^-T V)^T
-    gpk_cov_kernel<16><<<dim3((unsigned)(NP / 128), (unsigned)(mp / 32)), 256, 0, h->stream>>>(
-        h->spec, ptr<double>(h->Xt), NP, h->n, ptr<double>(h->cand), d, m, lo, up, ptr<double>(h->Kstar), NP, 0);
-    CKL();
+    if ((rc = launch_cov_tiles(h, h->stream, train_operand(h), NP, h->n, ptr<double>(h->cand), d, m, mp, lo, up,
+                               ptr<double>(h->Kstar), NP, 0, false)))
+        return rc;
     std::vector<GemmJob> jobs;
     for (int ib = nb - 1; ib >= 0; --ib)
         for (int cb = 0; cb < mb; ++cb) jobs.push_back({ib * BM, cb * BM, 0, (ib + 1) * BM, ib * BM, cb * BM, 0, 0});
@@ -1727,18 +1920,17 @@ int gpk_kernel_matrix(gpk_handle* h, const double* X1, long n1, const double* X2
     CK(cudaSetDevice(h->device));
     const long n1p = round_up(n1, 32), n2p = round_up(n2, 128);
     if ((rc = ensure(h, h->tmp1, (size_t)n1 * d * 8))) return rc;
-    if ((rc = ensure(h, h->tmp2, (size_t)std::max<long>(n2 * d, d * n2p) * 8 * 2))) return rc;
+    const long x2off = round_up(n2 * d, 16);                 // keeps the operand 128-byte aligned (TMA source)
+    if ((rc = ensure(h, h->tmp2, (size_t)(x2off + (long)cov_operand_rows(h, d) * n2p) * 8))) return rc;
     if ((rc = ensure(h, h->tmp3, (size_t)n1p * n2p * 8))) return rc;
     double* X2row = ptr<double>(h->tmp2);
-    double* X2t = X2row + n2 * d;
+    double* X2t = X2row + x2off;
     CK(cudaMemcpyAsync(h->tmp1.p, X1, (size_t)n1 * d * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(X2row, X2, (size_t)n2 * d * 8, cudaMemcpyHostToDevice, h->stream));
-    long total = (long)d * n2p;
-    gpk_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(X2row, n2, d, nullptr, nullptr, X2t, n2p);
-    CKL();
-    gpk_cov_kernel<16><<<dim3((unsigned)(n2p / 128), (unsigned)(n1p / 32)), 256, 0, h->stream>>>(
-        h->spec, X2t, n2p, (int)n2, ptr<double>(h->tmp1), d, n1, nullptr, nullptr, ptr<double>(h->tmp3), n2p, 0);
-    CKL();
+    if ((rc = build_cov_operand(h, h->stream, X2row, n2, d, nullptr, nullptr, X2t, n2p))) return rc;
+    if ((rc = launch_cov_tiles(h, h->stream, X2t, n2p, (int)n2, ptr<double>(h->tmp1), d, n1, n1p, nullptr, nullptr,
+                               ptr<double>(h->tmp3), n2p, 0, false)))
+        return rc;
     CK(cudaMemcpy2DAsync(out, (size_t)n2 * 8, h->tmp3.p, (size_t)n2p * 8, (size_t)n2 * 8, (size_t)n1,
                          cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -18,7 +18,22 @@ struct KSpec {
     int axis[GPK_MAX_TERMS];
     int last[GPK_MAX_TERMS];        // 1 if term t closes its product group
     double inv_metric[GPK_MAX_TERMS];
+    double scale[GPK_MAX_TERMS];    // sqrt(c_f / metric_t): coordinates pre-scaled so that q = sum (s - s')^2 is the
+                                    // radial argument directly (c_f = 5 Matern-5/2, 3 Matern-3/2, 1/2 ExpSquared)
 };
+
+// f as a function of q = c_f * r2 (pre-scaled coordinates, gpk_cov_tma_kernel)
+__device__ __forceinline__ double gpk_radial_q(int family, double q) {
+    if (family == GPK_MATERN52) {
+        double r = sqrt(q);
+        return fma(q, 1.0 / 3.0, 1.0 + r) * exp(-r);           // 1 + r + 5 r2 / 3
+    } else if (family == GPK_EXPSQUARED) {
+        return exp(-q);
+    } else {
+        double r = sqrt(q);
+        return (1.0 + r) * exp(-r);
+    }
+}
 
 // f(r2) for the radial families (oracle/george_oracle.py: Matern52Kernel._f etc.).
 __device__ __forceinline__ double gpk_radial(int family, double r2) {

@@ -66,6 +66,124 @@ gpk_cov_kernel(const KSpec ks, const double* __restrict__ Xt, long ldx, int n,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Covariance tile builder, TMA-staged (default).  Same contract as gpk_cov_kernel, other operand layout:
+//   train side : TERM-major, pre-scaled   Xs[t][j] = x_j[axis_t] * sqrt(c_f / metric_t)   (gpk_termmajor_kernel),
+//                one cp.async.bulk.tensor.2d (box n_terms x 128 columns, no swizzle) per CTA into shared memory,
+//                completion on an mbarrier; threads read their two train points with one 16-byte LDS per term
+//   candidates : row-major raw inputs, scaled (bounds, then the same per-term factor) while filling shared memory
+// so the inner loop is  d = s - x ; q = fma(d, d, q)  : 2 FP64 instructions per (pair, term) instead of 3, and one
+// broadcast LDS per CC pairs instead of one per pair (the old kernel was co-limited by the LSU: 33 % of the DFMA peak).
+// CTA = 128 train points x 4 CC candidates, 256 threads, thread = 2 train points x CC candidates (CC = 8: 128 x 32 tile;
+// CC = 4: 128 x 16 tile, <= 64 registers so that a CTA fits next to a resident variance-GEMM CTA).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cov_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int CC>
+__global__ void __launch_bounds__(256, CC == 8 ? 2 : 4)
+gpk_cov_tma_kernel(const __grid_constant__ CUtensorMap mapX, const KSpec ks, int n,
+                   const double* __restrict__ cand, int dc, long m,
+                   const double* __restrict__ lower, const double* __restrict__ upper,
+                   double* __restrict__ out, long ldo, int tri)
+{
+    constexpr int TC = 4 * CC;
+    extern __shared__ unsigned char cov_raw[];
+    const int tid = threadIdx.x;
+    const long c0 = (long)blockIdx.y * TC;
+    if (tri && (long)blockIdx.x * 128 > c0 + TC - 1) return;
+    const int nt = ks.n_terms;
+    const uint32_t base = (cov_smem_u32(cov_raw) + 127u) & ~127u;
+    const uint32_t xs = base;                                   // nt x 128 doubles
+    const uint32_t scb = xs + (uint32_t)nt * 1024u;             // TC x nt doubles
+    const uint32_t bar = scb + (uint32_t)(TC * nt) * 8u;        // 8-byte aligned mbarrier
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)nt * 1024u) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     :: "r"(xs), "l"((uint64_t)&mapX), "r"(bar), "r"((int)(blockIdx.x * 128)), "r"(0) : "memory");
+    }
+    for (int e = tid; e < TC * nt; e += 256) {
+        const int c = e / nt, t = e - c * nt;
+        const long ci = c0 + c;
+        double v = 0.0;
+        if (ci < m) {
+            const int a = ks.axis[t];
+            v = cand[ci * dc + a];
+            if (lower != nullptr) v = (v - lower[a]) / (upper[a] - lower[a]);
+            v *= ks.scale[t];
+        }
+        asm volatile("st.shared.f64 [%0], %1;" :: "r"(scb + (uint32_t)e * 8u), "d"(v) : "memory");
+    }
+    __syncthreads();
+    {
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar) : "memory");
+    }
+    const int jp = tid & 63, cgp = tid >> 6;
+    double q[CC][2], pr[CC][2];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) { q[c][0] = q[c][1] = 0.0; pr[c][0] = pr[c][1] = 1.0; }
+    const uint32_t xrow = xs + (uint32_t)jp * 16u;
+    const uint32_t srow = scb + (uint32_t)(cgp * CC * nt) * 8u;
+    for (int t = 0; t < nt; ++t) {
+        double x0, x1;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(xrow + (uint32_t)t * 1024u));
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+            double sv;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(sv) : "r"(srow + (uint32_t)(c * nt + t) * 8u));
+            const double d0 = sv - x0, d1 = sv - x1;
+            q[c][0] = fma(d0, d0, q[c][0]);
+            q[c][1] = fma(d1, d1, q[c][1]);
+        }
+        if (ks.last[t]) {
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+                pr[c][0] *= gpk_radial_q(ks.family, q[c][0]);
+                pr[c][1] *= gpk_radial_q(ks.family, q[c][1]);
+                q[c][0] = q[c][1] = 0.0;
+            }
+        }
+    }
+    const int j0 = blockIdx.x * 128 + 2 * jp;
+    const bool v0 = j0 < n, v1 = j0 + 1 < n;
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+        const long ci = c0 + cgp * CC + c;
+        const bool cv = ci < m;
+        double2 o;
+        o.x = (cv && v0) ? ks.amp * pr[c][0] : 0.0;
+        o.y = (cv && v1) ? ks.amp * pr[c][1] : 0.0;
+        *reinterpret_cast<double2*>(out + ci * ldo + j0) = o;
+    }
+}
+
+inline size_t cov_tma_smem_bytes(int n_terms, int cc) { return (size_t)n_terms * 1024 + (size_t)4 * cc * n_terms * 8 + 8 + 128; }
+
+// Xs[t][j] = scaled x_j[axis_t] * scale_t  (term-major operand of gpk_cov_tma_kernel), zero padded to ldx columns
+__global__ void gpk_termmajor_kernel(const KSpec ks, const double* __restrict__ X, long n, int d,
+                                     const double* __restrict__ lower, const double* __restrict__ upper,
+                                     double* __restrict__ Xs, long ldx)
+{
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)ks.n_terms * ldx;
+    if (idx >= total) return;
+    int t = (int)(idx / ldx);
+    long j = idx - (long)t * ldx;
+    double v = 0.0;
+    if (j < n) {
+        const int a = ks.axis[t];
+        v = X[j * d + a];
+        if (lower != nullptr) v = (v - lower[a]) / (upper[a] - lower[a]);
+        v *= ks.scale[t];
+    }
+    Xs[idx] = v;
+}
+
 // Xt[a][j] = X[j][a] (optionally scaled), zero padded to ldx columns.
 __global__ void gpk_transpose_kernel(const double* __restrict__ X, long n, int d,
                                      const double* __restrict__ lower, const double* __restrict__ upper,
