@@ -44,6 +44,9 @@ struct gpk_handle {
     std::vector<cudaEvent_t> ev_panel, ev_rest;
     cudaStream_t panel_stream = nullptr;    // split chain: panel solve / next-panel update of the rows below block row k+1
     std::vector<cudaEvent_t> ev_cs;         // split chain: 5 events per step (diag, X, trsm', pu', rest_a)
+    int persist = 1;                // 1: persistent variance contraction (gpk_vargemm_persistent_kernel) [default]
+    DevBuf tile_cnt;
+    int n_sm = 0;
     int chainsplit = 1;             // 1: diag(k+1) waits only for block row k+1 of step k (gpk_chain_step_kernel on 4 CTAs)
     int lookahead = 1;
     int smalltile = 1;              // 32-row tiles for the panel solve / next-panel update
@@ -325,6 +328,12 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 1)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 1)));
+    CK(cudaFuncSetAttribute(gpk_vargemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_SMEM));
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, h->device));
+        h->n_sm = prop.multiProcessorCount;
+    }
     CK(cudaFuncSetAttribute(gpk_cov_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_tma_smem_bytes(GPK_MAX_TERMS, 8)));
     CK(cudaFuncSetAttribute(gpk_cov_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_tma_smem_bytes(GPK_MAX_TERMS, 4)));
     CK(cudaFuncSetAttribute(gpk_potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
@@ -731,7 +740,17 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         a.ldpart = cap;
         if (last) CK(cudaEventRecord(h->ev[10], h->stream));
         CK(cudaEventRecord(h->ev_g0[ci], h->stream));
-        if ((rc = launch_gemm<EPI_COLREDUCE>(h, h->mapP, second ? h->mapKs2 : h->mapKs, a, h->nb * a.mcb))) return rc;
+        if (h->persist && h->loader == LOADER_TMA_WS) {
+            // one CTA per SM, tiles handed out by a counter (zeroed in stream order before every launch)
+            if ((rc = ensure(h, h->tile_cnt, 4))) return rc;
+            CK(cudaMemsetAsync(h->tile_cnt.p, 0, 4, h->stream));
+            VarArgs v;
+            v.nb = a.nb; v.mcb = a.mcb; v.z = a.z; v.part_mu = a.part_mu; v.part_ssq = a.part_ssq; v.ldpart = a.ldpart;
+            v.counter = ptr<int>(h->tile_cnt);
+            const int grid = std::min(h->nb * a.mcb, std::max(h->n_sm, 1));
+            gpk_vargemm_persistent_kernel<<<grid, WS_THREADS, PV_SMEM, h->stream>>>(h->mapP, second ? h->mapKs2 : h->mapKs, v);
+            CKL();
+        } else if ((rc = launch_gemm<EPI_COLREDUCE>(h, h->mapP, second ? h->mapKs2 : h->mapKs, a, h->nb * a.mcb))) return rc;
         CK(cudaEventRecord(h->ev_g1[ci], h->stream));
         if (last) CK(cudaEventRecord(h->ev[11], h->stream));
         if (pipelined) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
@@ -818,7 +837,7 @@ int gpk_destroy(gpk_handle* h) {
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
                       &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
-                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts,
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt,
                       &h->multi_cand, &h->multi_A, &h->multi_B, &h->multi_out, &h->multi_bb, &h->gather, &h->best_global};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -854,6 +873,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->maps_ok = false;
         h->mapKs_rows = 0;
         h->mapVt_rows = 0;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "persist")) {
+        if (value != 0 && value != 1) BAD("persist must be 0 or 1");
+        h->persist = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "chainsplit")) {
