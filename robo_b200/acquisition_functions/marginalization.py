@@ -50,7 +50,8 @@ class MarginalizationGPMCMC(BaseAcquisitionFunction):
             # marginalization.py:115-121 as ONE call: the batch goes to the device once, the n sub-models score it
             # concurrently and the mean over models is taken there (gpk_acq_multi mode 0); M doubles come back
             kind, etas, par, handles = fused
-            r = _lib.acq_multi(handles, np.asarray(X_test, dtype=np.float64), 0, _lib.ACQ_KIND[kind], etas, par)
+            X_dev = self.model.models[0].device_inputs(np.asarray(X_test, dtype=np.float64))
+            r = _lib.acq_multi(handles, X_dev, 0, _lib.ACQ_KIND[kind], etas, par)
             if kind == "ei" and r["n_negative"] > 0:
                 raise ValueError("Expected Improvement is smaller than 0!")      # ei.py:86-88
             return r["values"]
@@ -65,8 +66,8 @@ class MarginalizationGPMCMC(BaseAcquisitionFunction):
         if fused is None:
             return int(np.argmax(self.compute(X_test)))
         kind, etas, par, handles = fused
-        r = _lib.acq_multi(handles, np.asarray(X_test, dtype=np.float64), 0, _lib.ACQ_KIND[kind], etas, par,
-                           want_argmax=True)
+        X_dev = self.model.models[0].device_inputs(np.asarray(X_test, dtype=np.float64))
+        r = _lib.acq_multi(handles, X_dev, 0, _lib.ACQ_KIND[kind], etas, par, want_argmax=True)
         if kind == "ei" and r["n_negative"] > 0:
             raise ValueError("Expected Improvement is smaller than 0!")
         return int(r["best_idx"])
@@ -79,7 +80,7 @@ class MarginalizationGPMCMC(BaseAcquisitionFunction):
         pars = set(float(getattr(e, "par", 0.0)) for e in self.estimators)
         if len(kinds) != 1 or len(pars) != 1 or list(kinds)[0] not in ("ei", "log_ei", "pi", "lcb"):
             return None
-        if any(e.model is not m for e, m in zip(self.estimators, self.model.models)):
+        if any(e.model is not m or not hasattr(m, "device_inputs") for e, m in zip(self.estimators, self.model.models)):
             return None
         handles = self.model.sub_model_handles()
         if handles is None or len(handles) != len(self.estimators):

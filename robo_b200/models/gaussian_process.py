@@ -174,6 +174,11 @@ class GaussianProcess(BaseModel):
             return self.gp.predict_cov(X_test)
         return self.gp.predict_moments(X_test)
 
+    def device_inputs(self, X_test):
+        """What the device handle expects for the raw inputs X_test (the handle applies the [lower, upper] scaling
+        itself); subclasses that transform inputs on the host (FabolasGP) return the transformed array."""
+        return X_test
+
     def score(self, X_test, kind, eta=None, par=0.0, want_values=True):
         """Fused predict -> acquisition -> arg-max used by robo_b200.acquisition_functions.
         ``kind``: one of 'ei', 'log_ei', 'pi', 'lcb'."""

@@ -100,10 +100,7 @@ class GaussianProcessMCMC(BaseModel):
     @BaseModel._check_shapes_train
     def train(self, X, y, do_optimize=True, **kwargs):
         """gaussian_process_mcmc.py:76-166."""
-        if self.normalize_input:
-            self.X, self.lower, self.upper = normalization.zero_one_normalization(X, self.lower, self.upper)
-        else:
-            self.X = X
+        self.X = self._likelihood_inputs(X)
         if self.normalize_output:
             self.y, self.y_mean, self.y_std = normalization.zero_mean_unit_var_normalization(y)
             if self.y_std == 0:
@@ -134,21 +131,36 @@ class GaussianProcessMCMC(BaseModel):
             self._pool.close()
             self._pool = None
         else:
-            self.hypers = self.gp.kernel[:].tolist()
-            self.hypers.append(self.noise)
-            self.hypers = [self.hypers]
+            self.hypers = self._hypers_without_optimisation()
 
         self.models = []
         for sample in self.hypers:
             kernel = deepcopy(self.kernel)
             kernel.set_parameter_vector(sample[:-1])
             noise = np.exp(sample[-1])
-            model = GaussianProcess(kernel, normalize_output=self.normalize_output,
-                                    normalize_input=self.normalize_input, noise=noise,
-                                    lower=self.lower, upper=self.upper, rng=self.rng, device=self.device)
+            model = self._new_sub_model(kernel, noise)
             model.train(X, y, do_optimize=False)
             self.models.append(model)
         self.is_trained = True
+
+    # hooks for FabolasGPMCMC (robo/models/fabolas_gp.py), which differs only in how inputs are prepared
+    def _likelihood_inputs(self, X):
+        """Inputs the MCMC phase factorises (gaussian_process_mcmc.py:95-99)."""
+        if self.normalize_input:
+            Xn, self.lower, self.upper = normalization.zero_one_normalization(X, self.lower, self.upper)
+            return Xn
+        return X
+
+    def _hypers_without_optimisation(self):
+        """gaussian_process_mcmc.py:144-147: the kernel's current parameters + the configured log-noise."""
+        hypers = self.gp.kernel[:].tolist()
+        hypers.append(self.noise)
+        return [hypers]
+
+    def _new_sub_model(self, kernel, noise):
+        """One GP per hyper-parameter sample (gaussian_process_mcmc.py:156-162)."""
+        return GaussianProcess(kernel, normalize_output=self.normalize_output, normalize_input=self.normalize_input,
+                               noise=noise, lower=self.lower, upper=self.upper, rng=self.rng, device=self.device)
 
     def loglikelihood(self, theta):
         """Log-likelihood + prior of one theta (gaussian_process_mcmc.py:168-202)."""
@@ -189,7 +201,7 @@ class GaussianProcessMCMC(BaseModel):
         if handles is not None:
             # one H2D of X_test, every sub-model scores it on its own stream, the mixture moments are reduced on the
             # device: 2 M doubles come back instead of 2 n_hypers M (gpk_acq_multi mode 1)
-            r = _lib.acq_multi(handles, np.asarray(X_test, dtype=np.float64), 1)
+            r = _lib.acq_multi(handles, self.models[0].device_inputs(np.asarray(X_test, dtype=np.float64)), 1)
             return r["mean"], r["var"]
         mu = np.zeros([len(self.models), X_test.shape[0]])
         var = np.zeros([len(self.models), X_test.shape[0]])

@@ -126,3 +126,73 @@ def test_product_host_layer_on_fake_handle_matches_golden(reference, golden_dir)
         np.testing.assert_allclose(model.get_incumbent()[0], d["inc_x"], rtol=1e-15)
         for cls, key in ((EI, "acq_ei"), (PI, "acq_pi"), (LCB, "acq_lcb"), (LogEI, "acq_log_ei")):
             np.testing.assert_allclose(cls(model).compute(d["Xs"]), d[key], rtol=1e-6, atol=1e-10)
+
+
+def test_fabolas_subclasses_ride_the_path(reference):
+    """robo/models/fabolas_gp.py (FabolasGP, FabolasGPMCMC) UNMODIFIED on the george / emcee shims, next to the
+    product's own FabolasGP / FabolasGPMCMC (robo_b200/models/fabolas_gp.py): same predictions, since both are the
+    base classes plus the input transform of fabolas_gp.py:122-126."""
+    import george
+    from robo.models.fabolas_gp import FabolasGP as RefFabolasGP, FabolasGPMCMC as RefFabolasGPMCMC
+    from robo_b200 import kernels as K
+    from robo_b200.acquisition_functions import EI, MarginalizationGPMCMC
+    from robo_b200.models import FabolasGP, FabolasGPMCMC
+    rng = np.random.RandomState(5)
+    lower, upper = np.array([-1.0, 2.0]), np.array([3.0, 5.0])
+    X = np.concatenate((lower + (upper - lower) * rng.rand(25, 2), rng.rand(25, 1)), axis=1)
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + (1 - X[:, 2]) ** 2
+    Xt = np.concatenate((lower + (upper - lower) * rng.rand(9, 2), rng.rand(9, 1)), axis=1)
+
+    def basis(s):
+        return (1 - s) ** 2                                   # fabolas.py:96-98
+
+    def ref_kernel():
+        k = 1.3 * george.kernels.Matern52Kernel(np.ones(1) * 0.4, ndim=3, axes=0)
+        k *= george.kernels.Matern52Kernel(np.ones(1) * 0.6, ndim=3, axes=1)
+        k *= george.kernels.Matern52Kernel(np.ones(1) * 0.9, ndim=3, axes=2)
+        return k
+
+    def own_kernel():
+        k = 1.3 * K.Matern52Kernel(np.ones(1) * 0.4, ndim=3, axes=0)
+        k *= K.Matern52Kernel(np.ones(1) * 0.6, ndim=3, axes=1)
+        k *= K.Matern52Kernel(np.ones(1) * 0.9, ndim=3, axes=2)
+        return k
+    ref = RefFabolasGP(ref_kernel(), basis_function=basis, noise=1e-3, lower=lower, upper=upper, rng=np.random.RandomState(0))
+    own = FabolasGP(own_kernel(), basis_function=basis, noise=1e-3, lower=lower, upper=upper, rng=np.random.RandomState(0))
+    ref.train(X, y, do_optimize=False)
+    own.train(X, y, do_optimize=False)
+    m1, v1 = ref.predict(Xt)
+    m2, v2 = own.predict(Xt)
+    np.testing.assert_allclose(m2, m1, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(v2, v1, rtol=1e-7)
+    np.testing.assert_allclose(EI(own).compute(Xt), EI(ref).compute(Xt), rtol=1e-6, atol=1e-12)
+    # MCMC variants: short chains; the product's sub-models are FabolasGP on the device path and the marginalised
+    # acquisition goes through the fused multi-model call on transformed inputs
+    class Prior(object):
+        def __init__(self, r):
+            self.r = r
+
+        def lnprob(self, t):
+            return 0.0 if np.all(np.abs(t) < 6) else -np.inf
+
+        def sample_from_prior(self, n):
+            return self.r.uniform(-2, 1, size=(n, 5))
+    refm = RefFabolasGPMCMC(ref_kernel(), basis_func=basis, prior=Prior(np.random.RandomState(1)), n_hypers=10,
+                            chain_length=4, burnin_steps=3, lower=lower, upper=upper, rng=np.random.RandomState(2))
+    refm.train(X, y, do_optimize=True)
+    assert len(refm.models) == 10 and refm.predict(Xt)[0].shape == (9,)
+    ownm = FabolasGPMCMC(own_kernel(), basis_func=basis, prior=Prior(np.random.RandomState(1)), n_hypers=10,
+                         chain_length=4, burnin_steps=3, lower=lower, upper=upper, rng=np.random.RandomState(2))
+    ownm.train(X, y, do_optimize=True)
+    assert len(ownm.models) == 10 and all(isinstance(m, FabolasGP) for m in ownm.models)
+    m, v = ownm.predict(Xt)
+    mus = np.array([sub.predict(Xt)[0] for sub in ownm.models])
+    vs = np.array([sub.predict(Xt)[1] for sub in ownm.models])
+    np.testing.assert_allclose(m, mus.mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(v, np.clip(mus.var(axis=0) + vs.mean(axis=0), np.finfo(float).eps, np.inf), rtol=1e-10)
+    acq = MarginalizationGPMCMC(EI(ownm))
+    assert acq._fused_spec() is not None
+    np.testing.assert_allclose(acq.compute(Xt), np.mean([EI(s).compute(Xt) for s in ownm.models], axis=0), rtol=1e-12)
+    hyp = [list(hh) for hh in ownm.hypers]
+    ownm.train(X, y, do_optimize=False)                       # fabolas_gp.py:77-81: samples are kept
+    assert [list(hh) for hh in ownm.hypers] == hyp
