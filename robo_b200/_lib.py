@@ -141,6 +141,11 @@ class Handle(object):
             self.set_option("diag", int(os.environ["GPK_DIAG"]))
         if os.environ.get("GPK_CHUNK"):
             self.set_option("chunk", int(os.environ["GPK_CHUNK"]))
+        # implementation switches (all default-on variants have a cross-check twin): GPK_COV=1|2, GPK_PERSIST=0|1,
+        # GPK_CHAINSPLIT=0|1
+        for env, key in (("GPK_COV", "cov"), ("GPK_PERSIST", "persist"), ("GPK_CHAINSPLIT", "chainsplit")):
+            if os.environ.get(env):
+                self.set_option(key, int(os.environ[env]))
 
     # -- plumbing -----------------------------------------------------------------
     def close(self):
