@@ -27,6 +27,8 @@
 
 namespace {
 
+constexpr int APP_KC = 512;          // split-K chunk of gpk_fit_append's long contractions
+
 struct Range { int off = 0, cnt = 0; };
 
 struct DevBuf {
@@ -89,6 +91,7 @@ struct gpk_handle {
     std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r, trsm32_r, pu32_r, trsm16_r, pu16_r;
     Range kinv_r;
     Range app_row_r, app_syrk_r, app_t_r, app_p_r;      // gpk_fit_append (last block row only)
+    Range app_row2_r, app_t2_r;                         // split-K versions of the two long contractions
 
     // tensor maps
     CUtensorMap mapK, mapP, mapQ, mapW, mapKs, mapVt;
@@ -469,6 +472,18 @@ int build_job_tables(gpk_handle* h) {
             for (int q = 0; q < 4; ++q)
                 jobs.push_back({N1 + 32 * q, j * BM, j * BM, N1, N1 + 32 * q, j * BM, 0, 0});
         h->app_t_r.cnt = (int)jobs.size() - h->app_t_r.off;
+        // split-K versions (default): 128-row tiles, the contraction cut into chunks of APP_KC columns, partial tile
+        // (chunk c, column block j) -> scratch tile W(c, j); summed in fixed order by gpk_append_reduce_kernel
+        h->app_row2_r.off = (int)jobs.size();
+        for (int j = b - 1; j >= 0; --j)
+            for (int c = 0, k0 = 0; k0 < (j + 1) * BM; ++c, k0 += APP_KC)
+                jobs.push_back({N1, j * BM, k0, std::min(k0 + APP_KC, (j + 1) * BM), c * BM, j * BM, 0, 0});
+        h->app_row2_r.cnt = (int)jobs.size() - h->app_row2_r.off;
+        h->app_t2_r.off = (int)jobs.size();
+        for (int j = 0; j < b; ++j)
+            for (int c = 0, k0 = j * BM; k0 < N1; ++c, k0 += APP_KC)
+                jobs.push_back({N1, j * BM, k0, std::min(k0 + APP_KC, N1), c * BM, j * BM, 0, 0});
+        h->app_t2_r.cnt = (int)jobs.size() - h->app_t2_r.off;
         // P[b, j] = -P_bb T[:, j]
         h->app_p_r.off = (int)jobs.size();
         for (int j = 0; j < b; ++j)
@@ -576,6 +591,22 @@ __global__ void gpk_kfix_rows_kernel(double* __restrict__ K, long ld, int n, int
     int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NP) return;
     K[(long)i * ld + i] = (i < n) ? K[(long)i * ld + i] + diag_add : 1.0;
+}
+
+// dst[:, j-block] = sum_c W(c, j) over the nc(j) partial tiles of column block j (c ascending: deterministic);
+// mode 0: nc = ceil((j + 1) * 128 / APP_KC) (L_row), mode 1: nc = ceil((b - j) * 128 / APP_KC) (L_row P11).
+// dstT (may be NULL) receives the transpose: dstT[j*128 + c][r].  grid = (b, 64), 256 threads, one element each.
+__global__ void gpk_append_reduce_kernel(const double* __restrict__ W, long ld, int b, int mode, double* __restrict__ dst,
+                                         long ldd, double* __restrict__ dstT, long lddT, int tcol0) {
+    const int j = blockIdx.x;
+    const int e = blockIdx.y * 256 + threadIdx.x;              // 0 .. 128*128-1
+    const int r = e >> 7, c = e & 127;
+    const int len = mode == 0 ? (j + 1) * 128 : (b - j) * 128;
+    const int nc = (len + APP_KC - 1) / APP_KC;
+    double acc = 0.0;
+    for (int q = 0; q < nc; ++q) acc += W[(long)(q * 128 + r) * ld + j * 128 + c];
+    dst[(long)r * ldd + j * 128 + c] = acc;
+    if (dstT != nullptr) dstT[(long)(j * 128 + c) * lddT + tcol0 + r] = acc;
 }
 
 // K[b,b] -= sum_s T_s with T_s = W tile (s, b), s ascending (deterministic); one thread per element
@@ -1436,12 +1467,14 @@ int gpk_fit_append(gpk_handle* h, const double* X, const double* y, int n, int d
     CK(cudaMemsetAsync(h->status.p, 0, 4, h->stream));
     CK(cudaEventRecord(h->ev[1], h->stream));
     GemmArgs a;
-    // L_row -> W[b, 0:N1]
+    // L_row = K[b, 0:N1] P11^T -> W[b, 0:N1]: split-K partial tiles into the free tiles W(c, j), then a fixed-order sum
     memset(&a, 0, sizeof(a));
     a.A = K; a.lda = NP; a.B = P; a.ldb = NP; a.C = W; a.ldc = NP;
     a.alpha = 1.0; a.beta = 0; a.job_mode = JOBS_TABLE;
-    a.jobs = ptr<GemmJob>(h->jobs) + h->app_row_r.off;
-    if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapP, a, h->app_row_r.cnt))) return rc;
+    a.jobs = ptr<GemmJob>(h->jobs) + h->app_row2_r.off;
+    if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapP, a, h->app_row2_r.cnt))) return rc;
+    gpk_append_reduce_kernel<<<dim3(b, 64), 256, 0, h->stream>>>(W, NP, b, 0, W + (long)N1 * NP, NP, nullptr, 0, 0);
+    CKL();
     // partial Gram tiles, then the Schur complement of the last block
     memset(&a, 0, sizeof(a));
     a.A = W; a.lda = NP; a.B = W; a.ldb = NP; a.C = W; a.ldc = NP;
@@ -1474,12 +1507,14 @@ int gpk_fit_append(gpk_handle* h, const double* X, const double* y, int n, int d
                                                                 ptr<double>(h->logdet_part));
     }
     CKL();
-    // T = L_row P11 -> P[b, 0:N1], T^T -> Q[0:N1, b]
+    // T = L_row P11 -> P[b, 0:N1], T^T -> Q[0:N1, b]   (split-K like L_row; the Gram partials in W(s, b) are consumed)
     memset(&a, 0, sizeof(a));
-    a.A = K; a.lda = NP; a.B = Q; a.ldb = NP; a.C = P; a.ldc = NP; a.Ct = Q; a.ldct = NP;
+    a.A = K; a.lda = NP; a.B = Q; a.ldb = NP; a.C = W; a.ldc = NP;
     a.alpha = 1.0; a.beta = 0; a.job_mode = JOBS_TABLE; a.status = ptr<int>(h->status);
-    a.jobs = ptr<GemmJob>(h->jobs) + h->app_t_r.off;
-    if ((rc = launch_gemm<EPI_STORE, 2>(h, h->mapK32, h->mapQ, a, h->app_t_r.cnt))) return rc;
+    a.jobs = ptr<GemmJob>(h->jobs) + h->app_t2_r.off;
+    if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapQ, a, h->app_t2_r.cnt))) return rc;
+    gpk_append_reduce_kernel<<<dim3(b, 64), 256, 0, h->stream>>>(W, NP, b, 1, P + (long)N1 * NP, NP, Q, NP, N1);
+    CKL();
     // P[b, 0:N1] = -P_bb T (and its transpose into Q)
     memset(&a, 0, sizeof(a));
     a.A = P; a.lda = NP; a.B = Q; a.ldb = NP; a.C = P; a.ldc = NP; a.Ct = Q; a.ldct = NP;
