@@ -40,3 +40,6 @@ timeout 600 python tools/fit_compare.py > $out/r2_fit_compare.jsonl 2> $out/r2_f
 # int8 tcgen05 probe (VERDICT item 8 groundwork): descriptors checked against a CPU integer GEMM + issue rate
 (cd tools/microbench && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o i8_umma_probe.bin i8_umma_probe.cu -lcuda \
    && timeout 120 ./i8_umma_probe.bin) > $out/r2_i8_probe.json 2> $out/r2_i8_probe.err; cat $out/r2_i8_probe.json; tail -3 $out/r2_i8_probe.err
+# Ozaki prototype: fp64 variance contraction on the int8 tensor pipe (accuracy vs an 80-bit CPU reference + C2-chunk timing)
+(cd tools/microbench && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o ozaki_probe.bin ozaki_probe.cu -lcuda \
+   && timeout 300 ./ozaki_probe.bin) > $out/r2_ozaki_probe.json 2> $out/r2_ozaki_probe.err; cat $out/r2_ozaki_probe.json; tail -3 $out/r2_ozaki_probe.err
