@@ -39,23 +39,29 @@ class _LikelihoodPool(object):
         """thetas: (B', H) with B' <= pool size -> log-likelihoods (no prior), -inf where not PD."""
         out = np.full(len(thetas), -np.inf)
         started = []
-        for i, theta in enumerate(thetas):
-            if np.any((-20 > theta) + (theta > 20)):           # gaussian_process_mcmc.py:187-188
-                continue
-            h = self.handles[i]
-            self.kernel.set_parameter_vector(theta[:-1])
-            f = self.kernel.flatten()
-            h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
-            yerr = np.sqrt(np.exp(theta[-1]))
-            diag_add = float(np.sqrt(np.float64(yerr) ** 2 + TINY) ** 2)
-            h.fit_begin(diag_add, self.mean)
-            started.append(i)
-        for i in started:
-            try:
-                _, ll = self.handles[i].fit_end()
-                out[i] = ll if np.isfinite(ll) else -np.inf
-            except np.linalg.LinAlgError:                       # :194-197 bare except -> -inf
-                out[i] = -np.inf
+        try:
+            for i, theta in enumerate(thetas):
+                if np.any((-20 > theta) + (theta > 20)):           # gaussian_process_mcmc.py:187-188
+                    continue
+                h = self.handles[i]
+                try:                                                # :194-197: any failure of one theta is -inf for it
+                    self.kernel.set_parameter_vector(theta[:-1])
+                    f = self.kernel.flatten()
+                    h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+                    yerr = np.sqrt(np.exp(theta[-1]))
+                    diag_add = float(np.sqrt(np.float64(yerr) ** 2 + TINY) ** 2)
+                    h.fit_begin(diag_add, self.mean)
+                except (ValueError, RuntimeError, np.linalg.LinAlgError):
+                    continue
+                started.append(i)
+        finally:
+            # every handle that started a factorisation is drained, whatever happened to the others
+            for i in started:
+                try:
+                    _, ll = self.handles[i].fit_end()
+                    out[i] = ll if np.isfinite(ll) else -np.inf
+                except (np.linalg.LinAlgError, ValueError, RuntimeError):
+                    out[i] = -np.inf
         return out
 
     def close(self):

@@ -18,6 +18,14 @@ class BayesianOptimization(object):
     def __init__(self, objective_func, lower, upper, acquisition_func, model, maximize_func,
                  initial_design=init_random_uniform, initial_points=3, output_path=None,
                  train_interval=1, n_restarts=1, rng=None):
+        if output_path is not None:
+            # the reference writes one JSON file per iteration (solver/bayesian_optimization.py:143-144, :251-261); this
+            # minimal loop does not: refuse loudly instead of silently dropping the logs (use the reference's own
+            # solver with the robo_b200 objects when they are wanted)
+            raise NotImplementedError("output_path is not supported by robo_b200.solver; run robo.solver.bayesian_optimization."
+                                      "BayesianOptimization with the robo_b200 model / acquisition / maximizer objects")
+        self.output_path = output_path
+        self.n_restarts = n_restarts
         self.rng = np.random.RandomState(np.random.randint(100000)) if rng is None else rng
         self.model = model
         self.acquisition_func = acquisition_func
