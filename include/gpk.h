@@ -65,6 +65,10 @@ const char* gpk_version(void);
  *   "chunk"     candidates per scoring pass (multiple of 128); 0 = automatic [default]: the K* buffer is kept near
  *               512 MB (16384 candidates at N = 4096, 65536 at N <= 1024)
  *   "cov"       covariance builder: 2 = TMA-staged, pre-scaled term-major operands [default], 1 = round-1 kernel
+ *   "ozaki"     1 = variance contraction on the int8 tensor pipe (tcgen05 kind::i8, TMEM accumulators) through an
+ *               error-free 8 x 8 slice split of L^-1 and K* (gpk_ozaki.cuh); used while max |L^-1| < 64, otherwise the
+ *               fp64 kernel runs; 0 = always fp64 DMMA [default]
+ *   "persist"   1 = persistent fp64 variance contraction (one CTA per SM, dynamic tile counter) [default]
  *   "chainsplit" 1 = split Cholesky chain [default]: diag(k+1) waits only for block row k+1 of step k (one launch on
  *               four 32-row tiles), the rows below run on a second high-priority stream, trailing update with
  *               look-ahead 2; 0 = plain look-ahead schedule (bit-identical factor)
@@ -266,8 +270,10 @@ int gpk_get_z(gpk_handle* h, double* z /* n */);
  * [5] K* build and [7] epilogue of the last candidate chunk, [6] variance GEMM averaged over the
  * full-size chunk launches of that call;
  * out[8] = variance-GEMM launches so far,
- * out[9] = total kernel launches so far. */
-int gpk_get_timings(gpk_handle* h, double* out10);
+ * out[9] = total kernel launches so far,
+ * out[10] = of those, launches of the int8 (Ozaki) contraction; out[11] = largest row exponent of L^-1 seen by it
+ * (option "ozaki"); out[12..15] reserved (zero). */
+int gpk_get_timings(gpk_handle* h, double* out16);
 /* diagnostics of the blocked diagonal-block kernel (option "diagprof" = 1): clock64() stamps of the last
  * launched block: out[0] start, out[1] tiles loaded, out[2+2p] panel p factorised + solved, out[3+2p] panel p's
  * rank-16 update applied and panel p+1 published, out[33] end, out[34..41] finer stamps inside panel 3. */

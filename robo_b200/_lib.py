@@ -142,8 +142,9 @@ class Handle(object):
         if os.environ.get("GPK_CHUNK"):
             self.set_option("chunk", int(os.environ["GPK_CHUNK"]))
         # implementation switches (all default-on variants have a cross-check twin): GPK_COV=1|2, GPK_PERSIST=0|1,
-        # GPK_CHAINSPLIT=0|1
-        for env, key in (("GPK_COV", "cov"), ("GPK_PERSIST", "persist"), ("GPK_CHAINSPLIT", "chainsplit")):
+        # GPK_CHAINSPLIT=0|1, GPK_OZAKI=0|1
+        for env, key in (("GPK_COV", "cov"), ("GPK_PERSIST", "persist"), ("GPK_CHAINSPLIT", "chainsplit"),
+                         ("GPK_OZAKI", "ozaki")):
             if os.environ.get(env):
                 self.set_option(key, int(os.environ[env]))
 
@@ -407,10 +408,10 @@ class Handle(object):
         return t
 
     def timings(self):
-        t = np.zeros(10)
+        t = np.zeros(16)
         self._check(self.lib.gpk_get_timings(self._h, _as_dp(t)))
         keys = ["fit_ms", "kbuild_ms", "potrf_ms", "linv_ms", "score_ms", "kstar_ms", "vargemm_ms", "finish_ms",
-                "launches_vargemm", "launches_total"]
+                "launches_vargemm", "launches_total", "launches_ozaki", "ozaki_max_row_exponent"]
         return dict(zip(keys, t.tolist()))
 
 

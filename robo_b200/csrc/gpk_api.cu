@@ -24,6 +24,7 @@
 #include "gpk_kernels.cuh"
 #include "gpk_diag16.cuh"
 #include "gpk_chain.cuh"
+#include "gpk_ozaki.cuh"
 
 namespace {
 
@@ -46,6 +47,15 @@ struct gpk_handle {
     std::vector<cudaEvent_t> ev_panel, ev_rest;
     cudaStream_t panel_stream = nullptr;    // split chain: panel solve / next-panel update of the rows below block row k+1
     std::vector<cudaEvent_t> ev_cs;         // split chain: 5 events per step (diag, X, trsm', pu', rest_a)
+    // variance contraction on the int8 tensor pipe (gpk_ozaki.cuh); 0 = fp64 DMMA kernels
+    int ozaki = 0;
+    DevBuf oz_Pq, oz_Kq, oz_Kq2, oz_eP, oz_emax;
+    long oz_linv_serial = -1;       // linv_serial the slices of L^-1 were made for
+    long linv_serial = 0;           // bumped whenever L^-1 is (re)built
+    int oz_emax_host = 0;
+    long oz_rows = 0, oz_rows2 = 0;
+    CUtensorMap mapOzP, mapOzK, mapOzK2;
+    double oz_launches = 0;
     int persist = 1;                // 1: persistent variance contraction (gpk_vargemm_persistent_kernel) [default]
     DevBuf tile_cnt;
     int n_sm = 0;
@@ -331,6 +341,7 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 2)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 1)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 1)));
+    CK(cudaFuncSetAttribute(gpk_oz_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
     CK(cudaFuncSetAttribute(gpk_vargemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_SMEM));
     {
         cudaDeviceProp prop;
@@ -662,6 +673,48 @@ int build_linv(gpk_handle* h) {
     }
     CK(cudaEventRecord(h->ev[5], h->stream));
     h->linv_ready = true;
+    h->linv_serial += 1;
+    return GPK_OK;
+}
+
+// int8 tensor map over S stacked slice matrices [S * rows][cols] (int8, K contiguous): box = 64 bytes x box_rows, 64B swizzle
+int make_oz_map(gpk_handle* h, CUtensorMap* map, void* base, long rows_total, long cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_err(h, "cuTensorMapEncodeTiled entry point not available"); return GPK_CUDA_ERROR; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows_total};
+    cuuint64_t strides[1] = {(cuuint64_t)cols};
+    cuuint32_t box[2] = {(cuuint32_t)OZ_KB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_err(h, "cuTensorMapEncodeTiled (int8 slices) failed with CUresult %d", (int)r); return GPK_CUDA_ERROR; }
+    return GPK_OK;
+}
+
+// Slices of L^-1 for the int8 contraction, once per factorisation.  Returns true in *usable when the factor is
+// conditioned well enough for S = 8 slices (row exponents <= OZ_MAX_EXP) and the sizes fit the int32 accumulators.
+int prepare_ozaki(gpk_handle* h, bool* usable) {
+    *usable = false;
+    if (!h->ozaki || h->loader == LOADER_CPASYNC || h->NP > 16384) return GPK_OK;
+    const long NP = h->NP;
+    if (h->oz_linv_serial != h->linv_serial) {
+        int rc;
+        if ((rc = ensure(h, h->oz_Pq, (size_t)OZ_S * NP * NP))) return rc;
+        if ((rc = ensure(h, h->oz_eP, (size_t)NP * 4))) return rc;
+        if ((rc = ensure(h, h->oz_emax, 4))) return rc;
+        const int lowest = -100000;
+        CK(cudaMemcpyAsync(h->oz_emax.p, &lowest, 4, cudaMemcpyHostToDevice, h->stream));
+        gpk_oz_rowexp_kernel<<<(unsigned)NP, 256, 0, h->stream>>>(ptr<double>(h->P), NP, (int)NP, ptr<int>(h->oz_eP), ptr<int>(h->oz_emax));
+        CKL();
+        gpk_oz_split_kernel<<<(unsigned)((NP * NP + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->P), NP, NP, ptr<int>(h->oz_eP), 0,
+                                                                                   ptr<int8_t>(h->oz_Pq), NP * NP);
+        CKL();
+        CK(cudaMemcpyAsync(&h->oz_emax_host, h->oz_emax.p, 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if ((rc = make_oz_map(h, &h->mapOzP, h->oz_Pq.p, (long)OZ_S * NP, NP, OZ_TM))) return rc;
+        h->oz_linv_serial = h->linv_serial;
+    }
+    *usable = h->oz_emax_host <= OZ_MAX_EXP;
     return GPK_OK;
 }
 
@@ -693,6 +746,27 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
     const long NP = h->NP;
     const long cap = std::min<long>(chunk_rows(h), round_up(std::max<long>(m, 1), BM));
     if ((rc = ensure_score_scratch(h, cap))) return rc;
+    bool use_oz = false;
+    if ((rc = prepare_ozaki(h, &use_oz))) return rc;
+    int oz_eK = 0;
+    if (use_oz) {
+        // slices of K* per chunk buffer: [S][cap][NP] int8; one exponent for the whole matrix (0 < k <= amp)
+        bool grew = false;
+        if ((rc = ensure(h, h->oz_Kq, (size_t)OZ_S * cap * NP, &grew))) return rc;
+        if (grew || h->oz_rows != cap) {
+            if ((rc = make_oz_map(h, &h->mapOzK, h->oz_Kq.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
+            h->oz_rows = cap;
+        }
+        if (h->overlap) {
+            if ((rc = ensure(h, h->oz_Kq2, (size_t)OZ_S * cap * NP, &grew))) return rc;
+            if (grew || h->oz_rows2 != cap) {
+                if ((rc = make_oz_map(h, &h->mapOzK2, h->oz_Kq2.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
+                h->oz_rows2 = cap;
+            }
+        }
+        frexp(h->spec.amp, &oz_eK);
+        oz_eK += 1;
+    }
     if (d_best == nullptr) d_best = ptr<BestPair>(h->best);
     if (d_nneg == nullptr) d_nneg = ptr<unsigned long long>(h->nneg);
     if (reset) {
@@ -733,7 +807,13 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         }
         const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
         const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
-        return launch_cov_tiles(h, st, train_operand(h), NP, h->n, dX + base * h->d, h->d, mc, mcp, lo, up, dst, NP, 0, small);
+        int crc = launch_cov_tiles(h, st, train_operand(h), NP, h->n, dX + base * h->d, h->d, mc, mcp, lo, up, dst, NP, 0, small);
+        if (crc || !use_oz) return crc;
+        // int8 slices of this chunk's K* (rows beyond mc are exact zeros in K*, so are their digits)
+        int8_t* qdst = (pipelined && (ci & 1)) ? ptr<int8_t>(h->oz_Kq2) : ptr<int8_t>(h->oz_Kq);
+        gpk_oz_split_kernel<<<(unsigned)((mcp * NP + 255) / 256), 256, 0, st>>>(dst, mcp, NP, nullptr, oz_eK, qdst, cap * NP);
+        CKL();
+        return GPK_OK;
     };
     if (pipelined) {
         CK(cudaEventRecord(h->ev_order, h->stream));          // side stream starts after all prior work
@@ -771,7 +851,15 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         a.ldpart = cap;
         if (last) CK(cudaEventRecord(h->ev[10], h->stream));
         CK(cudaEventRecord(h->ev_g0[ci], h->stream));
-        if (h->persist && h->loader == LOADER_TMA_WS) {
+        if (use_oz) {
+            OzArgs o;
+            o.nb = h->nb; o.ncb = (int)(mcp / OZ_TN); o.NP = (int)NP; o.rows = (int)cap;
+            o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK; o.z = a.z;
+            o.part_ssq = a.part_ssq; o.part_mu = a.part_mu; o.ldpart = a.ldpart;
+            gpk_oz_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ_SMEM, h->stream>>>(h->mapOzP, second ? h->mapOzK2 : h->mapOzK, o);
+            CKL();
+            h->oz_launches += 1;
+        } else if (h->persist && h->loader == LOADER_TMA_WS) {
             // one CTA per SM, tiles handed out by a counter (zeroed in stream order before every launch)
             if ((rc = ensure(h, h->tile_cnt, 4))) return rc;
             CK(cudaMemsetAsync(h->tile_cnt.p, 0, 4, h->stream));
@@ -868,7 +956,7 @@ int gpk_destroy(gpk_handle* h) {
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
                       &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
-                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt,
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt, &h->oz_Pq, &h->oz_Kq, &h->oz_Kq2, &h->oz_eP, &h->oz_emax,
                       &h->multi_cand, &h->multi_A, &h->multi_B, &h->multi_out, &h->multi_bb, &h->gather, &h->best_global};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -904,6 +992,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->maps_ok = false;
         h->mapKs_rows = 0;
         h->mapVt_rows = 0;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "ozaki")) {
+        if (value != 0 && value != 1) BAD("ozaki must be 0 (fp64 DMMA) or 1 (int8 tensor pipe, error-free split)");
+        h->ozaki = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "persist")) {
@@ -2118,11 +2211,11 @@ int gpk_get_diag_profile(gpk_handle* h, long long* out34) {      // 64 entries
     return GPK_OK;
 }
 
-int gpk_get_timings(gpk_handle* h, double* out) {
+int gpk_get_timings(gpk_handle* h, double* out /* 16 */) {
     if (!h || !out) return GPK_BAD_ARG;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < 10; ++i) out[i] = 0.0;
+    for (int i = 0; i < 16; ++i) out[i] = 0.0;
     float ms = 0.f;
     if (h->fit_timed) {
         if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]) == cudaSuccess) out[0] = ms;
@@ -2146,6 +2239,8 @@ int gpk_get_timings(gpk_handle* h, double* out) {
     cudaGetLastError();
     out[8] = h->launches_var;
     out[9] = h->launches_total;
+    out[10] = h->oz_launches;
+    out[11] = (double)h->oz_emax_host;
     return GPK_OK;
 }
 

@@ -899,3 +899,44 @@ def test_incremental_refit_through_the_model_classes():
     assert_mean_close(mu, mu_r, y[:330])
     assert_var_close(var, var_r, 1.3)
     assert abs(model.gp.log_likelihood(model.y) - ref.gp.log_likelihood(ref.y)) <= 1e-11 * abs(ref.gp.log_likelihood(ref.y))
+
+
+# --------------------------------------------------------------------------- int8 tensor-pipe contraction (option "ozaki")
+def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
+    """Option "ozaki": V = L^-1 K*^T as 36 exact int8 slice products (tcgen05 kind::i8) instead of fp64 DMMA.  Same
+    posterior moments / EI within the north_star tolerances against the oracle AND against the fp64 kernel; the handle
+    must fall back to fp64 when the factor is too ill-conditioned for 8 slices (max |L^-1| >= 64)."""
+    from robo_b200 import _lib
+    N, D, M = 1500, 8, 6000
+    X, y, Xs, theta, noise = O.synthetic_problem(N, D, M, seed_train=3)
+    eta = float(np.min(y))
+    res = {}
+    for oz in (0, 1):
+        h, logdet, ll, diag_add, mean = _handle_for("matern52", theta, X, y, noise)
+        h.set_option("ozaki", oz)
+        res[oz] = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
+        t = h.timings()
+        if oz:
+            assert t["launches_ozaki"] >= 1 and t["ozaki_max_row_exponent"] <= 7, t
+        else:
+            assert t["launches_ozaki"] == 0
+        h.close()
+    st = O.gp_fit(oracle_kernel("matern52", theta, D), X, y, noise=noise, normalize_input=False)
+    mu_ref, var_ref = O.gp_predict_var_only_fast(st, Xs)
+    amp = float(np.exp(theta[0]))
+    for oz in (0, 1):
+        assert_mean_close(res[oz]["mu"], mu_ref, y)
+        assert_var_close(res[oz]["var"], var_ref, amp)
+        assert_acq_close(res[oz]["values"], O.acq_ei(mu_ref, var_ref, eta), rtol=1e-8, atol=1e-13)
+    assert res[0]["best_idx"] == res[1]["best_idx"] == int(np.argmax(O.acq_ei(mu_ref, var_ref, eta)))
+    # ill-conditioned factor (tiny noise, long length scales): row exponents of L^-1 exceed the 8-slice budget -> fp64
+    theta_bad = theta + np.r_[0.0, np.full(D, np.log(4.0))]
+    h, logdet, ll, diag_add, mean = _handle_for("matern52", theta_bad, X, y, 1e-8)
+    h.set_option("ozaki", 1)
+    r = h.acq(Xs[:2000], _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
+    t = h.timings()
+    assert t["ozaki_max_row_exponent"] > 7 and t["launches_ozaki"] == 0, t
+    st = O.gp_fit(oracle_kernel("matern52", theta_bad, D), X, y, noise=1e-8, normalize_input=False)
+    mu_ref, var_ref = O.gp_predict_var_only_fast(st, Xs[:2000])
+    assert_mean_close(r["mu"], mu_ref, y, tol=1e-8)          # cond ~1e11: the fp64 path itself is at its limit here
+    h.close()
