@@ -146,6 +146,43 @@ class DeviceGP(object):
         self._fit_sig = sig
         self.computed = True
 
+    # the same factorisation in two halves (gpk_fit_begin / gpk_fit_end): several DeviceGPs — the n_hypers sub-models of
+    # a GaussianProcessMCMC, gaussian_process_mcmc.py:149-164 — enqueue their fits first and collect afterwards, so the
+    # latency-bound Cholesky chains overlap on the GPU instead of running one after the other
+    def compute_begin(self, x=None, yerr=0.0):
+        if x is not None and (self._x is None or x is not self._x):
+            x = _lib.f64(x)
+            if self._x is None or x.shape != self._x.shape or not np.array_equal(x, self._x):
+                if self._y is None or len(self._y) != len(x):
+                    raise ValueError("DeviceGP.compute_begin: call set_data(X, y) first")
+                self._x = x
+                self._data_dirty = True
+        if self._x is None or self._y is None:
+            raise ValueError("DeviceGP.compute_begin: no training data")
+        h = self.handle
+        f = self.kernel.flatten()
+        self._yerr = float(yerr)
+        yerr_tot = np.sqrt(np.float64(self._yerr) ** 2 + np.exp(self.white_noise))
+        diag_add = float(yerr_tot ** 2)
+        self._pending_sig = (int(f["family"]), float(f["log_amp"]), tuple(int(a) for a in f["axis"]),
+                             tuple(int(g) for g in f["group"]),
+                             tuple(float(v) for v in np.asarray(f["log_metric"]).ravel()), diag_add)
+        self.computed = False
+        self._fit_x = None
+        if self._data_dirty:
+            h.set_data(self._x, self._y)
+            self._data_dirty = False
+        self._push_cfg()
+        h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+        h.fit_begin(diag_add, self.mean)
+
+    def compute_end(self):
+        """Collects compute_begin(); raises numpy.linalg.LinAlgError like compute()."""
+        self.log_determinant, self._ll = self.handle.fit_end()
+        self._fit_x = self._x.copy()
+        self._fit_sig = self._pending_sig
+        self.computed = True
+
     def log_likelihood(self, y=None, quiet=False):
         if y is not None and self._y is not None and y is not self._y and not np.array_equal(y, self._y):
             # different targets: refit with them (the forward solve is part of the factorisation)

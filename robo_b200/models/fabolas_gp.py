@@ -44,6 +44,10 @@ class FabolasGP(GaussianProcess):
         self.original_X = X
         return super(FabolasGP, self).train(self.normalize(X), y, do_optimize)
 
+    def train_begin(self, X, y):
+        self.original_X = X
+        return super(FabolasGP, self).train_begin(self.normalize(X), y)
+
     def predict(self, X_test, full_cov=False, **kwargs):
         return super(FabolasGP, self).predict(self.normalize(X_test), full_cov)
 

@@ -56,6 +56,30 @@ class GaussianProcess(BaseModel):
     @BaseModel._check_shapes_train
     def train(self, X, y, do_optimize=True):
         """gaussian_process.py:70-124."""
+        self._train_prepare(X, y, do_optimize)
+        try:
+            self.gp.compute(self.X, yerr=np.sqrt(self.noise))
+        except np.linalg.LinAlgError:
+            self.noise *= 10
+            self.gp.compute(self.X, yerr=np.sqrt(self.noise))
+        self.is_trained = True
+
+    # train(do_optimize=False) in two halves, for callers that fit many models at once (GaussianProcessMCMC builds
+    # n_hypers sub-models, gaussian_process_mcmc.py:149-164): begin enqueues the factorisation, end collects it
+    def train_begin(self, X, y):
+        BaseModel._check_shapes_train(lambda s, a, b: None)(self, X, y)
+        self._train_prepare(X, y, False)
+        self.gp.compute_begin(self.X, yerr=np.sqrt(self.noise))
+
+    def train_end(self):
+        try:
+            self.gp.compute_end()
+        except np.linalg.LinAlgError:                      # :120-122: once more with ten times the noise
+            self.noise *= 10
+            self.gp.compute(self.X, yerr=np.sqrt(self.noise))
+        self.is_trained = True
+
+    def _train_prepare(self, X, y, do_optimize):
         if self.normalize_input:
             self.X, self.lower, self.upper = normalization.zero_one_normalization(X, self.lower, self.upper)
         else:
@@ -94,14 +118,6 @@ class GaussianProcess(BaseModel):
             self.hypers = np.append(self.hypers, np.log(self.noise))
 
         logger.debug("GP Hyperparameters: " + str(self.hypers))
-
-        try:
-            self.gp.compute(self.X, yerr=np.sqrt(self.noise))
-        except np.linalg.LinAlgError:
-            self.noise *= 10
-            self.gp.compute(self.X, yerr=np.sqrt(self.noise))
-
-        self.is_trained = True
 
     def get_noise(self):
         return self.noise

@@ -144,9 +144,13 @@ class GaussianProcessMCMC(BaseModel):
             kernel = deepcopy(self.kernel)
             kernel.set_parameter_vector(sample[:-1])
             noise = np.exp(sample[-1])
-            model = self._new_sub_model(kernel, noise)
-            model.train(X, y, do_optimize=False)
-            self.models.append(model)
+            self.models.append(self._new_sub_model(kernel, noise))
+        # all n_hypers factorisations are enqueued (one handle / stream per sub-model) before the first is collected:
+        # the latency-bound Cholesky chains overlap on the GPU (gaussian_process_mcmc.py:163 trains them one by one)
+        for model in self.models:
+            model.train_begin(X, y)
+        for model in self.models:
+            model.train_end()
         self.is_trained = True
 
     # hooks for FabolasGPMCMC (robo/models/fabolas_gp.py), which differs only in how inputs are prepared
