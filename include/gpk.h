@@ -65,6 +65,9 @@ const char* gpk_version(void);
  *   "chunk"     candidates per scoring pass (multiple of 128); 0 = automatic [default]: the K* buffer is kept near
  *               512 MB (16384 candidates at N = 4096, 65536 at N <= 1024)
  *   "cov"       covariance builder: 2 = TMA-staged, pre-scaled term-major operands [default], 1 = round-1 kernel
+ *   "graph"     1 = the split-chain schedule of a factorisation (~600 launches / event records / stream waits at
+ *               N = 4096) is captured once per layout into a CUDA graph and replayed per fit [default]; 0 = enqueue
+ *               every call directly
  *   "ozaki"     1 = variance contraction on the int8 tensor pipe (tcgen05 kind::i8, TMEM accumulators) through an
  *               error-free 8 x 8 slice split of L^-1 and K* (gpk_ozaki.cuh); used while max |L^-1| < 64, otherwise the
  *               fp64 kernel runs; 0 = always fp64 DMMA [default]

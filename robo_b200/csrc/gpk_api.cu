@@ -59,6 +59,9 @@ struct gpk_handle {
     int persist = 1;                // 1: persistent variance contraction (gpk_vargemm_persistent_kernel) [default]
     DevBuf tile_cnt;
     int n_sm = 0;
+    int use_graph = 1;              // split chain: one CUDA graph per layout, replayed per fit
+    cudaGraphExec_t fit_graph = nullptr;
+    double fit_graph_launches = 0;
     int chainsplit = 1;             // 1: diag(k+1) waits only for block row k+1 of step k (gpk_chain_step_kernel on 4 CTAs)
     int lookahead = 1;
     int smalltile = 1;              // 32-row tiles for the panel solve / next-panel update
@@ -910,6 +913,10 @@ extern "C" {
 
 int gpk_comm_destroy(gpk_handle* h);
 
+static void drop_fit_graph(gpk_handle* h) {
+    if (h->fit_graph) { cudaGraphExecDestroy(h->fit_graph); h->fit_graph = nullptr; }
+}
+
 const char* gpk_version(void) { return "gpk 0.2 (sm_100a, fp64 DMMA + TMA)"; }
 
 const char* gpk_last_error(gpk_handle* h) { return h ? h->err : "null handle"; }
@@ -951,6 +958,7 @@ int gpk_destroy(gpk_handle* h) {
     if (!h) return GPK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    drop_fit_graph(h);
     gpk_comm_destroy(h);
     if (h->ev_multi) cudaEventDestroy(h->ev_multi);
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
@@ -985,6 +993,12 @@ int gpk_destroy(gpk_handle* h) {
 
 int gpk_set_option(gpk_handle* h, const char* key, long value) {
     if (!h || !key) return GPK_BAD_ARG;
+    drop_fit_graph(h);                       // every switch may change what a factorisation launches
+    if (!strcmp(key, "graph")) {
+        if (value != 0 && value != 1) BAD("graph must be 0 or 1");
+        h->use_graph = (int)value;
+        return GPK_OK;
+    }
     if (!strcmp(key, "loader")) {
         if (value < LOADER_CPASYNC || value > LOADER_TMA_WS) BAD("loader must be 0 (cp.async), 1 (TMA) or 2 (TMA, warp-specialised)");
         if (value != LOADER_CPASYNC && get_encode_fn() == nullptr) BAD("TMA descriptors unavailable on this driver");
@@ -1103,6 +1117,7 @@ int gpk_set_data(gpk_handle* h, const double* X, const double* y, int n, int d) 
     if ((rc = ensure(h, h->logdet_part, (size_t)(NP / BM) * 8))) return rc;
     const bool relayout = (h->layout_NP != NP) || g1 || g2 || g3 || g4;
     h->n = n; h->d = d; h->NP = (int)NP; h->nb = (int)(NP / BM);
+    if (relayout || h->jobs_nb != (int)(NP / BM)) drop_fit_graph(h);       // the graph holds buffer / job-table addresses
     if (relayout) {
         CK(cudaMemsetAsync(h->Kbuf.p, 0, (size_t)(NP + BM) * NP * 8, h->stream));
         CK(cudaMemsetAsync(h->P.p, 0, (size_t)NP * NP * 8, h->stream));
@@ -1242,8 +1257,7 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
                        h->loader != LOADER_CPASYNC && nb >= 3;
     if (split) {
         if ((rc = ensure(h, h->chain_cnt, (size_t)nb * 4))) return rc;
-        CK(cudaMemsetAsync(h->chain_cnt.p, 0, (size_t)nb * 4, h->stream));
-        while ((int)h->ev_cs.size() < 5 * nb) {
+        while ((int)h->ev_cs.size() < 5 * nb + 3) {
             cudaEvent_t e;
             CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             h->ev_cs.push_back(e);
@@ -1253,11 +1267,16 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
         auto evT = [&](int k) { return h->ev_cs[5 * k + 2]; };
         auto evPU = [&](int k) { return h->ev_cs[5 * k + 3]; };
         auto evRA = [&](int k) { return h->ev_cs[5 * k + 4]; };
-        std::vector<char> haveX(nb, 0), havePU(nb, 0), haveRA(nb, 0);
         cudaStream_t C = h->stream, Pst = h->panel_stream, R = h->side_stream;
-        CK(cudaEventRecord(h->ev_order, C));                       // K is built: the other streams may start
-        CK(cudaStreamWaitEvent(Pst, h->ev_order, 0));
-        CK(cudaStreamWaitEvent(R, h->ev_order, 0));
+        cudaEvent_t evFork = h->ev_cs[5 * nb], evJoinP = h->ev_cs[5 * nb + 1], evJoinR = h->ev_cs[5 * nb + 2];
+        // the whole schedule of one factorisation (about 6 launches, 5 event records and 7 stream waits per step);
+        // depends on the buffers and job tables only, so it is captured ONCE into a CUDA graph and replayed per fit
+        auto enqueue = [&]() -> int {
+        std::vector<char> haveX(nb, 0), havePU(nb, 0), haveRA(nb, 0);
+        CK(cudaMemsetAsync(h->chain_cnt.p, 0, (size_t)nb * 4, C));
+        CK(cudaEventRecord(evFork, C));                            // K is built: the other streams may start
+        CK(cudaStreamWaitEvent(Pst, evFork, 0));
+        CK(cudaStreamWaitEvent(R, evFork, 0));
         gpk_diag_prezero_kernel<<<nb, 256, 0, C>>>(K, (long)NP, ptr<double>(h->P), (long)NP);
         CKL();
         for (int k = 0; k < nb; ++k) {
@@ -1333,12 +1352,44 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
             }
         }
         // join: everything the factor consists of is complete once P and R have drained
-        CK(cudaEventRecord(h->ev_order, Pst));
-        CK(cudaStreamWaitEvent(C, h->ev_order, 0));
-        CK(cudaEventRecord(h->ev_panel[0], R));
-        CK(cudaStreamWaitEvent(C, h->ev_panel[0], 0));
+        CK(cudaEventRecord(evJoinP, Pst));
+        CK(cudaStreamWaitEvent(C, evJoinP, 0));
+        CK(cudaEventRecord(evJoinR, R));
+        CK(cudaStreamWaitEvent(C, evJoinR, 0));
         gpk_diag_qfill_kernel<<<nb, 256, 0, C>>>(ptr<double>(h->P), ptr<double>(h->Q), (long)NP, ptr<int>(h->status));
         CKL();
+        return GPK_OK;
+        };
+        const bool want_graph = h->use_graph && !h->diag_prof;
+        if (want_graph && h->fit_graph == nullptr) {
+            // capture (thread-local mode: other threads' CUDA calls are unaffected); P and R join the capture through
+            // evFork and are joined back before the end.  A failed capture falls back to direct enqueueing.
+            const double launches_before = h->launches_total;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(C, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int erc = enqueue();
+                const cudaError_t ce = cudaStreamEndCapture(C, &graph);
+                if (erc == GPK_OK && ce == cudaSuccess && graph != nullptr &&
+                    cudaGraphInstantiate(&h->fit_graph, graph, 0) == cudaSuccess) {
+                    h->fit_graph_launches = h->launches_total - launches_before;
+                } else {
+                    h->fit_graph = nullptr;
+                    h->use_graph = 0;                               // do not try again on this handle
+                }
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                h->launches_total = launches_before;
+            } else {
+                cudaGetLastError();
+                h->use_graph = 0;
+            }
+        }
+        if (want_graph && h->fit_graph != nullptr) {
+            CK(cudaGraphLaunch(h->fit_graph, C));
+            h->launches_total += h->fit_graph_launches;
+        } else if ((rc = enqueue())) {
+            return rc;
+        }
     }
     if (!split && h->diag_kernel >= 3) {
         gpk_diag_prezero_kernel<<<nb, 256, 0, h->stream>>>(K, (long)NP, ptr<double>(h->P), (long)NP);

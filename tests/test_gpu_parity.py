@@ -161,9 +161,10 @@ def test_split_chain_schedule_is_bit_identical(N):
     D = 6
     X, y, _, theta, noise = O.synthetic_problem(N, D, 1, seed_train=5)
     got = []
-    for split in (1, 0):
+    for split, graph in ((1, 1), (0, 1), (1, 0)):
         h = _lib.Handle(0)
         h.set_option("chainsplit", split)
+        h.set_option("graph", graph)                        # CUDA-graph replay of the schedule vs direct enqueueing
         h.set_data(X, y)
         f = product_kernel("matern52", theta, D).flatten()
         h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
@@ -172,9 +173,10 @@ def test_split_chain_schedule_is_bit_identical(N):
         n_chk = min(N, 1024)
         got.append((logdet, ll, h.get_z(N), h.get_factor(N)[-n_chk:], h.get_linv(N)[-n_chk:]))
         h.close()
-    assert got[0][0] == got[1][0] and got[0][1] == got[1][1]
-    for a, b in zip(got[0][2:], got[1][2:]):
-        np.testing.assert_array_equal(a, b)
+    for other in got[1:]:
+        assert got[0][0] == other[0] and got[0][1] == other[1]
+        for a, b in zip(got[0][2:], other[2:]):
+            np.testing.assert_array_equal(a, b)
 
 
 def test_not_positive_definite_is_linalgerror():

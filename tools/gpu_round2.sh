@@ -15,7 +15,7 @@ run_tests() {  # tag, extra env...
 }
 if ! run_tests default; then
   # which switch? (the exact-config file is skipped in the reruns: minutes of CPU oracle each time)
-  for sw in "GPK_COV=1" "GPK_PERSIST=0" "GPK_CHAINSPLIT=0" "GPK_COV=1 GPK_PERSIST=0 GPK_CHAINSPLIT=0"; do
+  for sw in "GPK_COV=1" "GPK_PERSIST=0" "GPK_CHAINSPLIT=0" "GPK_GRAPH=0" "GPK_COV=1 GPK_PERSIST=0 GPK_CHAINSPLIT=0"; do
     tag=$(echo $sw | tr ' =' '__')
     env $sw timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider --timeout 600 > $out/r2_pytest_$tag.log 2>&1
     echo "pytest[$sw] exit $?" >> $out/r2_pytest_$tag.log
