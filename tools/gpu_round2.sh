@@ -43,3 +43,5 @@ timeout 600 python tools/fit_compare.py > $out/r2_fit_compare.jsonl 2> $out/r2_f
 # Ozaki prototype: fp64 variance contraction on the int8 tensor pipe (accuracy vs an 80-bit CPU reference + C2-chunk timing)
 (cd tools/microbench && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o ozaki_probe.bin ozaki_probe.cu -lcuda \
    && timeout 300 ./ozaki_probe.bin) > $out/r2_ozaki_probe.json 2> $out/r2_ozaki_probe.err; cat $out/r2_ozaki_probe.json; tail -3 $out/r2_ozaki_probe.err
+# the other BASELINE configs (C3 host-fed on one GPU, C4 likelihood pool + fused marginalised EI, C5 nll + gradient)
+timeout 900 python tools/run_configs.py > $out/r2_configs_c3_c4_c5.jsonl 2> $out/r2_configs.err; cat $out/r2_configs_c3_c4_c5.jsonl; tail -3 $out/r2_configs.err

@@ -111,7 +111,38 @@ def c4():
     assert np.allclose(a, b, rtol=1e-12, equal_nan=True)
     sweep = np.tile(thetas, (10, 1))            # 200 likelihood evaluations = 10 emcee steps of 20 walkers
     t0 = time.perf_counter(); conc(sweep); t_sweep = time.perf_counter() - t0
+    # (c) marginalised EI over the 20 sub-models at M = 500 (marginalization.py:115-121): ONE fused multi-model call
+    # against the reference's loop over estimators (per-model compute, values through the host)
+    from robo_b200.acquisition_functions import EI, MarginalizationGPMCMC
+    from robo_b200.models import GaussianProcessMCMC
+    from robo_b200.models.gaussian_process import GaussianProcess
+    model = GaussianProcessMCMC(kern, n_hypers=n_theta, chain_length=1, burnin_steps=1, normalize_input=False)
+    model.X, model.y, model.hypers, model.models = X, y, thetas, []
+    t0 = time.perf_counter()
+    for th in thetas:
+        k2 = K.ConstantKernel(th[0], ndim=D)
+        for d in range(D):
+            k2 = K.Product(k2, K.Matern52Kernel(np.exp(th[1 + d:2 + d]), ndim=D, axes=d))
+        model.models.append(GaussianProcess(k2, noise=float(np.exp(th[-1])), normalize_input=False, rng=np.random.RandomState(0)))
+    for m in model.models:
+        m.train_begin(X, y)
+    for m in model.models:
+        m.train_end()
+    t_sub = time.perf_counter() - t0
+    model.is_trained = True
+    acq = MarginalizationGPMCMC(EI(model))
+    Xc = np.random.RandomState(3).rand(500, D)
+    acq.compute(Xc)                                   # builds the L^-1 of every sub-model
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter(); a = acq.compute(Xc); ts.append(time.perf_counter() - t0)
+    tl = []
+    for _ in range(3):
+        t0 = time.perf_counter(); b = np.mean([e.compute(Xc) for e in acq.estimators], axis=0); tl.append(time.perf_counter() - t0)
+    assert np.allclose(a, b, rtol=1e-12, atol=1e-300)
     return {"config": "C4 GP-MCMC likelihoods, N=2048, 3 cols, prod-of-1D Matern52, 20 thetas",
+            "submodels20_train_concurrent_ms": 1e3 * t_sub,
+            "marginalised_ei_20x500_fused_ms": 1e3 * min(ts), "marginalised_ei_20x500_loop_ms": 1e3 * min(tl),
             "fits20_sequential_ms": 1e3 * t_seq, "fits20_concurrent10_ms": 1e3 * t_conc,
             "per_fit_sequential_ms": 1e3 * t_seq / n_theta, "per_fit_concurrent_ms": 1e3 * t_conc / n_theta,
             "sweep200_concurrent_ms": 1e3 * t_sweep, "projected_4000_factorisations_s": t_sweep * 20}
