@@ -20,9 +20,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import robo_oracle as O   # noqa: E402  (study tool, not product code)
 
 
-def split(A, S, axis):
-    """A ~ sum_s Q_s * 2^(e - 7 (s+1)) with integer |Q_s| <= 127; e = per-row (axis=1) or per-column (axis=0) exponent."""
-    mx = np.max(np.abs(A), axis=axis, keepdims=True)
+def split(A, S, axis, global_max=None):
+    """A ~ sum_s Q_s * 2^(e - 7 (s+1)) with integer |Q_s| <= 127; e = per-row (axis=1) or per-column (axis=0) exponent,
+    or ONE exponent from global_max (what the kernel does for K*: 0 < k <= amp)."""
+    mx = np.max(np.abs(A), axis=axis, keepdims=True) if global_max is None else np.full((1, 1), float(global_max))
     e = np.where(mx > 0, np.ceil(np.log2(np.where(mx > 0, mx, 1.0))) + 1, 0.0)        # |A| / 2^e < 1/2
     r = A / np.exp2(e)
     Q = []
@@ -34,10 +35,10 @@ def split(A, S, axis):
     return Q, e
 
 
-def ozaki_matmul(P, Kt, S):
+def ozaki_matmul(P, Kt, S, amp=None):
     """P (n x k) @ Kt (k x m) from S x S slices, pairs with s + t <= S - 1 (0-based)."""
     QP, eP = split(P, S, axis=1)
-    QK, eK = split(Kt, S, axis=0)
+    QK, eK = split(Kt, S, axis=0, global_max=amp)
     out = np.zeros((P.shape[0], Kt.shape[1]))
     pairs = 0
     for lvl in range(S - 1, -1, -1):                  # least significant level first, then upwards
@@ -77,7 +78,7 @@ def main():
               % (label, N, M, np.linalg.cond(K), np.abs(P).max(), var_ref.min(), var_ref.max()))
         print("   fp64 (DMMA-equivalent) path: scaled variance error %.2e" % err64)
         for S in range(6, 13):
-            V, pairs = ozaki_matmul(P, Ks.T, S)
+            V, pairs = ozaki_matmul(P, Ks.T, S, amp)
             err = np.max(np.abs((amp - np.einsum("ij,ij->j", V, V)) - var_ref) / den)
             print("   S = %2d slices/operand: %3d int8 GEMMs per fp64 GEMM, scaled variance error %.2e  %s"
                   % (S, pairs, err, "<= 1e-10" if err <= 1e-10 else ""))
