@@ -62,7 +62,7 @@ struct gpk_handle {
     int use_graph = 1;              // split chain: one CUDA graph per layout, replayed per fit
     cudaGraphExec_t fit_graph = nullptr;
     double fit_graph_launches = 0;
-    int chainsplit = 1;             // 1: diag(k+1) waits only for block row k+1 of step k (gpk_chain_step_kernel on 4 CTAs)
+    int chainsplit = 0;             // 1: diag(k+1) waits only for block row k+1 of step k (gpk_chain_step_kernel on 4 CTAs)
     int lookahead = 1;
     int smalltile = 1;              // 32-row tiles for the panel solve / next-panel update
     int pdl = 1;                    // programmatic dependent launch on the Cholesky chain

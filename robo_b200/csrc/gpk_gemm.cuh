@@ -579,10 +579,11 @@ gpk_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 // ring stays full while the consumers reduce and store a finished tile: no pipeline fill / drain per tile (a 128-long
 // contraction is only 8 k-steps), no launch tail per wave, and the load balance is dynamic.  Same fragment layout,
 // accumulation order and column-reduction order as gpk_gemm_ws_kernel<EPI_COLREDUCE>: bit-identical partial sums.
-//   smem: PV_STAGES x 32 KB operand ring | full / empty mbarriers | 2 tile slots | 2 x (2 x 128) reduction scratch
+//   smem: PV_STAGES x 32 KB operand ring | full / empty mbarriers | 2 tile slots | 2 x (4 x 128) reduction scratch
 // ---------------------------------------------------------------------------------------
 constexpr int PV_STAGES = 6;
-constexpr int PV_SMEM = PV_STAGES * STAGE_BYTES_TMA + 1024 /*align*/ + 128 /*barriers + tile slots*/ + 4096 /*reduce*/;
+constexpr int PV_RED_BYTES = 4 * 128 * 8;          // {ssq, mu} x {wm = 0, 1} x 128 columns, per tile parity
+constexpr int PV_SMEM = PV_STAGES * STAGE_BYTES_TMA + 1024 /*align*/ + 128 /*barriers + tile slots*/ + 2 * PV_RED_BYTES;
 
 struct VarArgs {
     int nb, mcb;                       // row blocks of L^-1 x candidate blocks of the chunk
@@ -615,7 +616,7 @@ gpk_vargemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __
     const uint32_t full_bar = smem + RING;                       // PV_STAGES x 8 bytes
     const uint32_t empty_bar = smem + RING + 48;                 // PV_STAGES x 8 bytes
     const uint32_t slot = smem + RING + 96;                      // 2 x int: tile id of tile parity 0 / 1
-    const uint32_t red0 = smem + RING + 128;                     // 2 x (2 x 128 doubles)
+    const uint32_t red0 = smem + RING + 128;                     // 2 tile parities x (4 x 128 doubles)
     const int total = g.nb * g.mcb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -706,7 +707,7 @@ gpk_vargemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __
             if (++s == PV_STAGES) { s = 0; ++use; }
         }
         // ---- epilogue: column reductions over the tile's 128 rows (same order as gpk_gemm_ws_kernel<EPI_COLREDUCE>)
-        const uint32_t red = red0 + (uint32_t)(t & 1) * 2048u;
+        const uint32_t red = red0 + (uint32_t)(t & 1) * (uint32_t)PV_RED_BYTES;
         const int c_row = ib * BM, c_col = cb * BN;
         double zr[MI];
 #pragma unroll
