@@ -53,6 +53,23 @@ __device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 :: "r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 // K-major SWIZZLE_64B matrix descriptor: atoms of 8 rows x 64 bytes (512 B), stride byte offset 512, version 1, layout 4
 __device__ __forceinline__ uint64_t umma_desc64(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -126,6 +143,11 @@ struct OzArgs {
     double* part_ssq; double* part_mu;  // [nb][Mc]
 };
 
+// CL > 1: CL CTAs of a cluster work on the same row block and CL neighbouring candidate blocks; every CTA loads
+// S / CL of the L^-1 slice tiles of a k-block and multicasts them to the whole cluster (its K* slices stay private),
+// so the L^-1 traffic per CTA drops by CL.  A stage may be refilled once ALL CTAs of the cluster have consumed it:
+// the MMA issuers commit to the empty barrier of every CTA (count CL).
+template <int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapK, const OzArgs g)
 {
@@ -135,11 +157,14 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     const uint32_t tmem_slot = bar_tmem + 8;
     const uint32_t red = base + NSTG * STAGE + 256;                  // [4 warps][64 cols][2] doubles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ib = g.nb - 1 - (int)blockIdx.x / g.ncb, cb = (int)blockIdx.x % g.ncb;
+    const int crank = CL > 1 ? (int)cluster_rank() : 0;
+    const int cid = (int)blockIdx.x / CL, cpr = g.ncb / CL;          // cluster id, clusters per row block
+    const int ib = g.nb - 1 - cid / cpr, cb = (cid % cpr) * CL + crank;
     const int nkb = (ib + 1) * TM / KBY;                             // lower triangle: columns < (ib + 1) * 128
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1);
 
     if (tid == 0) {
-        for (int s = 0; s < NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
         mbar_init(bar_tmem, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -150,6 +175,7 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                  // every CTA's barriers exist before anyone signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
@@ -163,7 +189,8 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                 mbar_expect_tx(bar_full + 8 * s, STAGE);
 #pragma unroll
                 for (int q = 0; q < S; ++q) {
-                    tma_2d(st + q * A_SLICE, &mapP, kb * KBY, q * g.N + ib * TM, bar_full + 8 * s);
+                    if (CL == 1) tma_2d(st + q * A_SLICE, &mapP, kb * KBY, q * g.N + ib * TM, bar_full + 8 * s);
+                    else if (q % CL == crank) tma_2d_mc(st + q * A_SLICE, &mapP, kb * KBY, q * g.N + ib * TM, bar_full + 8 * s, cmask);
                     tma_2d(st + S * A_SLICE + q * B_SLICE, &mapK, kb * KBY, q * g.Mc + cb * TN, bar_full + 8 * s);
                 }
             }
@@ -187,7 +214,8 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                                     umma_desc64(st + S * A_SLICE + b * B_SLICE + k * UMMA_K), idesc,
                                     (uint32_t)((kb | a | k) != 0));
                     }
-                umma_commit(bar_empty + 8 * s);                      // frees the stage when these MMAs have read it
+                if (CL == 1) umma_commit(bar_empty + 8 * s);         // frees the stage when these MMAs have read it
+                else umma_commit_mc(bar_empty + 8 * s, cmask);       // ... in every CTA of the cluster
             }
             umma_commit(bar_tmem);                                   // all accumulators final
         }
@@ -249,6 +277,7 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                  // no CTA leaves while peers may still signal / write it
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
 }
@@ -337,7 +366,20 @@ static Problem synthetic_problem(int N, int M) {               // timing only: l
 
 struct Result { std::vector<double> ssq, mu; float ms_split_k, ms_gemm; };
 
-static Result run_gpu(const Problem& pr, int reps) {
+template <int CL>
+static void launch_oz(int grid, const CUtensorMap& mapP, const CUtensorMap& mapK, const OzArgs& a) {
+    CKC(cudaFuncSetAttribute(oz_vargemm_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = OZ_SMEM; cfg.stream = 0;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CKC(cudaLaunchKernelEx(&cfg, oz_vargemm_kernel<CL>, mapP, mapK, a));
+}
+
+static Result run_gpu(const Problem& pr, int reps, int cl = 1) {
     const int N = pr.N, M = pr.M, nb = N / TM, ncb = M / TN;
     double *dP, *dK, *dz, *dpss, *dpmu, *dssq, *dmu;
     int8_t *dPq, *dKq;
@@ -358,7 +400,6 @@ static Result run_gpu(const Problem& pr, int reps) {
     CUtensorMap mapP, mapK;
     make_map(&mapP, dPq, (long)S * N, N, TM);
     make_map(&mapK, dKq, (long)S * M, N, TN);
-    CKC(cudaFuncSetAttribute(oz_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
     OzArgs a; a.nb = nb; a.ncb = ncb; a.N = N; a.Mc = M; a.eP = deP; a.eK = deK; a.z = dz; a.part_ssq = dpss; a.part_mu = dpmu;
     cudaEvent_t e0, e1, e2;
     CKC(cudaEventCreate(&e0)); CKC(cudaEventCreate(&e1)); CKC(cudaEventCreate(&e2));
@@ -367,7 +408,9 @@ static Result run_gpu(const Problem& pr, int reps) {
         CKC(cudaEventRecord(e0));
         oz_split_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(dK, M, N, deK, 1, dKq);
         CKC(cudaEventRecord(e1));
-        oz_vargemm_kernel<<<nb * ncb, OZ_THREADS, OZ_SMEM>>>(mapP, mapK, a);
+        if (cl == 1) launch_oz<1>(nb * ncb, mapP, mapK, a);
+        else if (cl == 2) launch_oz<2>(nb * ncb, mapP, mapK, a);
+        else launch_oz<4>(nb * ncb, mapP, mapK, a);
         oz_finish_kernel<<<(M + 255) / 256, 256>>>(dpss, dpmu, nb, M, dssq, dmu);
         CKC(cudaEventRecord(e2));
         CKC(cudaGetLastError());
@@ -391,7 +434,10 @@ int main() {
     g_encode = (EncodeFn)p;
     // ---- accuracy on real GP data (N = 1024, D = 16, 256 candidates) against an 80-bit CPU contraction
     Problem pr = gp_problem(1024, 256, 16);
-    Result r = run_gpu(pr, 1);
+    Result r = run_gpu(pr, 1, 1), r2 = run_gpu(pr, 1, 2), r4 = run_gpu(pr, 1, 4);
+    double cl_diff = 0;
+    for (int c = 0; c < pr.M; ++c)
+        cl_diff = std::max(cl_diff, std::max(std::fabs(r.ssq[c] - r2.ssq[c]), std::fabs(r.ssq[c] - r4.ssq[c])) + std::max(std::fabs(r.mu[c] - r2.mu[c]), std::fabs(r.mu[c] - r4.mu[c])));
     double worst_var = 0, worst_mu = 0, var_min = 1e300;
     for (int c = 0; c < pr.M; ++c) {
         long double ssq = 0, mu = 0;
@@ -407,12 +453,12 @@ int main() {
     }
     // ---- timing on the C2 shape
     Problem big = synthetic_problem(4096, 16384);
-    Result t = run_gpu(big, 4);
+    Result t = run_gpu(big, 4, 1), t2 = run_gpu(big, 4, 2), t4 = run_gpu(big, 4, 4);
     const double flops = 16384.0 * (4096.0 * 4096.0 + 2 * 4096.0);
     printf("{\"probe\": \"Ozaki int8 variance contraction, S=%d slices, tile %dx%d\", \"scaled_var_err_vs_80bit\": %.3e, "
            "\"mu_err\": %.3e, \"var_min\": %.3e, \"c2_chunk_ms_gemm\": %.4f, \"c2_chunk_ms_split_kstar\": %.4f, "
-           "\"fp64_equiv_tflops_gemm\": %.2f, \"fp64_equiv_tflops_incl_split\": %.2f, \"dmma_reference_tflops\": 35.2}\n",
+           "\"fp64_equiv_tflops_gemm\": %.2f, \"fp64_equiv_tflops_incl_split\": %.2f, \"dmma_reference_tflops\": 35.2, \"cluster2_ms_gemm\": %.4f, \"cluster4_ms_gemm\": %.4f, \"cluster_vs_plain_max_abs_diff\": %.3e}\n",
            S, TM, TN, worst_var, worst_mu, var_min, t.ms_gemm, t.ms_split_k, flops / (t.ms_gemm * 1e-3) / 1e12,
-           flops / ((t.ms_gemm + t.ms_split_k) * 1e-3) / 1e12);
+           flops / ((t.ms_gemm + t.ms_split_k) * 1e-3) / 1e12, t2.ms_gemm, t4.ms_gemm, cl_diff);
     return 0;
 }
