@@ -72,9 +72,12 @@ const char* gpk_version(void);
  *               error-free 8 x 8 slice split of L^-1 and K* (gpk_ozaki.cuh); used while max |L^-1| < 64, otherwise the
  *               fp64 kernel runs; 0 = always fp64 DMMA [default]
  *   "persist"   1 = persistent fp64 variance contraction (one CTA per SM, dynamic tile counter) [default]
- *   "chainsplit" 1 = split Cholesky chain [default]: diag(k+1) waits only for block row k+1 of step k (one launch on
+ *   "depth2"    1 = trailing updates of two consecutive panels in one K = 256 contraction (odd steps; even steps update
+ *               only the next-but-one block column) [default]; 0 = one K = 128 update per step (bit-identical factor)
+ *   "chainsplit" 1 = split Cholesky chain: diag(k+1) waits only for block row k+1 of step k (one launch on
  *               four 32-row tiles), the rows below run on a second high-priority stream, trailing update with
- *               look-ahead 2; 0 = plain look-ahead schedule (bit-identical factor)
+ *               look-ahead 2 (measured neutral against the plain schedule: profiles/r02_fit_compare_*.jsonl);
+ *               0 = plain look-ahead schedule [default] (bit-identical factor)
  *   "diag"      diagonal-block Cholesky + inverse kernel: 4 = 16-column panels, square-root-free pivot chain in one warp,
  *               substitutions in four, rank-16 updates on the fp64 tensor pipe [default]; 3 = the same with DFMA register
  *               tiles; 2 = column-by-column register-tiled kernel; 0 = simple shared-memory version (cross-checks)

@@ -155,16 +155,18 @@ def test_cholesky_variants_agree():
 
 @pytest.mark.parametrize("N", [384, 1500, 4096])
 def test_split_chain_schedule_is_bit_identical(N):
-    """the split chain (diag(k+1) waits only for block row k+1; trailing update with look-ahead 2) applies the panels
-    to every tile in the same order as the plain look-ahead schedule: identical bits in the factor, z and log-det"""
+    """the split chain (diag(k+1) waits only for block row k+1; trailing update with look-ahead 2) and the depth-2
+    trailing update (two panels per K = 256 contraction) apply the panels to every tile in the same order as the plain
+    look-ahead schedule: identical bits in the factor, z and log-det"""
     from robo_b200 import _lib
     D = 6
     X, y, _, theta, noise = O.synthetic_problem(N, D, 1, seed_train=5)
     got = []
-    for split, graph in ((1, 1), (0, 1), (1, 0)):
+    for split, graph, depth2 in ((1, 1, 1), (0, 1, 1), (1, 0, 1), (0, 1, 0)):
         h = _lib.Handle(0)
         h.set_option("chainsplit", split)
         h.set_option("graph", graph)                        # CUDA-graph replay of the schedule vs direct enqueueing
+        h.set_option("depth2", depth2)                      # K = 256 trailing updates vs one K = 128 update per step
         h.set_data(X, y)
         f = product_kernel("matern52", theta, D).flatten()
         h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])

@@ -15,7 +15,7 @@ from robo_b200 import _lib                                   # noqa: E402
 from robo_b200 import kernels as K                           # noqa: E402
 
 
-def ours(N, D, split, reps=6, graph=1):
+def ours(N, D, split, reps=6, graph=1, depth2=1):
     rng = np.random.RandomState(1234)
     X = rng.rand(N, D)
     y = np.sinc(X * 10 - 5).sum(axis=1) + 0.01 * rng.randn(N)
@@ -23,6 +23,7 @@ def ours(N, D, split, reps=6, graph=1):
     h = _lib.Handle(0)
     h.set_option("chainsplit", split)
     h.set_option("graph", graph)
+    h.set_option("depth2", depth2)
     h.set_data(X, y)
     f = K.Product(K.ConstantKernel(theta[0], ndim=D), K.Matern52Kernel(np.exp(theta[1:]), ndim=D)).flatten()
     h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
@@ -60,6 +61,7 @@ for N, D in ((1024, 8), (2048, 3), (4096, 16), (8192, 32)):
     a = ours(N, D, 1)
     a0 = ours(N, D, 1, graph=0)
     b = ours(N, D, 0)
+    b0 = ours(N, D, 0, depth2=0)
     c = cusolver(N)
     flop = N ** 3 / 3.0
     print(json.dumps({"N": N, "D": D,
@@ -68,5 +70,6 @@ for N, D in ((1024, 8), (2048, 3), (4096, 16), (8192, 32)):
                       "split_chain_direct_enqueue": {"fit_ms": a0[0], "potrf_incl_forward_solve_logdet_ms": a0[2]},
                       "plain_lookahead": {"fit_ms": b[0], "kbuild_ms": b[1], "potrf_incl_forward_solve_logdet_ms": b[2],
                                           "potrf_tflops": flop / (b[2] * 1e-3) / 1e12},
+                      "plain_lookahead_depth1": {"fit_ms": b0[0], "potrf_incl_forward_solve_logdet_ms": b0[2]},
                       "cusolver_torch_linalg_cholesky": {"potrf_ms": c[0], "forward_solve_ms": c[1],
                                                          "potrf_tflops": flop / (c[0] * 1e-3) / 1e12}}))
