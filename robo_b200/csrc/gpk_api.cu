@@ -49,7 +49,7 @@ struct gpk_handle {
     std::vector<cudaEvent_t> ev_cs;         // split chain: 5 events per step (diag, X, trsm', pu', rest_a)
     // variance contraction on the int8 tensor pipe (gpk_ozaki.cuh); 0 = fp64 DMMA kernels
     int ozaki = 0;
-    DevBuf oz_Pq, oz_Kq, oz_Kq2, oz_eP, oz_emax;
+    DevBuf oz_Pq, oz_Kq, oz_Kq2, oz_eP, oz_emax, oz_mu, oz_mu2;
     long oz_linv_serial = -1;       // linv_serial the slices of L^-1 were made for
     long linv_serial = 0;           // bumped whenever L^-1 is (re)built
     int oz_emax_host = 0;
@@ -724,6 +724,11 @@ int prepare_ozaki(gpk_handle* h, bool* usable) {
         gpk_oz_split_kernel<<<(unsigned)((NP * NP + 255) / 256), 256, 0, h->stream>>>(ptr<double>(h->P), NP, NP, ptr<int>(h->oz_eP), 0,
                                                                                    ptr<int8_t>(h->oz_Pq), NP * NP);
         CKL();
+        // alpha = L^-T z (Q = L^-T is upper triangular): the mean goes through fp64, mu - mean = K* alpha
+        if ((rc = ensure(h, h->alpha, (size_t)NP * 8))) return rc;
+        gpk_rowdot_kernel<<<(unsigned)((NP + 7) / 8), 256, 0, h->stream>>>(ptr<double>(h->Q), NP, NP, (int)NP, 1,
+                                                                           ptr<double>(h->Kbuf) + NP * NP, ptr<double>(h->alpha));
+        CKL();
         CK(cudaMemcpyAsync(&h->oz_emax_host, h->oz_emax.p, 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         if ((rc = make_oz_map(h, &h->mapOzP, h->oz_Pq.p, (long)OZ_S * NP, NP, OZ_TM))) return rc;
@@ -761,8 +766,9 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
     const long NP = h->NP;
     const long cap = std::min<long>(chunk_rows(h), round_up(std::max<long>(m, 1), BM));
     if ((rc = ensure_score_scratch(h, cap))) return rc;
+    // int8 path only for batches that amortise slicing L^-1 (once per fit, ~0.4 ms at N = 4096)
     bool use_oz = false;
-    if ((rc = prepare_ozaki(h, &use_oz))) return rc;
+    if (m >= 2048 && (rc = prepare_ozaki(h, &use_oz))) return rc;
     int oz_eK = 0;
     if (use_oz) {
         // slices of K* per chunk buffer: [S][cap][NP] int8; one exponent for the whole matrix (0 < k <= amp)
@@ -779,6 +785,8 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
                 h->oz_rows2 = cap;
             }
         }
+        if ((rc = ensure(h, h->oz_mu, (size_t)cap * 8))) return rc;
+        if (h->overlap && (rc = ensure(h, h->oz_mu2, (size_t)cap * 8))) return rc;
         frexp(h->spec.amp, &oz_eK);
         oz_eK += 1;
     }
@@ -828,6 +836,10 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         int8_t* qdst = (pipelined && (ci & 1)) ? ptr<int8_t>(h->oz_Kq2) : ptr<int8_t>(h->oz_Kq);
         gpk_oz_split_kernel<<<(unsigned)((mcp * NP + 255) / 256), 256, 0, st>>>(dst, mcp, NP, nullptr, oz_eK, qdst, cap * NP);
         CKL();
+        // the mean of this chunk in fp64: one warp per candidate, K*[c, :] . alpha
+        double* mdst = (pipelined && (ci & 1)) ? ptr<double>(h->oz_mu2) : ptr<double>(h->oz_mu);
+        gpk_rowdot_kernel<<<(unsigned)((mcp + 7) / 8), 256, 0, st>>>(dst, NP, mcp, (int)NP, 0, ptr<double>(h->alpha), mdst);
+        CKL();
         return GPK_OK;
     };
     if (pipelined) {
@@ -869,8 +881,8 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         if (use_oz) {
             OzArgs o;
             o.nb = h->nb; o.ncb = (int)(mcp / OZ_TN); o.NP = (int)NP; o.rows = (int)cap;
-            o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK; o.z = a.z;
-            o.part_ssq = a.part_ssq; o.part_mu = a.part_mu; o.ldpart = a.ldpart;
+            o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
+            o.part_ssq = a.part_ssq; o.ldpart = a.ldpart;
             gpk_oz_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ_SMEM, h->stream>>>(h->mapOzP, second ? h->mapOzK2 : h->mapOzK, o);
             CKL();
             h->oz_launches += 1;
@@ -902,6 +914,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         f.out_acq = d_out ? d_out + index_offset + base : nullptr;
         f.block_best = ptr<BestPair>(h->block_best);
         f.n_negative = d_nneg;
+        f.mu_direct = use_oz ? (second ? ptr<double>(h->oz_mu2) : ptr<double>(h->oz_mu)) : nullptr;
         const int fb = (int)((mc + 255) / 256);
         gpk_finish_kernel<<<fb, 256, 0, h->stream>>>(f);
         CKL();
@@ -976,7 +989,7 @@ int gpk_destroy(gpk_handle* h) {
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
                       &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
-                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt, &h->oz_Pq, &h->oz_Kq, &h->oz_Kq2, &h->oz_eP, &h->oz_emax,
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt, &h->oz_Pq, &h->oz_Kq, &h->oz_Kq2, &h->oz_eP, &h->oz_emax, &h->oz_mu, &h->oz_mu2,
                       &h->multi_cand, &h->multi_A, &h->multi_B, &h->multi_out, &h->multi_bb, &h->gather, &h->best_global};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -1725,6 +1738,7 @@ int gpk_fit_append(gpk_handle* h, const double* X, const double* y, int n, int d
     h->n = n;
     h->mean = mean;
     h->alpha_ready = false;
+    h->linv_serial += 1;                 // L^-1 changed in place: slices / alpha derived from it are stale
     const double ld2 = h->pin[1];
     const double ll = -0.5 * h->pin[0] - 0.5 * ld2 - 0.5 * (double)n * log(2.0 * M_PI);
     if (logdet) *logdet = ld2;

@@ -15,8 +15,11 @@
 // DMMA kernel when the factor is worse conditioned than that (eP > OZ_MAX_EXP) or N > 16384.
 //
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocation, warps 2..5 = epilogue (TMEM ->
-// fp64 with the level scales, least significant level first; row scale; column reductions sum V^2, sum V z).
-// Output: the same per-row-block partial sums the DMMA kernel writes (part_ssq / part_mu [nb][ld]).
+// fp64 with the level scales, least significant level first; row scale; column reduction sum V^2).
+// Output: the per-row-block partial sums part_ssq [nb][ld] the DMMA kernel writes too.  The posterior MEAN does not go
+// through the slices: mu - mean = K* alpha is one fp64 dot product of length N per candidate (gpk_rowdot_kernel on the
+// fp64 K* that is built anyway, alpha = L^-T z once per fit), like george's own K* alpha; sum_i V_i z_i would put the
+// slices' 5e-12 error in front of |z| ~ 1e2 and cost the 1e-10 tolerance on the mean (measured: 1.1e-10 .. 1.9e-10).
 #pragma once
 #include "gpk_gemm.cuh"
 
@@ -28,7 +31,7 @@ constexpr int OZ_NSTG = 2;
 constexpr int OZ_A_SLICE = OZ_TM * OZ_KB, OZ_B_SLICE = OZ_TN * OZ_KB;
 constexpr int OZ_STAGE = OZ_S * (OZ_A_SLICE + OZ_B_SLICE);               // 98304 bytes
 constexpr int OZ_THREADS = 192;
-constexpr int OZ_SMEM = OZ_NSTG * OZ_STAGE + 1024 + 256 + 4 * OZ_TN * 16;
+constexpr int OZ_SMEM = OZ_NSTG * OZ_STAGE + 1024 + 256 + 4 * OZ_TN * 8;
 constexpr int OZ_MAX_EXP = 7;                 // row exponents above this (|L^-1| >= 64): use the fp64 kernel
 
 __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
@@ -109,8 +112,7 @@ struct OzArgs {
     int nb, ncb;                        // row blocks of L^-1 (128 rows), candidate blocks of the chunk (64 candidates)
     int NP, rows;                       // L^-1 is NP x NP; the K* slices have `rows` rows each
     const int* eP; int eK;
-    const double* z;
-    double* part_ssq; double* part_mu; long ldpart;
+    double* part_ssq; long ldpart;
 };
 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
@@ -120,7 +122,7 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
     const uint32_t bar_full = base + OZ_NSTG * OZ_STAGE, bar_empty = bar_full + 8 * OZ_NSTG, bar_tmem = bar_empty + 8 * OZ_NSTG;
     const uint32_t tmem_slot = bar_tmem + 8;
-    const uint32_t red = base + OZ_NSTG * OZ_STAGE + 256;            // [4 lane groups][64 columns] x {ssq, mu}
+    const uint32_t red = base + OZ_NSTG * OZ_STAGE + 256;            // [4 lane groups][64 columns] partial sums of V^2
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ib = g.nb - 1 - (int)blockIdx.x / g.ncb, cb = (int)blockIdx.x % g.ncb;     // longest contractions first
     const int nkb = (ib + 1) * OZ_TM / OZ_KB;                                             // lower triangle only
@@ -182,7 +184,6 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
         // epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. + 31 = tile rows
         const int lg = warp & 3;
         const int row = ib * OZ_TM + lg * 32 + lane;
-        const double zr = g.z[row];
         const double rs = ldexp(1.0, g.eP[row] + g.eK);
         oz_mbar_wait(bar_tmem, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -200,36 +201,27 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
                 for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sc, v[j]);
             }
             // column sums over the warp's 32 rows by a transposed butterfly: lane l ends up with column l
-            double q2[32], qm[32];
+            double q2[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { const double x = v[j] * rs; q2[j] = x * x; qm[j] = x * zr; }
+            for (int j = 0; j < 32; ++j) { const double x = v[j] * rs; q2[j] = x * x; }
 #pragma unroll
             for (int w = 16; w >= 1; w >>= 1) {
                 const bool up = (lane & w) != 0;
 #pragma unroll
                 for (int j = 0; j < w; ++j) {
                     const double keep2 = up ? q2[j + w] : q2[j], send2 = up ? q2[j] : q2[j + w];
-                    const double keepm = up ? qm[j + w] : qm[j], sendm = up ? qm[j] : qm[j + w];
                     q2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
-                    qm[j] = keepm + __shfl_xor_sync(0xffffffffu, sendm, w);
                 }
             }
-            const uint32_t slot = red + (uint32_t)(((lg * OZ_TN) + half * 32 + lane) * 16);
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(slot), "d"(q2[0]), "d"(qm[0]) : "memory");
+            sts64(red + (uint32_t)(((lg * OZ_TN) + half * 32 + lane) * 8), q2[0]);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int et = tid - 64;
         if (et < OZ_TN) {
-            double s2 = 0.0, sm = 0.0;
+            double s2 = 0.0;
 #pragma unroll
-            for (int w4 = 0; w4 < 4; ++w4) {
-                double a, b;
-                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(red + (uint32_t)((w4 * OZ_TN + et) * 16)));
-                s2 += a;
-                sm += b;
-            }
+            for (int w4 = 0; w4 < 4; ++w4) s2 += lds64(red + (uint32_t)((w4 * OZ_TN + et) * 8));
             g.part_ssq[(long)ib * g.ldpart + cb * OZ_TN + et] = s2;
-            g.part_mu[(long)ib * g.ldpart + cb * OZ_TN + et] = sm;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

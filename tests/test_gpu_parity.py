@@ -787,7 +787,9 @@ def test_full_size_properties():
     f = product_kernel("matern52", theta, D).flatten()
     h2.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
     logdet2, ll2 = h2.fit(diag_add, mean)
-    assert logdet2 == logdet and ll2 == ll
+    # without TMA the handle also builds K with the round-1 covariance kernel (other rounding of K itself, 1e-16
+    # relative): equal to the conditioning of the problem, not bitwise
+    assert abs(logdet2 - logdet) <= 1e-12 * abs(logdet) and abs(ll2 - ll) <= 1e-12 * abs(ll)
     r3 = h2.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
     # the two staging layouts assign tile rows to DMMA fragments differently, so the column
     # reductions add the same numbers in a different order: equal to rounding, not bitwise

@@ -32,8 +32,9 @@ PY
 }
 timeout 900 python bench.py --steps 5 --warmup 3 > $out/r2_bench.json 2> $out/r2_bench.err; summ $out/r2_bench.json default; tail -3 $out/r2_bench.err
 GPK_OZAKI=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/r2_bench_ozaki.json 2> $out/r2_bench_ozaki.err; summ $out/r2_bench_ozaki.json ozaki; tail -3 $out/r2_bench_ozaki.err
-GPK_PERSIST=0 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-c3 > $out/r2_bench_nopersist.json 2> $out/r2_bench_nopersist.err; summ $out/r2_bench_nopersist.json persist0
+GPK_PERSIST=0 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/r2_bench_nopersist.json 2> $out/r2_bench_nopersist.err; summ $out/r2_bench_nopersist.json persist0
 timeout 900 python tools/run_configs.py > $out/r2_configs_c3_c4_c5.jsonl 2> $out/r2_configs.err; cat $out/r2_configs_c3_c4_c5.jsonl; tail -3 $out/r2_configs.err
 # Ozaki prototype with cluster multicast of the L^-1 slices (cluster 1 / 2 / 4)
 (cd tools/microbench && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o ozaki_probe.bin ozaki_probe.cu -lcuda \
    && timeout 300 ./ozaki_probe.bin) > $out/r2_ozaki_probe_v2.json 2> $out/r2_ozaki_probe_v2.err; cat $out/r2_ozaki_probe_v2.json; tail -3 $out/r2_ozaki_probe_v2.err
+timeout 600 python tools/fit_compare.py > $out/r2_fit_compare2.jsonl 2> $out/r2_fit_compare2.err; cat $out/r2_fit_compare2.jsonl | cut -c1-700; tail -3 $out/r2_fit_compare2.err
