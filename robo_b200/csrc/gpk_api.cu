@@ -49,7 +49,8 @@ struct gpk_handle {
     std::vector<cudaEvent_t> ev_cs;         // split chain: 5 events per step (diag, X, trsm', pu', rest_a)
     // variance contraction on the int8 tensor pipe (gpk_ozaki.cuh); 0 = fp64 DMMA kernels
     int ozaki = 0;
-    DevBuf oz_Pq, oz_Kq, oz_Kq2, oz_eP, oz_emax, oz_mu, oz_mu2;
+    DevBuf oz_Pq, oz_Kq, oz_Kq2, oz_eP, oz_emax, oz_mu, oz_mu2, oz_pmu2;
+    int oz_fused = 1;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
     long oz_linv_serial = -1;       // linv_serial the slices of L^-1 were made for
     long linv_serial = 0;           // bumped whenever L^-1 is (re)built
     int oz_emax_host = 0;
@@ -347,6 +348,8 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 1)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 1)));
     CK(cudaFuncSetAttribute(gpk_oz_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    CK(cudaFuncSetAttribute(gpk_cov_oz_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_oz_smem_bytes(GPK_MAX_TERMS, 8)));
+    CK(cudaFuncSetAttribute(gpk_cov_oz_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_oz_smem_bytes(GPK_MAX_TERMS, 4)));
     CK(cudaFuncSetAttribute(gpk_vargemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_SMEM));
     {
         cudaDeviceProp prop;
@@ -770,6 +773,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
     bool use_oz = false;
     if (m >= 2048 && (rc = prepare_ozaki(h, &use_oz))) return rc;
     int oz_eK = 0;
+    const bool oz_fused = use_oz && h->oz_fused && cov_tma(h);
     if (use_oz) {
         // slices of K* per chunk buffer: [S][cap][NP] int8; one exponent for the whole matrix (0 < k <= amp)
         bool grew = false;
@@ -787,6 +791,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         }
         if ((rc = ensure(h, h->oz_mu, (size_t)cap * 8))) return rc;
         if (h->overlap && (rc = ensure(h, h->oz_mu2, (size_t)cap * 8))) return rc;
+        if (h->overlap && (rc = ensure(h, h->oz_pmu2, (size_t)h->nb * cap * 8))) return rc;
         frexp(h->spec.amp, &oz_eK);
         oz_eK += 1;
     }
@@ -830,10 +835,26 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         }
         const double* lo = h->has_bounds ? ptr<double>(h->lower) : nullptr;
         const double* up = h->has_bounds ? ptr<double>(h->upper) : nullptr;
+        int8_t* qdst = (pipelined && (ci & 1)) ? ptr<int8_t>(h->oz_Kq2) : ptr<int8_t>(h->oz_Kq);
+        if (use_oz && oz_fused) {
+            // K* never reaches HBM in fp64: digits + this tile's share of the mean straight out of the builder
+            CUtensorMap map;
+            int mrc = make_cov_map(h, &map, (void*)train_operand(h), h->spec.n_terms, NP);
+            if (mrc) return mrc;
+            double* pmu = (pipelined && (ci & 1)) ? ptr<double>(h->oz_pmu2) : ptr<double>(h->part_mu);
+            const unsigned gx = (unsigned)(NP / 128);
+            if (small)
+                gpk_cov_oz_kernel<4><<<dim3(gx, (unsigned)(mcp / 16)), 256, cov_oz_smem_bytes(h->spec.n_terms, 4), st>>>(
+                    map, h->spec, h->n, dX + base * h->d, h->d, mc, lo, up, ptr<double>(h->alpha), oz_eK, qdst, NP, cap * NP, pmu, cap);
+            else
+                gpk_cov_oz_kernel<8><<<dim3(gx, (unsigned)(mcp / 32)), 256, cov_oz_smem_bytes(h->spec.n_terms, 8), st>>>(
+                    map, h->spec, h->n, dX + base * h->d, h->d, mc, lo, up, ptr<double>(h->alpha), oz_eK, qdst, NP, cap * NP, pmu, cap);
+            CKL();
+            return GPK_OK;
+        }
         int crc = launch_cov_tiles(h, st, train_operand(h), NP, h->n, dX + base * h->d, h->d, mc, mcp, lo, up, dst, NP, 0, small);
         if (crc || !use_oz) return crc;
         // int8 slices of this chunk's K* (rows beyond mc are exact zeros in K*, so are their digits)
-        int8_t* qdst = (pipelined && (ci & 1)) ? ptr<int8_t>(h->oz_Kq2) : ptr<int8_t>(h->oz_Kq);
         gpk_oz_split_kernel<<<(unsigned)((mcp * NP + 255) / 256), 256, 0, st>>>(dst, mcp, NP, nullptr, oz_eK, qdst, cap * NP);
         CKL();
         // the mean of this chunk in fp64: one warp per candidate, K*[c, :] . alpha
@@ -899,7 +920,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         } else if ((rc = launch_gemm<EPI_COLREDUCE>(h, h->mapP, second ? h->mapKs2 : h->mapKs, a, h->nb * a.mcb))) return rc;
         CK(cudaEventRecord(h->ev_g1[ci], h->stream));
         if (last) CK(cudaEventRecord(h->ev[11], h->stream));
-        if (pipelined) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
+        if (pipelined && !oz_fused) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
         h->launches_var += 1;
         h->last_chunk_rows = mcp;
         FinishArgs f;
@@ -914,7 +935,8 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         f.out_acq = d_out ? d_out + index_offset + base : nullptr;
         f.block_best = ptr<BestPair>(h->block_best);
         f.n_negative = d_nneg;
-        f.mu_direct = use_oz ? (second ? ptr<double>(h->oz_mu2) : ptr<double>(h->oz_mu)) : nullptr;
+        f.mu_direct = (use_oz && !oz_fused) ? (second ? ptr<double>(h->oz_mu2) : ptr<double>(h->oz_mu)) : nullptr;
+        if (oz_fused && second) f.part_mu = ptr<double>(h->oz_pmu2);
         const int fb = (int)((mc + 255) / 256);
         gpk_finish_kernel<<<fb, 256, 0, h->stream>>>(f);
         CKL();
@@ -922,6 +944,8 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             gpk_argmax_final_kernel<<<1, 256, 0, h->stream>>>(ptr<BestPair>(h->block_best), fb, d_best);
             CKL();
         }
+        // fused int8 builder: it also writes this parity's mean partials, which the finish kernel above still reads
+        if (pipelined && oz_fused) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
         if (last) CK(cudaEventRecord(h->ev[12], h->stream));
     }
     CK(cudaEventRecord(h->ev[7], h->stream));
@@ -989,7 +1013,7 @@ int gpk_destroy(gpk_handle* h) {
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
                       &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
-                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt, &h->oz_Pq, &h->oz_Kq, &h->oz_Kq2, &h->oz_eP, &h->oz_emax, &h->oz_mu, &h->oz_mu2,
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt, &h->oz_Pq, &h->oz_Kq, &h->oz_Kq2, &h->oz_eP, &h->oz_emax, &h->oz_mu, &h->oz_mu2, &h->oz_pmu2,
                       &h->multi_cand, &h->multi_A, &h->multi_B, &h->multi_out, &h->multi_bb, &h->gather, &h->best_global};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -1031,6 +1055,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->maps_ok = false;
         h->mapKs_rows = 0;
         h->mapVt_rows = 0;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "ozfused")) {
+        if (value != 0 && value != 1) BAD("ozfused must be 0 or 1");
+        h->oz_fused = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "ozaki")) {
