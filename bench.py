@@ -524,6 +524,8 @@ def run_ours(args, rank, world, local_rank):
         return
     dgemm = measure_dgemm_tflops(torch, dev)
     dmma_peak, dfma_peak = h.measure_fp64_peaks()
+    used_int8 = tim.get("launches_ozaki", 0) > 0
+    int8_peak = h.measure_int8_peak() if used_int8 else None
     # ---- CPU baselines on this box's host cores (bounded sample; rank 0, N = 1 only) ----
     cpu, cpu_opt = None, None
     if world == 1 and not args.no_cpu_baseline:
@@ -546,6 +548,37 @@ def run_ours(args, rank, world, local_rank):
     except Exception as e:                                   # noqa: BLE001
         print("fit_append timing skipped: %r" % (e,), file=sys.stderr)
     traffic = ncu_dram_bytes(VARGEMM_NCU_CSV, "gpk_gemm_ws_kernel<1>") if last_rows == 16384 else None
+    fp64_block = {"fp64_equivalent_tflops": achieved, "dmma_peak_tflops": dmma_peak, "frac_of_dmma_peak": achieved / dmma_peak,
+                  "frac_of_datasheet_fp64": achieved / FP64_PEAK_TFLOPS, "dfma_vector_peak_tflops": dfma_peak,
+                  "dgemm_cublas_tflops": dgemm, "frac_of_cublas_dgemm": achieved / dgemm if dgemm > 0 else None,
+                  "launch_ms": gemm_ms, "launch_candidates": int(last_rows),
+                  "launches_averaged": int(max(1, (M + rows - 1) // rows - 1)) if M > rows else 1}
+    if used_int8:
+        # the contraction ran on the int8 tensor pipe: 36 exact slice-pair products per fp64 product over the lower
+        # triangle of L^-1 in 128-row blocks = 36 (N^2 + 128 N) int8 multiply-adds x 2 per candidate row
+        int8_ops = float(last_rows) * 36.0 * (N_TRAIN ** 2 + 128 * N_TRAIN)
+        int8_achieved = int8_ops / (gemm_ms * 1e-3) / 1e12
+        roofline = dict(fp64_block, bound="tensor",
+                        kernel="gpk_oz_vargemm_kernel (L^-1 K*^T as 36 int8 slice products, tcgen05.mma kind::i8, TMEM "
+                               "accumulators, TMA-staged 64B-swizzled slices)",
+                        achieved=int8_achieved, peak=int8_peak, unit="TFLOP/s", frac=int8_achieved / int8_peak,
+                        ops="int8 multiply-accumulate counted as 2 ops (TOP/s)",
+                        peak_source="measured live on this GPU: tcgen05.mma kind::i8 128x128x32 issue rate from shared "
+                                    "memory (gpk_measure_int8_peak); nominal dense int8 = 4500 TOP/s (2x the bf16 figure of "
+                                    "MEASURED_PEAKS.json's datasheet)",
+                        traffic=None, traffic_source="no ncu capture of the int8 kernel committed yet")
+    else:
+        roofline = dict(fp64_block, bound="tensor",
+                        kernel="%s (L^-1 K*^T contraction, fp64 DMMA, warp-specialised TMA)"
+                               % ("gpk_vargemm_persistent_kernel" if os.environ.get("GPK_PERSIST", "") == "1" else "gpk_gemm_ws_kernel<EPI_COLREDUCE>"),
+                        achieved=achieved, peak=dmma_peak, unit="TFLOP/s", frac=achieved / dmma_peak,
+                        peak_source="measured live on this GPU: register-resident DMMA m8n8k4 issue rate "
+                                    "(gpk_measure_fp64_peaks); MEASURED_PEAKS.json has no fp64 figure; datasheet "
+                                    "FP64-tensor = %.0f TF/s (SURVEY 8d P64)" % FP64_PEAK_TFLOPS,
+                        traffic=traffic,
+                        traffic_source="read at run time from the committed capture %s (ncu --set full, one 16384-candidate "
+                                       "launch: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic minimum 0.60e9 "
+                                       "(L^-1 lower triangle 67 MB + K* 537 MB read once)" % VARGEMM_NCU_CSV)
     line = {
         "metric": METRIC, "value": value, "unit": "EI evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -574,19 +607,7 @@ def run_ours(args, rank, world, local_rank):
                                    "ms_per_step": ms_pinned / args.steps,
                                    "call": "gpk_acq on a page-locked host buffer, arg-max only (round-1 e2e)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gpk_gemm_ws_kernel<EPI_COLREDUCE> (L^-1 K*^T contraction, fp64 DMMA, warp-specialised TMA)",
-                     "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
-                     "peak_source": "measured live on this GPU: register-resident DMMA m8n8k4 issue rate "
-                                    "(gpk_measure_fp64_peaks); MEASURED_PEAKS.json has no fp64 figure; datasheet "
-                                    "FP64-tensor = %.0f TF/s (SURVEY 8d P64)" % FP64_PEAK_TFLOPS,
-                     "frac_of_datasheet": achieved / FP64_PEAK_TFLOPS, "dfma_vector_peak_tflops": dfma_peak,
-                     "dgemm_cublas_tflops": dgemm, "frac_of_cublas_dgemm": achieved / dgemm if dgemm > 0 else None,
-                     "launch_ms": gemm_ms, "launch_candidates": int(last_rows),
-                     "launches_averaged": int(max(1, (M + rows - 1) // rows - 1)) if M > rows else 1,
-                     "traffic": traffic,
-                     "traffic_source": "read at run time from the committed capture %s (ncu --set full, one 16384-candidate "
-                                       "launch: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic minimum 0.60e9 "
-                                       "(L^-1 lower triangle 67 MB + K* 537 MB read once)" % VARGEMM_NCU_CSV},
+        "roofline": roofline,
         "kernel_ms_last_chunk": {k: tim[k] for k in ("kstar_ms", "vargemm_ms", "finish_ms")},
         "configs": {"c3": c3},
         "cpu_baseline": cpu, "cpu_baseline_optimised": cpu_opt, "clocks": clocks,

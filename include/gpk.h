@@ -267,6 +267,10 @@ int gpk_nll_grad(gpk_handle* h, double noise_var, double* grad);
  * uses the DMMA figure as the roofline denominator (MEASURED_PEAKS.json has no fp64 entry). */
 int gpk_measure_fp64_peaks(gpk_handle* h, double* dmma_tflops, double* dfma_tflops);
 
+/* int8 tensor-pipe issue-rate peak in TOP/s (tcgen05.mma kind::i8, 128 x 128 x 32, operands in shared memory,
+ * accumulator in TMEM): the roofline denominator of the option-"ozaki" contraction. */
+int gpk_measure_int8_peak(gpk_handle* h, double* tops);
+
 /* ---- introspection (tests / debugging) ----------------------------------------------- */
 int gpk_get_factor(gpk_handle* h, double* L /* n x n row-major, lower */);
 int gpk_get_linv(gpk_handle* h, double* Linv /* n x n row-major, lower */);

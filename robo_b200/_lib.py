@@ -63,6 +63,7 @@ _SIGNATURES = {
                                     C.c_double, C.c_double, _dp, _dp, _lp],
     "gpk_nll_grad": [_vp, C.c_double, _dp],
     "gpk_measure_fp64_peaks": [_vp, _dp, _dp],
+    "gpk_measure_int8_peak": [_vp, _dp],
     "gpk_get_factor": [_vp, _dp],
     "gpk_get_linv": [_vp, _dp],
     "gpk_get_z": [_vp, _dp],
@@ -385,6 +386,12 @@ class Handle(object):
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.gpk_measure_fp64_peaks(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def measure_int8_peak(self):
+        """-> int8 tensor-pipe issue-rate peak in TOP/s (tcgen05 kind::i8) measured on this GPU."""
+        a = C.c_double()
+        self._check(self.lib.gpk_measure_int8_peak(self._h, C.byref(a)))
+        return a.value
 
     # -- introspection ----------------------------------------------------------------
     def get_factor(self, n):

@@ -2290,6 +2290,30 @@ int gpk_measure_fp64_peaks(gpk_handle* h, double* dmma_tflops, double* dfma_tflo
     return GPK_OK;
 }
 
+int gpk_measure_int8_peak(gpk_handle* h, double* tops) {
+    if (!h || !tops) return GPK_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    const int blocks = std::max(h->n_sm, 1), iters = 4000, smem = 2 * 8192 + 1024 + 64;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        float ms = 0.f;
+        CK(cudaEventRecord(e0, h->stream));
+        gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters);
+        CKL();
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::max(best, 2.0 * 128 * 128 * 32 * 2.0 * iters * blocks / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tops = best;
+    return GPK_OK;
+}
+
 int gpk_get_factor(gpk_handle* h, double* L) {
     int rc = require(h, true, true, true);
     if (rc) return rc;

@@ -346,3 +346,41 @@ gpk_cov_oz_kernel(const __grid_constant__ CUtensorMap mapX, const KSpec ks, int 
     }
 }
 inline size_t cov_oz_smem_bytes(int n_terms, int cc) { return (size_t)n_terms * 1024 + (size_t)4 * cc * n_terms * 8 + 8 + 8 * cc * 8 + 128; }
+
+// ---------------------------------------------------------------------------------------
+// int8 tensor-pipe issue-rate peak of this GPU (roofline denominator of gpk_oz_vargemm_kernel in bench.py): every SM
+// issues `iters` kind::i8 MMAs of 128 x 128 x 32 on one shared-memory operand pair (contents irrelevant) into one
+// TMEM accumulator; no loads in the loop.  tools/microbench/i8_umma_probe.cu checks the same instruction against a
+// CPU integer GEMM.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) gpk_peak_i8_kernel(int iters)
+{
+    extern __shared__ unsigned char pk_raw[];
+    const uint32_t base = (smem_u32(pk_raw) + 1023u) & ~1023u;            // A: 128 x 64 B, B: 128 x 64 B (64B swizzle atoms)
+    const uint32_t bar = base + 2 * 8192, slot = bar + 8;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 4096; e += 128) asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + 4u * e), "r"(0x01010101u * (e & 3)) : "memory");
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot) : "memory");
+    if (tid == 0) {
+        const uint32_t idesc = oz_idesc(128, 128);
+        for (int i = 0; i < iters; ++i) {
+            oz_mma(tmem, oz_desc(base), oz_desc(base + 8192), idesc, (uint32_t)(i != 0));
+            oz_mma(tmem, oz_desc(base + 32), oz_desc(base + 8192 + 32), idesc, 1u);
+        }
+        oz_commit(bar);
+        oz_mbar_wait(bar, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u) : "memory");
+}
