@@ -570,7 +570,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         roofline = dict(fp64_block, bound="tensor",
                         kernel="%s (L^-1 K*^T contraction, fp64 DMMA, warp-specialised TMA)"
-                               % ("gpk_vargemm_persistent_kernel" if os.environ.get("GPK_PERSIST", "") == "1" else "gpk_gemm_ws_kernel<EPI_COLREDUCE>"),
+                               % ("gpk_vargemm_persistent_kernel" if tim.get("persist") else "gpk_gemm_ws_kernel<EPI_COLREDUCE>"),
                         achieved=achieved, peak=dmma_peak, unit="TFLOP/s", frac=achieved / dmma_peak,
                         peak_source="measured live on this GPU: register-resident DMMA m8n8k4 issue rate "
                                     "(gpk_measure_fp64_peaks); MEASURED_PEAKS.json has no fp64 figure; datasheet "

@@ -70,10 +70,16 @@ const char* gpk_version(void);
  *               every call directly
  *   "ozaki"     1 = variance contraction on the int8 tensor pipe (tcgen05 kind::i8, TMEM accumulators) through an
  *               error-free 8 x 8 slice split of L^-1 and K* (gpk_ozaki.cuh); used while max |L^-1| < 64, otherwise the
- *               fp64 kernel runs; 0 = always fp64 DMMA [default]
- *   "persist"   1 = persistent fp64 variance contraction (one CTA per SM, dynamic tile counter) [default]
+ *               fp64 kernel runs [default; batches of >= 2048 candidates]; 0 = always fp64 DMMA.  The posterior mean
+ *               never goes through the slices (fp64 K* alpha)
+ *   "ozfused"   1 = with "ozaki": the covariance builder writes the int8 digits and mean partials itself, no fp64 K*
+ *               in HBM; 0 = fp64 K* + split kernel + mean dot [default: measured slightly faster, the contraction is
+ *               bound by shared-memory operand reads, not by L2 / HBM]
+ *   "persist"   1 = persistent fp64 variance contraction (one CTA per SM, dynamic tile counter); 0 = one CTA per tile
+ *               [default: the persistent variant measured 2 % slower at N = 4096 and equal at N = 1024]
  *   "depth2"    1 = trailing updates of two consecutive panels in one K = 256 contraction (odd steps; even steps update
- *               only the next-but-one block column) [default]; 0 = one K = 128 update per step (bit-identical factor)
+ *               only the next-but-one block column); 0 = one K = 128 update per step (bit-identical factor);
+ *               2 = automatic [default]: on for N >= 6144, where the trailing updates gate the fit (5 % at N = 8192)
  *   "chainsplit" 1 = split Cholesky chain: diag(k+1) waits only for block row k+1 of step k (one launch on
  *               four 32-row tiles), the rows below run on a second high-priority stream, trailing update with
  *               look-ahead 2 (measured neutral against the plain schedule: profiles/r02_fit_compare_*.jsonl);
@@ -282,7 +288,7 @@ int gpk_get_z(gpk_handle* h, double* z /* n */);
  * out[8] = variance-GEMM launches so far,
  * out[9] = total kernel launches so far,
  * out[10] = of those, launches of the int8 (Ozaki) contraction; out[11] = largest row exponent of L^-1 seen by it
- * (option "ozaki"); out[12..15] reserved (zero). */
+ * (option "ozaki"); out[12] = option "persist"; out[13..15] reserved (zero). */
 int gpk_get_timings(gpk_handle* h, double* out16);
 /* diagnostics of the blocked diagonal-block kernel (option "diagprof" = 1): clock64() stamps of the last
  * launched block: out[0] start, out[1] tiles loaded, out[2+2p] panel p factorised + solved, out[3+2p] panel p's

@@ -48,16 +48,16 @@ struct gpk_handle {
     cudaStream_t panel_stream = nullptr;    // split chain: panel solve / next-panel update of the rows below block row k+1
     std::vector<cudaEvent_t> ev_cs;         // split chain: 5 events per step (diag, X, trsm', pu', rest_a)
     // variance contraction on the int8 tensor pipe (gpk_ozaki.cuh); 0 = fp64 DMMA kernels
-    int ozaki = 0;
+    int ozaki = 1;
     DevBuf oz_Pq, oz_Kq, oz_Kq2, oz_eP, oz_emax, oz_mu, oz_mu2, oz_pmu2;
-    int oz_fused = 1;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
+    int oz_fused = 0;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
     long oz_linv_serial = -1;       // linv_serial the slices of L^-1 were made for
     long linv_serial = 0;           // bumped whenever L^-1 is (re)built
     int oz_emax_host = 0;
     long oz_rows = 0, oz_rows2 = 0;
     CUtensorMap mapOzP, mapOzK, mapOzK2;
     double oz_launches = 0;
-    int persist = 1;                // 1: persistent variance contraction (gpk_vargemm_persistent_kernel) [default]
+    int persist = 0;                // 1: persistent variance contraction (gpk_vargemm_persistent_kernel); measured 2 % slower than one CTA per tile
     DevBuf tile_cnt;
     int n_sm = 0;
     int use_graph = 1;              // split chain: one CUDA graph per layout, replayed per fit
@@ -104,7 +104,7 @@ struct gpk_handle {
     // job tables
     std::vector<Range> trsm_r, syrk_r, tri1_r, tri2_r, trsm32_r, pu32_r, trsm16_r, pu16_r;
     std::vector<Range> syrk2_r;     // depth-2 trailing update: columns >= k+2 with panels k-1 and k in one contraction (K = 256)
-    int depth2 = 1;
+    int depth2 = 2;                 // 0 / 1, or 2 = automatic: on for nb >= 48 (trailing updates gate the fit only there)
     Range kinv_r;
     Range app_row_r, app_syrk_r, app_t_r, app_p_r;      // gpk_fit_append (last block row only)
     Range app_row2_r, app_t2_r;                         // split-K versions of the two long contractions
@@ -1073,7 +1073,7 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         return GPK_OK;
     }
     if (!strcmp(key, "depth2")) {
-        if (value != 0 && value != 1) BAD("depth2 must be 0 or 1");
+        if (value < 0 || value > 2) BAD("depth2 must be 0, 1 or 2 (automatic)");
         h->depth2 = (int)value;
         return GPK_OK;
     }
@@ -1558,7 +1558,8 @@ int gpk_fit_begin(gpk_handle* h, double diag_add, double mean) {
                 s.jobs = ptr<GemmJob>(h->jobs) + off;
                 if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, npu))) return rc;
             }
-            if (cnt > npu && !(h->depth2 && h->smalltile)) {
+            const bool d2 = h->smalltile && (h->depth2 == 1 || (h->depth2 == 2 && nb >= 48));
+            if (cnt > npu && !d2) {
                 CK(cudaStreamWaitEvent(h->side_stream, h->ev_panel[k], 0));
                 s.jobs = ptr<GemmJob>(h->jobs) + off + npu;
                 if ((rc = launch_gemm<EPI_STORE>(h, h->mapK, h->mapK, s, cnt - npu, h->side_stream))) return rc;
@@ -2390,6 +2391,7 @@ int gpk_get_timings(gpk_handle* h, double* out /* 16 */) {
     out[9] = h->launches_total;
     out[10] = h->oz_launches;
     out[11] = (double)h->oz_emax_host;
+    out[12] = (double)h->persist;
     return GPK_OK;
 }
 

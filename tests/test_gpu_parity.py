@@ -791,12 +791,12 @@ def test_full_size_properties():
     # relative): equal to the conditioning of the problem, not bitwise
     assert abs(logdet2 - logdet) <= 1e-12 * abs(logdet) and abs(ll2 - ll) <= 1e-12 * abs(ll)
     r3 = h2.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
-    # the two staging layouts assign tile rows to DMMA fragments differently, so the column
-    # reductions add the same numbers in a different order: equal to rounding, not bitwise
-    np.testing.assert_allclose(r1["mu"], r3["mu"], rtol=0, atol=1e-13 * np.abs(y).max())
-    np.testing.assert_allclose(r1["var"], r3["var"], rtol=1e-12)
+    # other staging layout (fragment rows in another order) AND the round-1 covariance builder (K, K* rounded
+    # differently in the last bit): equal to the conditioning of the problem (the parity tolerances), not bitwise
+    assert_mean_close(r3["mu"], r1["mu"], y)
+    assert_var_close(r3["var"], r1["var"], float(np.exp(theta[0])))
     big = r1["values"] > 1e-30
-    np.testing.assert_allclose(r1["values"][big], r3["values"][big], rtol=1e-9)
+    np.testing.assert_allclose(r1["values"][big], r3["values"][big], rtol=1e-8)
     amp = float(np.exp(theta[0]))
     assert np.all(r1["var"] >= np.finfo(float).eps) and np.all(r1["var"] <= amp * (1 + 1e-12))
     assert np.all(r1["values"] >= 0)
@@ -948,10 +948,10 @@ def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
     theta_bad = theta + np.r_[0.0, np.full(D, np.log(4.0))]
     h, logdet, ll, diag_add, mean = _handle_for("matern52", theta_bad, X, y, 1e-8)
     h.set_option("ozaki", 1)
-    r = h.acq(Xs[:2000], _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
+    r = h.acq(Xs[:4096], _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
     t = h.timings()
     assert t["ozaki_max_row_exponent"] > 7 and t["launches_ozaki"] == 0, t
     st = O.gp_fit(oracle_kernel("matern52", theta_bad, D), X, y, noise=1e-8, normalize_input=False)
-    mu_ref, var_ref = O.gp_predict_var_only_fast(st, Xs[:2000])
+    mu_ref, var_ref = O.gp_predict_var_only_fast(st, Xs[:4096])
     assert_mean_close(r["mu"], mu_ref, y, tol=1e-8)          # cond ~1e11: the fp64 path itself is at its limit here
     h.close()

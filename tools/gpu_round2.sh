@@ -13,8 +13,7 @@ run_tests() {  # tag, extra env...
   return $rc
 }
 run_tests default X=1
-# the same suite with the variance contraction on the int8 tensor pipe wherever the factor allows it
-run_tests ozaki GPK_OZAKI=1
+run_tests fp64 GPK_OZAKI=0
 timeout 300 python __graft_entry__.py --smoke > $out/r2_smoke.log 2>&1; tail -2 $out/r2_smoke.log
 summ() {
   python - "$1" "$2" <<'PY'
@@ -22,8 +21,8 @@ import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     c3 = (d.get("configs") or {}).get("c3") or {}
-    print(sys.argv[2], "value %.4g e2e %.4g ms/step %.3f roofline %.3f fit_ms %.3f argmax_check %s kernel_ms %s c3 host %.2f ms dev %.2f ms check %s" % (
-        d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["frac"], d["fit_ms"], d.get("argmax_check"),
+    print(sys.argv[2], "value %.4g e2e %.4g ms/step %.3f roofline %.3f (%s) fit_ms %.3f argmax_check %s kernel_ms %s c3 host %.2f ms dev %.2f ms check %s" % (
+        d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["kernel"][:28], d["fit_ms"], d.get("argmax_check"),
         d["kernel_ms_last_chunk"], (c3.get("host_pageable") or {}).get("wall_ms", float("nan")),
         (c3.get("device_philox") or {}).get("wall_ms", float("nan")), c3.get("argmax_check")))
 except Exception as e:
@@ -31,10 +30,8 @@ except Exception as e:
 PY
 }
 timeout 900 python bench.py --steps 5 --warmup 3 > $out/r2_bench.json 2> $out/r2_bench.err; summ $out/r2_bench.json default; tail -3 $out/r2_bench.err
-GPK_OZAKI=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/r2_bench_ozaki.json 2> $out/r2_bench_ozaki.err; summ $out/r2_bench_ozaki.json ozaki; tail -3 $out/r2_bench_ozaki.err
-GPK_PERSIST=0 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/r2_bench_nopersist.json 2> $out/r2_bench_nopersist.err; summ $out/r2_bench_nopersist.json persist0
-timeout 900 python tools/run_configs.py > $out/r2_configs_c3_c4_c5.jsonl 2> $out/r2_configs.err; cat $out/r2_configs_c3_c4_c5.jsonl; tail -3 $out/r2_configs.err
-# Ozaki prototype with cluster multicast of the L^-1 slices (cluster 1 / 2 / 4)
+GPK_OZAKI=0 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/r2_bench_fp64.json 2> $out/r2_bench_fp64.err; summ $out/r2_bench_fp64.json fp64; tail -3 $out/r2_bench_fp64.err
+GPK_OZFUSED=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-c3 > $out/r2_bench_ozfused.json 2> $out/r2_bench_ozfused.err; summ $out/r2_bench_ozfused.json ozfused
+timeout 900 python tools/run_configs.py > $out/r2_configs_c3_c4_c5.jsonl 2> $out/r2_configs.err; cut -c1-600 $out/r2_configs_c3_c4_c5.jsonl; tail -3 $out/r2_configs.err
 (cd tools/microbench && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o ozaki_probe.bin ozaki_probe.cu -lcuda \
-   && timeout 300 ./ozaki_probe.bin) > $out/r2_ozaki_probe_v2.json 2> $out/r2_ozaki_probe_v2.err; cat $out/r2_ozaki_probe_v2.json; tail -3 $out/r2_ozaki_probe_v2.err
-timeout 600 python tools/fit_compare.py > $out/r2_fit_compare2.jsonl 2> $out/r2_fit_compare2.err; cat $out/r2_fit_compare2.jsonl | cut -c1-700; tail -3 $out/r2_fit_compare2.err
+   && timeout 300 ./ozaki_probe.bin) > $out/r2_ozaki_probe_v3.json 2> $out/r2_ozaki_probe_v3.err; cat $out/r2_ozaki_probe_v3.json; tail -3 $out/r2_ozaki_probe_v3.err
