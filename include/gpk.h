@@ -72,9 +72,8 @@ const char* gpk_version(void);
  *               error-free 8 x 8 slice split of L^-1 and K* (gpk_ozaki.cuh); used while max |L^-1| < 64, otherwise the
  *               fp64 kernel runs [default; batches of >= 2048 candidates]; 0 = always fp64 DMMA.  The posterior mean
  *               never goes through the slices (fp64 K* alpha)
- *   "ozfused"   1 = with "ozaki": the covariance builder writes the int8 digits and mean partials itself, no fp64 K*
- *               in HBM; 0 = fp64 K* + split kernel + mean dot [default: measured slightly faster, the contraction is
- *               bound by shared-memory operand reads, not by L2 / HBM]
+ *   "ozfused"   1 = with "ozaki": the covariance builder writes the int8 digits and the mean partials itself, no fp64
+ *               K* in HBM [default: 3.35 vs 3.16 M EI/s at N = 4096]; 0 = fp64 K* + split kernel + mean dot
  *   "persist"   1 = persistent fp64 variance contraction (one CTA per SM, dynamic tile counter); 0 = one CTA per tile
  *               [default: the persistent variant measured 2 % slower at N = 4096 and equal at N = 1024]
  *   "depth2"    1 = trailing updates of two consecutive panels in one K = 256 contraction (odd steps; even steps update
