@@ -295,6 +295,202 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
 }
 
+// =======================================================================================
+// v4: 128 x 128 tiles in TWO passes over the contraction (levels 0..3, then 4..7): the int8 MMA reads both operands
+// from shared memory at 128 B / clock / SM, so a 128 x 64 MMA (6 KB) is operand-fetch bound at 48 cycles instead of
+// its 33 compute cycles; 128 x 128 (8 KB, 64 cycles) is balanced.  TMEM holds 4 accumulators of 128 columns per pass;
+// the fp64 partial result of pass 1 waits in an L2-resident scratch tile (one per SM).  32-byte k-blocks (SWIZZLE_32B),
+// 3 stages of 64 KB (pass 1 fills half of a stage: 4 + 4 slice tiles, pass 2 all 8 + 8).
+// =======================================================================================
+constexpr int KB2 = 32;
+constexpr int T2 = 128;
+constexpr int SL2 = T2 * KB2;                       // 4096 bytes per slice tile
+constexpr int STAGE2 = 16 * SL2;                    // 65536
+constexpr int NSTG2 = 3;
+constexpr int OZ2_SMEM = NSTG2 * STAGE2 + 1024 + 256 + 4 * T2 * 8;
+
+__device__ __forceinline__ uint64_t umma_desc32(uint32_t smem_addr) {      // K-major SWIZZLE_32B: 8 rows x 32 B atoms
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+__device__ __forceinline__ void mbar_arrive1(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+struct Oz2Args {
+    int nb, ncb;                        // row blocks of P, candidate blocks of 128
+    int N, Mc;
+    const int* eP; const int* eK;
+    double* part_ssq;                   // [nb][Mc]
+    double* scratch;                    // [nsmid][128][128]
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapK, const Oz2Args g)
+{
+    extern __shared__ unsigned char raw[];
+    const uint32_t base = (s_u32(raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + NSTG2 * STAGE2, bar_empty = bar_full + 8 * NSTG2;
+    const uint32_t bar_tfull = bar_empty + 8 * NSTG2, bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
+    const uint32_t red = base + NSTG2 * STAGE2 + 256;                // [4 lane groups][128 columns]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ib = g.nb - 1 - (int)blockIdx.x / g.ncb, cb = (int)blockIdx.x % g.ncb;
+    const int nkb = (ib + 1) * T2 / KB2;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTG2; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                const int ns = pass == 0 ? 4 : 8;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % NSTG2;
+                    if (it >= NSTG2) mbar_wait(bar_empty + 8 * s, (uint32_t)((it / NSTG2 - 1) & 1));
+                    const uint32_t st = base + s * STAGE2;
+                    mbar_expect_tx(bar_full + 8 * s, (uint32_t)(2 * ns * SL2));
+                    for (int q = 0; q < ns; ++q) {
+                        tma_2d(st + q * SL2, &mapP, kb * KB2, q * g.N + ib * T2, bar_full + 8 * s);
+                        tma_2d(st + (8 + q) * SL2, &mapK, kb * KB2, q * g.Mc + cb * T2, bar_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(T2, T2);
+            int it = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1) {                                      // the epilogue has read the first four accumulators
+                    mbar_wait(bar_tempty, 0);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % NSTG2;
+                    mbar_wait(bar_full + 8 * s, (uint32_t)((it / NSTG2) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * STAGE2;
+                    if (pass == 0) {
+#pragma unroll
+                        for (int lvl = 0; lvl < 4; ++lvl)
+#pragma unroll
+                            for (int a = 0; a <= lvl; ++a)
+                                umma_i8(tmem + (uint32_t)(lvl * T2), umma_desc32(st + a * SL2), umma_desc32(st + (8 + lvl - a) * SL2),
+                                        idesc, (uint32_t)((kb | a) != 0));
+                    } else {
+#pragma unroll
+                        for (int lvl = 4; lvl < 8; ++lvl)
+#pragma unroll
+                            for (int a = 0; a <= lvl; ++a)
+                                umma_i8(tmem + (uint32_t)((lvl - 4) * T2), umma_desc32(st + a * SL2), umma_desc32(st + (8 + lvl - a) * SL2),
+                                        idesc, (uint32_t)((kb | a) != 0));
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_tfull);
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        const int rl = lg * 32 + lane, row = ib * T2 + rl;
+        const double rs = ldexp(1.0, g.eP[row] + g.eK[0]);
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        double* sc = g.scratch + ((size_t)smid * T2 + rl) * T2;
+        const uint32_t lane_base = tmem + ((uint32_t)(lg * 32) << 16);
+        // ---- pass 1 result -> scratch
+        mbar_wait(bar_tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < T2; c0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+            for (int lvl = 3; lvl >= 0; --lvl) {
+                uint32_t d[32];
+                tmem_ld32(lane_base + (uint32_t)(lvl * T2 + c0), d);
+                const double sf = ldexp(1.0, -7 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(sc + c0 + j) = make_double2(v[j], v[j + 1]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 64) mbar_arrive1(bar_tempty);
+        // ---- pass 2 result + scratch -> squares -> column sums
+        mbar_wait(bar_tfull, 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < T2; c0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+            for (int lvl = 7; lvl >= 4; --lvl) {
+                uint32_t d[32];
+                tmem_ld32(lane_base + (uint32_t)((lvl - 4) * T2 + c0), d);
+                const double sf = ldexp(1.0, -7 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
+            }
+            double q2[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const double2 h = *reinterpret_cast<const double2*>(sc + c0 + j);
+                const double x0 = (v[j] + h.x) * rs, x1 = (v[j + 1] + h.y) * rs;
+                q2[j] = x0 * x0; q2[j + 1] = x1 * x1;
+            }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+                const bool up = (lane & w) != 0;
+#pragma unroll
+                for (int j = 0; j < w; ++j) {
+                    const double keep2 = up ? q2[j + w] : q2[j], send2 = up ? q2[j] : q2[j + w];
+                    q2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+                }
+            }
+            asm volatile("st.shared.f64 [%0], %1;" :: "r"(red + (uint32_t)((lg * T2 + c0 + lane) * 8)), "d"(q2[0]) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - 64;
+        double s2 = 0.0;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+            double a;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(red + (uint32_t)((w4 * T2 + et) * 8)));
+            s2 += a;
+        }
+        g.part_ssq[(long)ib * g.Mc + cb * T2 + et] = s2;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
 __global__ void oz_finish_kernel(const double* part_ssq, const double* part_mu, int nb, long Mc, double* ssq, double* mu) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Mc) return;
@@ -319,6 +515,16 @@ static void make_map(CUtensorMap* map, void* base, long rows, long cols, int box
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("{\"error\": \"cuTensorMapEncodeTiled %d\"}\n", (int)r); exit(1); }
+}
+
+static void make_map32(CUtensorMap* map, void* base, long rows, long cols) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols};
+    cuuint32_t box[2] = {(cuuint32_t)KB2, (cuuint32_t)T2};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("{\"error\": \"cuTensorMapEncodeTiled(32B) %d\"}\n", (int)r); exit(1); }
 }
 
 struct Problem { int N, M; std::vector<double> P, Ks, z; double amp; };
@@ -392,7 +598,7 @@ static void launch_oz(int grid, const CUtensorMap& mapP, const CUtensorMap& mapK
     CKC(cudaLaunchKernelEx(&cfg, oz_vargemm_kernel<CL, ORDER>, mapP, mapK, a));
 }
 
-static Result run_gpu(const Problem& pr, int reps, int cl = 1) {
+static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = false) {
     const int N = pr.N, M = pr.M, nb = N / TM, ncb = M / TN;
     double *dP, *dK, *dz, *dpss, *dpmu, *dssq, *dmu;
     int8_t *dPq, *dKq;
@@ -410,9 +616,15 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1) {
     oz_rowmax_kernel<<<N, 256>>>(dP, N, N, deP);
     oz_split_kernel<<<(unsigned)(((size_t)N * N + 255) / 256), 256>>>(dP, N, N, deP, 0, dPq);
     CKC(cudaGetLastError());
-    CUtensorMap mapP, mapK;
+    CUtensorMap mapP, mapK, mapP32, mapK32;
     make_map(&mapP, dPq, (long)S * N, N, TM);
     make_map(&mapK, dKq, (long)S * M, N, TN);
+    make_map32(&mapP32, dPq, (long)S * N, N);
+    make_map32(&mapK32, dKq, (long)S * M, N);
+    double* dscr = nullptr;
+    CKC(cudaMalloc(&dscr, (size_t)256 * T2 * T2 * 8));
+    CKC(cudaFuncSetAttribute(oz2_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM));
+    Oz2Args a2; a2.nb = nb; a2.ncb = M / T2; a2.N = N; a2.Mc = M; a2.eP = deP; a2.eK = deK; a2.part_ssq = dpss; a2.scratch = dscr;
     OzArgs a; a.nb = nb; a.ncb = ncb; a.N = N; a.Mc = M; a.eP = deP; a.eK = deK; a.z = dz; a.part_ssq = dpss; a.part_mu = dpmu;
     cudaEvent_t e0, e1, e2;
     CKC(cudaEventCreate(&e0)); CKC(cudaEventCreate(&e1)); CKC(cudaEventCreate(&e2));
@@ -421,7 +633,8 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1) {
         CKC(cudaEventRecord(e0));
         oz_split_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(dK, M, N, deK, 1, dKq);
         CKC(cudaEventRecord(e1));
-        if (cl == 1) launch_oz<1, 0>(nb * ncb, mapP, mapK, a);
+        if (two_pass) oz2_vargemm_kernel<<<nb * (M / T2), OZ_THREADS, OZ2_SMEM>>>(mapP32, mapK32, a2);
+        else if (cl == 1) launch_oz<1, 0>(nb * ncb, mapP, mapK, a);
         else if (cl == 2) launch_oz<2, 0>(nb * ncb, mapP, mapK, a);
         else launch_oz<1, 1>(nb * ncb, mapP, mapK, a);            // cl == 4 slot reused: A-sharing issue order
         oz_finish_kernel<<<(M + 255) / 256, 256>>>(dpss, dpmu, nb, M, dssq, dmu);
@@ -436,7 +649,7 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1) {
     CKC(cudaMemcpy(res.ssq.data(), dssq, (size_t)M * 8, cudaMemcpyDeviceToHost));
     CKC(cudaMemcpy(res.mu.data(), dmu, (size_t)M * 8, cudaMemcpyDeviceToHost));
     cudaFree(dP); cudaFree(dK); cudaFree(dz); cudaFree(dPq); cudaFree(dKq); cudaFree(deP); cudaFree(deK);
-    cudaFree(dpss); cudaFree(dpmu); cudaFree(dssq); cudaFree(dmu);
+    cudaFree(dpss); cudaFree(dpmu); cudaFree(dssq); cudaFree(dmu); cudaFree(dscr);
     return res;
 }
 
@@ -447,7 +660,8 @@ int main() {
     g_encode = (EncodeFn)p;
     // ---- accuracy on real GP data (N = 1024, D = 16, 256 candidates) against an 80-bit CPU contraction
     Problem pr = gp_problem(1024, 256, 16);
-    Result r = run_gpu(pr, 1, 1), r2 = run_gpu(pr, 1, 2), r4 = run_gpu(pr, 1, 4);
+    Result r = run_gpu(pr, 1, 1), r2 = run_gpu(pr, 1, 2), r4 = run_gpu(pr, 1, 4), rt = run_gpu(pr, 1, 1, true);
+    double worst_var2 = 0;
     double cl_diff = 0;
     for (int c = 0; c < pr.M; ++c)
         cl_diff = std::max(cl_diff, std::max(std::fabs(r.ssq[c] - r2.ssq[c]), std::fabs(r.ssq[c] - r4.ssq[c])) + std::max(std::fabs(r.mu[c] - r2.mu[c]), std::fabs(r.mu[c] - r4.mu[c])));
@@ -463,15 +677,16 @@ int main() {
         var_min = std::min(var_min, var_ref);
         worst_var = std::max(worst_var, std::fabs(var - var_ref) / std::max(std::fabs(var_ref), 1e-6 * pr.amp));
         worst_mu = std::max(worst_mu, std::fabs(r.mu[c] - (double)mu) / std::max(std::fabs((double)mu), 1.0));
+        worst_var2 = std::max(worst_var2, std::fabs((pr.amp - rt.ssq[c]) - var_ref) / std::max(std::fabs(var_ref), 1e-6 * pr.amp));
     }
     // ---- timing on the C2 shape
     Problem big = synthetic_problem(4096, 16384);
-    Result t = run_gpu(big, 4, 1), t2 = run_gpu(big, 4, 2), t4 = run_gpu(big, 4, 4);
+    Result t = run_gpu(big, 4, 1), t2 = run_gpu(big, 4, 2), t4 = run_gpu(big, 4, 4), tt = run_gpu(big, 4, 1, true);
     const double flops = 16384.0 * (4096.0 * 4096.0 + 2 * 4096.0);
     printf("{\"probe\": \"Ozaki int8 variance contraction, S=%d slices, tile %dx%d\", \"scaled_var_err_vs_80bit\": %.3e, "
            "\"mu_err\": %.3e, \"var_min\": %.3e, \"c2_chunk_ms_gemm\": %.4f, \"c2_chunk_ms_split_kstar\": %.4f, "
-           "\"fp64_equiv_tflops_gemm\": %.2f, \"fp64_equiv_tflops_incl_split\": %.2f, \"dmma_reference_tflops\": 35.2, \"cluster2_ms_gemm\": %.4f, \"a_sharing_order_ms_gemm\": %.4f, \"cluster_vs_plain_max_abs_diff\": %.3e}\n",
+           "\"fp64_equiv_tflops_gemm\": %.2f, \"fp64_equiv_tflops_incl_split\": %.2f, \"dmma_reference_tflops\": 35.2, \"cluster2_ms_gemm\": %.4f, \"a_sharing_order_ms_gemm\": %.4f, \"cluster_vs_plain_max_abs_diff\": %.3e, \"two_pass_128x128_ms_gemm\": %.4f, \"two_pass_scaled_var_err\": %.3e, \"two_pass_fp64_equiv_tflops\": %.2f}\n",
            S, TM, TN, worst_var, worst_mu, var_min, t.ms_gemm, t.ms_split_k, flops / (t.ms_gemm * 1e-3) / 1e12,
-           flops / ((t.ms_gemm + t.ms_split_k) * 1e-3) / 1e12, t2.ms_gemm, t4.ms_gemm, cl_diff);
+           flops / ((t.ms_gemm + t.ms_split_k) * 1e-3) / 1e12, t2.ms_gemm, t4.ms_gemm, cl_diff, tt.ms_gemm, worst_var2, flops / (tt.ms_gemm * 1e-3) / 1e12);
     return 0;
 }

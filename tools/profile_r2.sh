@@ -8,19 +8,21 @@ NCU="ncu --clock-control none"
 # launch lists (device time per launch; cold-cache, serialised: compare shares)
 timeout 600 $NCU --metrics gpu__time_duration.sum -c 1500 --csv --log-file $out/${tag}_launches_fit_score_grad.csv \
     python tools/profile_driver.py 4096 16 32768 > $out/${tag}_driver.log 2>&1
-# full captures
-cap() {  # name regex skip
-  timeout 600 $NCU --set full --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c 1 -f -o $out/${tag}_$1 \
+GPK_OZAKI=0 timeout 600 $NCU --metrics gpu__time_duration.sum -c 1500 --csv --log-file $out/${tag}_launches_fit_score_grad_fp64.csv \
+    python tools/profile_driver.py 4096 16 32768 > $out/${tag}_driver_fp64.log 2>&1
+cap() {  # name regex skip [env]
+  env $4 timeout 600 $NCU --set full --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c 1 -f -o $out/${tag}_$1 \
       python tools/profile_driver.py 4096 16 32768 > $out/${tag}_$1.log 2>&1
   tail -2 $out/${tag}_$1.log
 }
-cap cov_kbuild        'gpk_cov_tma_kernel<8>'   2      # third fit's K build (tri = 1)
-cap cov_kstar         'gpk_cov_tma_kernel<4>'   1      # K* of a look-ahead chunk (128 x 16 tiles, next to the GEMM)
-cap gemm_trailing_ws  'gpk_gemm_ws_kernel<0>'   70     # a trailing update of the third fit
-cap gemm_chain32      'gpk_gemm_nt_kernel<0, 1, 2>' 70 # 32-row panel solve / next-panel update
-cap chain_step        'gpk_chain_step_kernel'   70     # X(k): block row k+1 between two diagonal blocks
-cap diag_dmma         'gpk_potrf_diag_dmma_kernel' 70
-cap vargemm           'gpk_gemm_ws_kernel<1>'   2
-cap finish            'gpk_finish_kernel'       2
-cap grad_trace        'gpk_grad_trace_kernel'   0
+cap oz_vargemm        'gpk_oz_vargemm_kernel'   2      X=1           # int8 variance contraction (default scoring kernel)
+cap cov_oz            'gpk_cov_oz_kernel<4>'    1      X=1           # fused covariance builder + int8 digits (look-ahead chunk)
+cap cov_kbuild        'gpk_cov_tma_kernel<8>'   2      X=1           # third fit's K build (tri = 1)
+cap cov_kstar_fp64    'gpk_cov_tma_kernel<4>'   1      GPK_OZAKI=0   # fp64 K* of a look-ahead chunk
+cap vargemm_fp64      'gpk_gemm_ws_kernel<1>'   2      GPK_OZAKI=0   # fp64 DMMA variance contraction
+cap gemm_trailing_ws  'gpk_gemm_ws_kernel<0>'   70     X=1           # a trailing update of the third fit
+cap gemm_chain32      'gpk_gemm_nt_kernel<0, 1, 2>' 70 X=1           # 32-row panel solve / next-panel update
+cap diag_dmma         'gpk_potrf_diag_dmma_kernel' 70  X=1
+cap finish            'gpk_finish_kernel'       2      X=1
+cap grad_trace        'gpk_grad_trace_kernel'   0      X=1
 ls -la $out/*.ncu-rep

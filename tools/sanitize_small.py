@@ -34,6 +34,30 @@ for loader, diag in ((2, 4), (1, 3), (0, 2)):
     X2, y2 = np.vstack([X, rng.rand(10, D)]), np.concatenate([y, rng.rand(10)])
     print(" append", h.fit_append(X2, y2, 1e-3 + 1.25e-12, float(y2.mean())), h.predict(Xs[:64])[0][:2])
     h.close()
+# round-2 kernels: int8 contraction (fused and unfused digit builders, several chunks), persistent fp64 contraction,
+# split chain replayed from a CUDA graph, depth-2 trailing updates, fused multi-model scoring, raw posterior covariance
+Xb = rng.rand(2304, D)
+hs = []
+for opts in ({"ozaki": 1, "ozfused": 1}, {"ozaki": 1, "ozfused": 0}, {"ozaki": 0, "persist": 1},
+             {"ozaki": 0, "chainsplit": 1, "graph": 1, "depth2": 1}):
+    h = _lib.Handle(0)
+    for k, v in opts.items():
+        h.set_option(k, v)
+    h.set_option("chunk", 1024)
+    h.set_data(X, y)
+    h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
+    for _ in range(2):
+        ll = h.fit(1e-3 + 1.25e-12, float(y.mean()))
+    r = h.acq(Xb, _lib.ACQ_EI, float(y.min()), 0.0, want_values=True, want_moments=True)
+    t = h.timings()
+    print(opts, "fit", ll, "best", r["best_idx"], "oz launches", t["launches_ozaki"])
+    mu, cov = h.posterior_cov(Xs[:100])
+    hs.append(h)
+rm = _lib.acq_multi(hs[:3], Xs[:300], 0, _lib.ACQ_EI, [float(y.min())] * 3, 0.0, want_argmax=True)
+rp = _lib.acq_multi(hs[:3], Xs[:300], 1)
+print("multi", rm["best_idx"], rp["var"][:2])
+for h in hs:
+    h.close()
 h = _lib.moments_handle()
 print(h.acq_moments(rng.randn(100), rng.rand(100) + 0.1, _lib.ACQ_LOG_EI, 0.0, 0.0)[0][:3])
 print(h.reduce_models(rng.rand(4, 50), rng.rand(4, 50))[1][:3])
