@@ -72,6 +72,9 @@ const char* gpk_version(void);
  *               error-free 8 x 8 slice split of L^-1 and K* (gpk_ozaki.cuh); used while max |L^-1| < 64, otherwise the
  *               fp64 kernel runs [default; batches of >= 2048 candidates]; 0 = always fp64 DMMA.  The posterior mean
  *               never goes through the slices (fp64 K* alpha)
+ *   "oztile"    64 = int8 contraction in one pass, 128 x 64 tiles, 8 accumulators of 64 TMEM columns [default]; 128 = two
+ *               passes over the contraction (levels 0..3, then 4..7), 128 x 128 tiles, 4 accumulators of 128 columns
+ *               (kind::i8 reads both operands from shared memory: the wider MMA halves the operand bytes per product)
  *   "ozfused"   1 = with "ozaki": the covariance builder writes the int8 digits and the mean partials itself, no fp64
  *               K* in HBM [default: 3.35 vs 3.16 M EI/s at N = 4096]; 0 = fp64 K* + split kernel + mean dot
  *   "persist"   1 = persistent fp64 variance contraction (one CTA per SM, dynamic tile counter); 0 = one CTA per tile

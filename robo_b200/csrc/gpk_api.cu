@@ -50,6 +50,10 @@ struct gpk_handle {
     // variance contraction on the int8 tensor pipe (gpk_ozaki.cuh); 0 = fp64 DMMA kernels
     int ozaki = 1;
     DevBuf oz_Pq, oz_Kq, oz_Kq2, oz_eP, oz_emax, oz_mu, oz_mu2, oz_pmu2;
+    int oz_tile = 64;               // 64: one pass, 128 x 64 tiles (gpk_oz_vargemm_kernel); 128: two passes, 128 x 128 tiles
+    DevBuf oz_scratch;
+    CUtensorMap mapOzP32, mapOzK32, mapOzK32b;
+    long oz_rows32 = 0, oz_rows32b = 0;
     int oz_fused = 1;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
     long oz_linv_serial = -1;       // linv_serial the slices of L^-1 were made for
     long linv_serial = 0;           // bumped whenever L^-1 is (re)built
@@ -348,6 +352,7 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_CPASYNC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_CPASYNC, 1)));
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 1)));
     CK(cudaFuncSetAttribute(gpk_oz_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    CK(cudaFuncSetAttribute(gpk_oz2_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM));
     CK(cudaFuncSetAttribute(gpk_cov_oz_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_oz_smem_bytes(GPK_MAX_TERMS, 8)));
     CK(cudaFuncSetAttribute(gpk_cov_oz_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_oz_smem_bytes(GPK_MAX_TERMS, 4)));
     CK(cudaFuncSetAttribute(gpk_vargemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_SMEM));
@@ -696,15 +701,16 @@ int build_linv(gpk_handle* h) {
 }
 
 // int8 tensor map over S stacked slice matrices [S * rows][cols] (int8, K contiguous): box = 64 bytes x box_rows, 64B swizzle
-int make_oz_map(gpk_handle* h, CUtensorMap* map, void* base, long rows_total, long cols, int box_rows) {
+int make_oz_map(gpk_handle* h, CUtensorMap* map, void* base, long rows_total, long cols, int box_rows, int box_bytes = OZ_KB) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_err(h, "cuTensorMapEncodeTiled entry point not available"); return GPK_CUDA_ERROR; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows_total};
     cuuint64_t strides[1] = {(cuuint64_t)cols};
-    cuuint32_t box[2] = {(cuuint32_t)OZ_KB, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_err(h, "cuTensorMapEncodeTiled (int8 slices) failed with CUresult %d", (int)r); return GPK_CUDA_ERROR; }
     return GPK_OK;
 }
@@ -776,18 +782,17 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
     const bool oz_fused = use_oz && h->oz_fused && cov_tma(h);
     if (use_oz) {
         // slices of K* per chunk buffer: [S][cap][NP] int8; one exponent for the whole matrix (0 < k <= amp)
-        bool grew = false;
-        if ((rc = ensure(h, h->oz_Kq, (size_t)OZ_S * cap * NP, &grew))) return rc;
-        if (grew || h->oz_rows != cap) {
+        // (the tensor maps are re-encoded per call: a few microseconds, and they depend on the buffer, cap and NP)
+        if ((rc = ensure(h, h->oz_Kq, (size_t)OZ_S * cap * NP))) return rc;
+        if (h->overlap && (rc = ensure(h, h->oz_Kq2, (size_t)OZ_S * cap * NP))) return rc;
+        if (h->oz_tile == 128) {
+            if ((rc = ensure(h, h->oz_scratch, (size_t)OZ2_SCRATCH_SLOTS * OZ2_T * OZ2_T * 8))) return rc;
+            if ((rc = make_oz_map(h, &h->mapOzP32, h->oz_Pq.p, (long)OZ_S * NP, NP, OZ2_T, OZ2_KB))) return rc;
+            if ((rc = make_oz_map(h, &h->mapOzK32, h->oz_Kq.p, (long)OZ_S * cap, NP, OZ2_T, OZ2_KB))) return rc;
+            if (h->overlap && (rc = make_oz_map(h, &h->mapOzK32b, h->oz_Kq2.p, (long)OZ_S * cap, NP, OZ2_T, OZ2_KB))) return rc;
+        } else {
             if ((rc = make_oz_map(h, &h->mapOzK, h->oz_Kq.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
-            h->oz_rows = cap;
-        }
-        if (h->overlap) {
-            if ((rc = ensure(h, h->oz_Kq2, (size_t)OZ_S * cap * NP, &grew))) return rc;
-            if (grew || h->oz_rows2 != cap) {
-                if ((rc = make_oz_map(h, &h->mapOzK2, h->oz_Kq2.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
-                h->oz_rows2 = cap;
-            }
+            if (h->overlap && (rc = make_oz_map(h, &h->mapOzK2, h->oz_Kq2.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
         }
         if ((rc = ensure(h, h->oz_mu, (size_t)cap * 8))) return rc;
         if (h->overlap && (rc = ensure(h, h->oz_mu2, (size_t)cap * 8))) return rc;
@@ -899,7 +904,15 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         a.ldpart = cap;
         if (last) CK(cudaEventRecord(h->ev[10], h->stream));
         CK(cudaEventRecord(h->ev_g0[ci], h->stream));
-        if (use_oz) {
+        if (use_oz && h->oz_tile == 128) {
+            Oz2Args o;
+            o.nb = h->nb; o.ncb = (int)(mcp / OZ2_T); o.NP = (int)NP; o.rows = (int)cap;
+            o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
+            o.part_ssq = a.part_ssq; o.ldpart = a.ldpart; o.scratch = ptr<double>(h->oz_scratch);
+            gpk_oz2_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ2_SMEM, h->stream>>>(h->mapOzP32, second ? h->mapOzK32b : h->mapOzK32, o);
+            CKL();
+            h->oz_launches += 1;
+        } else if (use_oz) {
             OzArgs o;
             o.nb = h->nb; o.ncb = (int)(mcp / OZ_TN); o.NP = (int)NP; o.rows = (int)cap;
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
@@ -1013,7 +1026,7 @@ int gpk_destroy(gpk_handle* h) {
     DevBuf* bufs[] = {&h->Xrow, &h->Xt, &h->y, &h->Kbuf, &h->P, &h->Q, &h->W, &h->lower, &h->upper, &h->logdet_part,
                       &h->scal, &h->status, &h->jobs, &h->cand, &h->Kstar, &h->Kstar2, &h->cand2, &h->part_mu, &h->part_ssq, &h->out_mu,
                       &h->out_var, &h->out_acq, &h->block_best, &h->best, &h->nneg, &h->Vt, &h->cov, &h->XsT,
-                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt, &h->oz_Pq, &h->oz_Kq, &h->oz_Kq2, &h->oz_eP, &h->oz_emax, &h->oz_mu, &h->oz_mu2, &h->oz_pmu2,
+                      &h->tmpjobs, &h->alpha, &h->tmp1, &h->tmp2, &h->tmp3, &h->chain_cnt, &h->dprof, &h->Xts, &h->tile_cnt, &h->oz_Pq, &h->oz_Kq, &h->oz_Kq2, &h->oz_eP, &h->oz_emax, &h->oz_mu, &h->oz_mu2, &h->oz_pmu2, &h->oz_scratch,
                       &h->multi_cand, &h->multi_A, &h->multi_B, &h->multi_out, &h->multi_bb, &h->gather, &h->best_global};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -1055,6 +1068,11 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         h->maps_ok = false;
         h->mapKs_rows = 0;
         h->mapVt_rows = 0;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "oztile")) {
+        if (value != 64 && value != 128) BAD("oztile must be 64 (one pass, 128 x 64 tiles) or 128 (two passes, 128 x 128 tiles)");
+        h->oz_tile = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "ozfused")) {

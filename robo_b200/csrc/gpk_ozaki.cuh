@@ -231,6 +231,198 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------
+// Two-pass variant (option "oztile" = 128): 128 x 128 tiles, levels 0..3 in a first pass over the contraction, levels
+// 4..7 in a second.  kind::i8 reads BOTH operands from shared memory at 128 B / clock / SM (measured: a 128 x 128 x 32
+// MMA takes 65.9 cycles = 8 KB / 128 B), so the 128 x 64 MMAs of gpk_oz_vargemm_kernel are operand-fetch bound (6 KB ->
+// 48 cycles for 33 cycles of arithmetic); 128 x 128 is balanced.  TMEM holds 4 accumulators of 128 columns per pass;
+// the fp64 partial result of pass 1 waits in an L2-resident scratch tile (one per SM, indexed by %smid: 1 CTA / SM).
+// 32-byte k-blocks (SWIZZLE_32B), 3 stages of 64 KB (pass 1 fills 4 + 4 slice tiles of a stage, pass 2 all 8 + 8).
+// ---------------------------------------------------------------------------------------
+constexpr int OZ2_KB = 32;
+constexpr int OZ2_T = 128;
+constexpr int OZ2_SL = OZ2_T * OZ2_KB;              // 4096 bytes per slice tile
+constexpr int OZ2_STAGE = 16 * OZ2_SL;              // 65536
+constexpr int OZ2_NSTG = 3;
+constexpr int OZ2_SMEM = OZ2_NSTG * OZ2_STAGE + 1024 + 256 + 4 * OZ2_T * 8;
+constexpr int OZ2_SCRATCH_SLOTS = 256;              // >= %nsmid
+
+__device__ __forceinline__ uint64_t oz_desc32(uint32_t smem_addr) {       // K-major SWIZZLE_32B: 8 rows x 32 B atoms
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+
+struct Oz2Args {
+    int nb, ncb;                        // row blocks of L^-1, candidate blocks of 128
+    int NP, rows;
+    const int* eP; int eK;
+    double* part_ssq; long ldpart;
+    double* scratch;                    // [OZ2_SCRATCH_SLOTS][128][128]
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapK, const Oz2Args g)
+{
+    extern __shared__ unsigned char oz_raw[];
+    const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + OZ2_NSTG * OZ2_STAGE, bar_empty = bar_full + 8 * OZ2_NSTG;
+    const uint32_t bar_tfull = bar_empty + 8 * OZ2_NSTG, bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
+    const uint32_t red = base + OZ2_NSTG * OZ2_STAGE + 256;          // [4 lane groups][128 columns]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ib = g.nb - 1 - (int)blockIdx.x / g.ncb, cb = (int)blockIdx.x % g.ncb;
+    const int nkb = (ib + 1) * OZ2_T / OZ2_KB;
+
+    if (tid == 0) {
+        for (int s = 0; s < OZ2_NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                const int ns = pass == 0 ? 4 : 8;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % OZ2_NSTG;
+                    if (it >= OZ2_NSTG) oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((it / OZ2_NSTG - 1) & 1));
+                    const uint32_t st = base + s * OZ2_STAGE;
+                    mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(2 * ns * OZ2_SL));
+                    for (int q = 0; q < ns; ++q) {
+                        tma_load_2d(st + q * OZ2_SL, &mapP, kb * OZ2_KB, q * g.NP + ib * OZ2_T, bar_full + 8 * s);
+                        tma_load_2d(st + (8 + q) * OZ2_SL, &mapK, kb * OZ2_KB, q * g.rows + cb * OZ2_T, bar_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = oz_idesc(OZ2_T, OZ2_T);
+            int it = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1) {                                      // the epilogue has drained the first four accumulators
+                    oz_mbar_wait(bar_tempty, 0);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % OZ2_NSTG;
+                    oz_mbar_wait(bar_full + 8 * s, (uint32_t)((it / OZ2_NSTG) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * OZ2_STAGE;
+                    if (pass == 0) {
+#pragma unroll
+                        for (int lvl = 0; lvl < 4; ++lvl)
+#pragma unroll
+                            for (int a = 0; a <= lvl; ++a)
+                                oz_mma(tmem + (uint32_t)(lvl * OZ2_T), oz_desc32(st + a * OZ2_SL), oz_desc32(st + (8 + lvl - a) * OZ2_SL),
+                                       idesc, (uint32_t)((kb | a) != 0));
+                    } else {
+#pragma unroll
+                        for (int lvl = 4; lvl < 8; ++lvl)
+#pragma unroll
+                            for (int a = 0; a <= lvl; ++a)
+                                oz_mma(tmem + (uint32_t)((lvl - 4) * OZ2_T), oz_desc32(st + a * OZ2_SL),
+                                       oz_desc32(st + (8 + lvl - a) * OZ2_SL), idesc, (uint32_t)((kb | a) != 0));
+                    }
+                    oz_commit(bar_empty + 8 * s);
+                }
+                oz_commit(bar_tfull);
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        const int rl = lg * 32 + lane, row = ib * OZ2_T + rl;
+        const double rs = ldexp(1.0, g.eP[row] + g.eK);
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        double* sc = g.scratch + ((size_t)(smid % OZ2_SCRATCH_SLOTS) * OZ2_T + rl) * OZ2_T;
+        const uint32_t lane_base = tmem + ((uint32_t)(lg * 32) << 16);
+        // pass 1 result (levels 0..3) -> scratch
+        oz_mbar_wait(bar_tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < OZ2_T; c0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+            for (int lvl = 3; lvl >= 0; --lvl) {
+                uint32_t d[32];
+                oz_tmem_ld32(lane_base + (uint32_t)(lvl * OZ2_T + c0), d);
+                const double sf = ldexp(1.0, -7 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(sc + c0 + j) = make_double2(v[j], v[j + 1]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 64) mbar_arrive(bar_tempty);
+        // pass 2 result (levels 4..7) + scratch -> squares -> column sums
+        oz_mbar_wait(bar_tfull, 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < OZ2_T; c0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+            for (int lvl = 7; lvl >= 4; --lvl) {
+                uint32_t d[32];
+                oz_tmem_ld32(lane_base + (uint32_t)((lvl - 4) * OZ2_T + c0), d);
+                const double sf = ldexp(1.0, -7 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
+            }
+            double q2[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const double2 hi = *reinterpret_cast<const double2*>(sc + c0 + j);
+                const double x0 = (v[j] + hi.x) * rs, x1 = (v[j + 1] + hi.y) * rs;
+                q2[j] = x0 * x0;
+                q2[j + 1] = x1 * x1;
+            }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+                const bool up = (lane & w) != 0;
+#pragma unroll
+                for (int j = 0; j < w; ++j) {
+                    const double keep2 = up ? q2[j + w] : q2[j], send2 = up ? q2[j] : q2[j + w];
+                    q2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+                }
+            }
+            sts64(red + (uint32_t)((lg * OZ2_T + c0 + lane) * 8), q2[0]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - 64;
+        double s2 = 0.0;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) s2 += lds64(red + (uint32_t)((w4 * OZ2_T + et) * 8));
+        g.part_ssq[(long)ib * g.ldpart + cb * OZ2_T + et] = s2;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // Covariance builder for the int8 path: gpk_cov_tma_kernel's tile loop (TMA-staged pre-scaled train operand, thread =
 // 2 train points x CC candidates), but the fp64 K* never reaches HBM: every value k = amp * prod f(q) leaves as its
 // OZ_S 7-bit digits (Kq[s][cand][j], two adjacent int8 per thread and slice), and the posterior mean's share
