@@ -907,6 +907,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         if (use_oz && h->oz_tile == 128) {
             Oz2Args o;
             o.nb = h->nb; o.ncb = (int)(mcp / OZ2_T); o.NP = (int)NP; o.rows = (int)cap;
+            o.group = (int)std::min<long>(64, std::max<long>(2, ((long)64 << 20) / ((long)OZ2_T * NP * OZ_S)));
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart; o.scratch = ptr<double>(h->oz_scratch);
             gpk_oz2_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ2_SMEM, h->stream>>>(h->mapOzP32, second ? h->mapOzK32b : h->mapOzK32, o);
@@ -915,6 +916,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         } else if (use_oz) {
             OzArgs o;
             o.nb = h->nb; o.ncb = (int)(mcp / OZ_TN); o.NP = (int)NP; o.rows = (int)cap;
+            o.group = (int)std::min<long>(128, std::max<long>(4, ((long)64 << 20) / ((long)OZ_TN * NP * OZ_S)));
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart;
             gpk_oz_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ_SMEM, h->stream>>>(h->mapOzP, second ? h->mapOzK2 : h->mapOzK, o);

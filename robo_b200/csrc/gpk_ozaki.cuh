@@ -108,8 +108,21 @@ __global__ void gpk_oz_split_kernel(const double* __restrict__ A, long rows, lon
 }
 
 // ---- the contraction ----------------------------------------------------------------------------------------------
+// Tile order: candidate blocks are taken in groups of `group` blocks whose K* slices (group x TN x NP x 8 bytes, about
+// 64 MB) stay L2-resident while the group walks all row blocks of L^-1, longest contraction first; without the grouping
+// every row block re-reads the whole chunk's slices from HBM (measured: 9.0 GB per launch instead of ~1.1 GB).
+__device__ __forceinline__ void oz_tile_of(int id, int nb, int ncb, int group, int& ib, int& cb) {
+    const int full = ncb / group;
+    int grp = id / (nb * group), gsz = group;
+    if (grp >= full) { grp = full; gsz = ncb - full * group; }
+    id -= grp * nb * group;
+    ib = nb - 1 - id / gsz;
+    cb = grp * group + id % gsz;
+}
+
 struct OzArgs {
     int nb, ncb;                        // row blocks of L^-1 (128 rows), candidate blocks of the chunk (64 candidates)
+    int group;                          // candidate blocks per L2-resident group
     int NP, rows;                       // L^-1 is NP x NP; the K* slices have `rows` rows each
     const int* eP; int eK;
     double* part_ssq; long ldpart;
@@ -124,7 +137,8 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     const uint32_t tmem_slot = bar_tmem + 8;
     const uint32_t red = base + OZ_NSTG * OZ_STAGE + 256;            // [4 lane groups][64 columns] partial sums of V^2
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ib = g.nb - 1 - (int)blockIdx.x / g.ncb, cb = (int)blockIdx.x % g.ncb;     // longest contractions first
+    int ib, cb;
+    oz_tile_of((int)blockIdx.x, g.nb, g.ncb, g.group, ib, cb);
     const int nkb = (ib + 1) * OZ_TM / OZ_KB;                                             // lower triangle only
 
     if (tid == 0) {
@@ -258,6 +272,7 @@ __device__ __forceinline__ uint64_t oz_desc32(uint32_t smem_addr) {       // K-m
 
 struct Oz2Args {
     int nb, ncb;                        // row blocks of L^-1, candidate blocks of 128
+    int group;
     int NP, rows;
     const int* eP; int eK;
     double* part_ssq; long ldpart;
@@ -273,7 +288,8 @@ gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_co
     const uint32_t bar_tfull = bar_empty + 8 * OZ2_NSTG, bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
     const uint32_t red = base + OZ2_NSTG * OZ2_STAGE + 256;          // [4 lane groups][128 columns]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ib = g.nb - 1 - (int)blockIdx.x / g.ncb, cb = (int)blockIdx.x % g.ncb;
+    int ib, cb;
+    oz_tile_of((int)blockIdx.x, g.nb, g.ncb, g.group, ib, cb);
     const int nkb = (ib + 1) * OZ2_T / OZ2_KB;
 
     if (tid == 0) {

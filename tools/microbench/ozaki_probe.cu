@@ -135,7 +135,17 @@ __global__ void oz_split_kernel(const double* __restrict__ A, long rows, long co
 // ---------------------------------------------------------------------------------------
 // the contraction: one CTA per tile (row block ib, 64-candidate block cb), longest contractions first
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void oz_tile_of(int id, int nb, int ncb, int group, int& ib, int& cb) {
+    const int full = ncb / group;
+    int grp = id / (nb * group), gsz = group;
+    if (grp >= full) { grp = full; gsz = ncb - full * group; }
+    id -= grp * nb * group;
+    ib = nb - 1 - id / gsz;
+    cb = grp * group + id % gsz;
+}
+
 struct OzArgs {
+    int group;                          // candidate blocks per L2-resident group (0: plain order)
     int nb, ncb;                        // row blocks of P (128 rows), candidate blocks (64)
     int N, Mc;                          // P is N x N, K* is Mc x N
     const int* eP; const int* eK;       // exponents
@@ -159,7 +169,9 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = CL > 1 ? (int)cluster_rank() : 0;
     const int cid = (int)blockIdx.x / CL, cpr = g.ncb / CL;          // cluster id, clusters per row block
-    const int ib = g.nb - 1 - cid / cpr, cb = (cid % cpr) * CL + crank;
+    int ib, cb;
+    if (CL == 1 && g.group > 0) oz_tile_of((int)blockIdx.x, g.nb, g.ncb, g.group, ib, cb);
+    else { ib = g.nb - 1 - cid / cpr; cb = (cid % cpr) * CL + crank; }
     const int nkb = (ib + 1) * TM / KBY;                             // lower triangle: columns < (ib + 1) * 128
     const uint16_t cmask = (uint16_t)((1u << CL) - 1);
 
@@ -323,6 +335,7 @@ __device__ __forceinline__ void mbar_arrive1(uint32_t bar) {
 }
 
 struct Oz2Args {
+    int group;
     int nb, ncb;                        // row blocks of P, candidate blocks of 128
     int N, Mc;
     const int* eP; const int* eK;
@@ -339,7 +352,9 @@ oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
     const uint32_t bar_tfull = bar_empty + 8 * NSTG2, bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
     const uint32_t red = base + NSTG2 * STAGE2 + 256;                // [4 lane groups][128 columns]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ib = g.nb - 1 - (int)blockIdx.x / g.ncb, cb = (int)blockIdx.x % g.ncb;
+    int ib, cb;
+    if (g.group > 0) oz_tile_of((int)blockIdx.x, g.nb, g.ncb, g.group, ib, cb);
+    else { ib = g.nb - 1 - (int)blockIdx.x / g.ncb; cb = (int)blockIdx.x % g.ncb; }
     const int nkb = (ib + 1) * T2 / KB2;
 
     if (tid == 0) {
@@ -598,7 +613,7 @@ static void launch_oz(int grid, const CUtensorMap& mapP, const CUtensorMap& mapK
     CKC(cudaLaunchKernelEx(&cfg, oz_vargemm_kernel<CL, ORDER>, mapP, mapK, a));
 }
 
-static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = false) {
+static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = false, bool grouped = false) {
     const int N = pr.N, M = pr.M, nb = N / TM, ncb = M / TN;
     double *dP, *dK, *dz, *dpss, *dpmu, *dssq, *dmu;
     int8_t *dPq, *dKq;
@@ -624,8 +639,8 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = f
     double* dscr = nullptr;
     CKC(cudaMalloc(&dscr, (size_t)256 * T2 * T2 * 8));
     CKC(cudaFuncSetAttribute(oz2_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM));
-    Oz2Args a2; a2.nb = nb; a2.ncb = M / T2; a2.N = N; a2.Mc = M; a2.eP = deP; a2.eK = deK; a2.part_ssq = dpss; a2.scratch = dscr;
-    OzArgs a; a.nb = nb; a.ncb = ncb; a.N = N; a.Mc = M; a.eP = deP; a.eK = deK; a.z = dz; a.part_ssq = dpss; a.part_mu = dpmu;
+    Oz2Args a2; a2.group = grouped ? 16 : 0; a2.nb = nb; a2.ncb = M / T2; a2.N = N; a2.Mc = M; a2.eP = deP; a2.eK = deK; a2.part_ssq = dpss; a2.scratch = dscr;
+    OzArgs a; a.group = grouped ? 32 : 0; a.nb = nb; a.ncb = ncb; a.N = N; a.Mc = M; a.eP = deP; a.eK = deK; a.z = dz; a.part_ssq = dpss; a.part_mu = dpmu;
     cudaEvent_t e0, e1, e2;
     CKC(cudaEventCreate(&e0)); CKC(cudaEventCreate(&e1)); CKC(cudaEventCreate(&e2));
     Result res; res.ms_split_k = res.ms_gemm = 1e30f;
@@ -682,11 +697,15 @@ int main() {
     // ---- timing on the C2 shape
     Problem big = synthetic_problem(4096, 16384);
     Result t = run_gpu(big, 4, 1), t2 = run_gpu(big, 4, 2), t4 = run_gpu(big, 4, 4), tt = run_gpu(big, 4, 1, true);
+    Result tg = run_gpu(big, 4, 1, false, true), ttg = run_gpu(big, 4, 1, true, true);
+    Result rg = run_gpu(pr, 1, 1, false, true), rtg = run_gpu(pr, 1, 1, true, true);
+    double grp_diff = 0;
+    for (int c = 0; c < pr.M; ++c) grp_diff = std::max(grp_diff, std::max(std::fabs(r.ssq[c] - rg.ssq[c]), std::fabs(rt.ssq[c] - rtg.ssq[c])));
     const double flops = 16384.0 * (4096.0 * 4096.0 + 2 * 4096.0);
     printf("{\"probe\": \"Ozaki int8 variance contraction, S=%d slices, tile %dx%d\", \"scaled_var_err_vs_80bit\": %.3e, "
            "\"mu_err\": %.3e, \"var_min\": %.3e, \"c2_chunk_ms_gemm\": %.4f, \"c2_chunk_ms_split_kstar\": %.4f, "
-           "\"fp64_equiv_tflops_gemm\": %.2f, \"fp64_equiv_tflops_incl_split\": %.2f, \"dmma_reference_tflops\": 35.2, \"cluster2_ms_gemm\": %.4f, \"a_sharing_order_ms_gemm\": %.4f, \"cluster_vs_plain_max_abs_diff\": %.3e, \"two_pass_128x128_ms_gemm\": %.4f, \"two_pass_scaled_var_err\": %.3e, \"two_pass_fp64_equiv_tflops\": %.2f}\n",
+           "\"fp64_equiv_tflops_gemm\": %.2f, \"fp64_equiv_tflops_incl_split\": %.2f, \"dmma_reference_tflops\": 35.2, \"cluster2_ms_gemm\": %.4f, \"a_sharing_order_ms_gemm\": %.4f, \"cluster_vs_plain_max_abs_diff\": %.3e, \"two_pass_128x128_ms_gemm\": %.4f, \"two_pass_scaled_var_err\": %.3e, \"two_pass_fp64_equiv_tflops\": %.2f, \"grouped_ms_gemm\": %.4f, \"two_pass_grouped_ms_gemm\": %.4f, \"grouped_max_abs_diff\": %.3e}\n",
            S, TM, TN, worst_var, worst_mu, var_min, t.ms_gemm, t.ms_split_k, flops / (t.ms_gemm * 1e-3) / 1e12,
-           flops / ((t.ms_gemm + t.ms_split_k) * 1e-3) / 1e12, t2.ms_gemm, t4.ms_gemm, cl_diff, tt.ms_gemm, worst_var2, flops / (tt.ms_gemm * 1e-3) / 1e12);
+           flops / ((t.ms_gemm + t.ms_split_k) * 1e-3) / 1e12, t2.ms_gemm, t4.ms_gemm, cl_diff, tt.ms_gemm, worst_var2, flops / (tt.ms_gemm * 1e-3) / 1e12, tg.ms_gemm, ttg.ms_gemm, grp_diff);
     return 0;
 }
