@@ -48,7 +48,8 @@ sys.path.insert(0, ROOT)
 N_TRAIN, DIM = 4096, 16
 METRIC = "EI evals/sec (GP N=4096, D=16, fp64)"
 FP64_PEAK_TFLOPS = 37.0      # SURVEY.md section 8d "P64": B200 FP64 / FP64-tensor datasheet (296 TF per 8-GPU HGX)
-VARGEMM_NCU_CSV = os.path.join("profiles", "r01b_vargemm_ws_ncu_full_raw.csv")
+VARGEMM_NCU_CSV = os.path.join("profiles", "r02_vargemm_fp64_ncu_full_raw.csv")
+OZ_NCU_CSV = os.path.join("profiles", "r02_oz_vargemm_ncu_full_raw.csv")
 
 
 def train_problem(n=N_TRAIN, d=DIM):
@@ -554,19 +555,24 @@ def run_ours(args, rank, world, local_rank):
                   "launch_ms": gemm_ms, "launch_candidates": int(last_rows),
                   "launches_averaged": int(max(1, (M + rows - 1) // rows - 1)) if M > rows else 1}
     if used_int8:
-        # the contraction ran on the int8 tensor pipe: 36 exact slice-pair products per fp64 product over the lower
-        # triangle of L^-1 in 128-row blocks = 36 (N^2 + 128 N) int8 multiply-adds x 2 per candidate row
-        int8_ops = float(last_rows) * 36.0 * (N_TRAIN ** 2 + 128 * N_TRAIN)
+        # the contraction ran on the int8 tensor pipe: `pairs` exact slice-pair products per fp64 product over the lower
+        # triangle of L^-1 in 128-row blocks = pairs (N^2 + 128 N) int8 multiply-adds x 2 per candidate row
+        pairs = float(tim.get("ozaki_slice_pairs") or 28.0)
+        int8_ops = float(last_rows) * pairs * (N_TRAIN ** 2 + 128 * N_TRAIN)
+        oz_traffic = ncu_dram_bytes(OZ_NCU_CSV, "gpk_oz") if last_rows == 16384 else None
         int8_achieved = int8_ops / (gemm_ms * 1e-3) / 1e12
         roofline = dict(fp64_block, bound="tensor",
-                        kernel="gpk_oz_vargemm_kernel (L^-1 K*^T as 36 int8 slice products, tcgen05.mma kind::i8, TMEM "
-                               "accumulators, TMA-staged 64B-swizzled slices)",
+                        kernel="gpk_oz_vargemm_kernel (L^-1 K*^T as %d int8 slice-pair products, tcgen05.mma kind::i8, TMEM "
+                               "accumulators, TMA-staged swizzled slices)" % int(pairs),
                         achieved=int8_achieved, peak=int8_peak, unit="TFLOP/s", frac=int8_achieved / int8_peak,
                         ops="int8 multiply-accumulate counted as 2 ops (TOP/s)",
                         peak_source="measured live on this GPU: tcgen05.mma kind::i8 128x128x32 issue rate from shared "
                                     "memory (gpk_measure_int8_peak); nominal dense int8 = 4500 TOP/s (2x the bf16 figure of "
                                     "MEASURED_PEAKS.json's datasheet)",
-                        traffic=None, traffic_source="no ncu capture of the int8 kernel committed yet")
+                        traffic=oz_traffic,
+                        traffic_source="read at run time from the committed capture %s (ncu --set full, one 16384-candidate "
+                                       "launch); algorithmic minimum = %d slices x (L^-1 lower triangle 8.4 MB + K* 67 MB) "
+                                       "read once" % (OZ_NCU_CSV, 7))
     else:
         roofline = dict(fp64_block, bound="tensor",
                         kernel="%s (L^-1 K*^T contraction, fp64 DMMA, warp-specialised TMA)"

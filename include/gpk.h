@@ -290,7 +290,8 @@ int gpk_get_z(gpk_handle* h, double* z /* n */);
  * out[8] = variance-GEMM launches so far,
  * out[9] = total kernel launches so far,
  * out[10] = of those, launches of the int8 (Ozaki) contraction; out[11] = largest row exponent of L^-1 seen by it
- * (option "ozaki"); out[12] = option "persist"; out[13..15] reserved (zero). */
+ * (option "ozaki"); out[12] = option "persist"; out[13] = int8 slice-pair products the int8 contraction spends per
+ * fp64 product (28: 7 balanced base-256 digits per operand); out[14..15] reserved (zero). */
 int gpk_get_timings(gpk_handle* h, double* out16);
 /* diagnostics of the blocked diagonal-block kernel (option "diagprof" = 1): clock64() stamps of the last
  * launched block: out[0] start, out[1] tiles loaded, out[2+2p] panel p factorised + solved, out[3+2p] panel p's

@@ -797,8 +797,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         if ((rc = ensure(h, h->oz_mu, (size_t)cap * 8))) return rc;
         if (h->overlap && (rc = ensure(h, h->oz_mu2, (size_t)cap * 8))) return rc;
         if (h->overlap && (rc = ensure(h, h->oz_pmu2, (size_t)h->nb * cap * 8))) return rc;
-        frexp(h->spec.amp, &oz_eK);
-        oz_eK += 1;
+        oz_eK = oz_exponent(h->spec.amp);
     }
     if (d_best == nullptr) d_best = ptr<BestPair>(h->best);
     if (d_nneg == nullptr) d_nneg = ptr<unsigned long long>(h->nneg);
@@ -2412,6 +2411,7 @@ int gpk_get_timings(gpk_handle* h, double* out /* 16 */) {
     out[10] = h->oz_launches;
     out[11] = (double)h->oz_emax_host;
     out[12] = (double)h->persist;
+    out[13] = (double)OZ_PAIRS;
     return GPK_OK;
 }
 

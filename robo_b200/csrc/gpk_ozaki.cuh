@@ -3,14 +3,16 @@
 // B200's fp64 ceiling is the DMMA / DFMA issue rate (37 TFLOP/s); its 5th-generation tensor cores have no fp64 kind,
 // but tcgen05.mma kind::i8 (s8 x s8 -> s32, accumulators in TMEM) runs two orders of magnitude faster.  An
 // error-free (Ozaki) split turns the fp64 product V = L^-1 K*^T into exact integer products:
-//   P  = L^-1 :  P[i][k]  ~ 2^eP[i] sum_s Pq[s][i][k] 2^(-7 (s+1))     per-row exponent, S = 8 slices of 7 signed bits
-//   K*        :  K*[c][k] ~ 2^eK    sum_t Kq[t][c][k] 2^(-7 (t+1))     one exponent (0 < k <= amp)
-//   V[i][c] = 2^(eP[i] + eK) sum_lvl 2^(-7 (lvl + 2)) sum_{s + t = lvl} <Pq[s][i][:], Kq[t][c][:]>      (lvl < S)
-// The 36 slice pairs with s + t < 8 carry 56 bits of each operand relative to its row maximum; the pairs of one level
-// share one int32 accumulator ((lvl + 1) K 127^2 < 2^31 for K <= 16384), so a 128 x 64 tile keeps 8 accumulators of
-// 64 columns = all 512 TMEM columns.  Per 64-byte k-block the CTA stages all 8 + 8 slice tiles (96 KB, TMA, 64B
-// swizzle) once and issues 72 MMAs (128 x 64 x 32) on them: 26 bytes of operand traffic per 1000 MMA cycles.
-// Measured accuracy (tools/ozaki_study.py, tools/microbench/ozaki_probe.cu): posterior variance within 3e-12 .. 3e-11
+//   P  = L^-1 :  P[i][k]  ~ 2^eP[i] sum_s Pq[s][i][k] 2^(-8 (s+1))     per-row exponent, S = 7 balanced base-256 digits
+//   K*        :  K*[c][k] ~ 2^eK    sum_t Kq[t][c][k] 2^(-8 (t+1))     one exponent (0 < k <= amp)
+//   V[i][c] = 2^(eP[i] + eK) sum_lvl 2^(-8 (lvl + 2)) sum_{s + t = lvl} <Pq[s][i][:], Kq[t][c][:]>      (lvl < S)
+// Digits are BALANCED (-128 .. 127, oz_digit below), so every int8 carries 8 bits: 7 slices hold 56 bits of each
+// operand relative to its row maximum and the triangle s + t < 7 has 28 slice pairs.  (The first version cut 7-bit
+// truncated digits: 8 slices, 36 pairs, for a LARGER error — tools/ozaki_study.py prints both.)  The pairs of one
+// level share one int32 accumulator ((lvl + 1) K 128^2 < 2^31 for K <= 16384), so a 128 x 64 tile keeps 7 accumulators
+// of 64 columns = 448 of the 512 TMEM columns.  Per 64-byte k-block the CTA stages all 7 + 7 slice tiles (84 KB, TMA,
+// 64B swizzle) once and issues 56 MMAs (128 x 64 x 32) on them.
+// Measured accuracy (tools/ozaki_study.py, tools/microbench/ozaki_probe.cu): posterior variance within 4e-13 .. 4e-11
 // (scaled as in the parity tests) of an 80-bit reference while max |L^-1| < 64; the handle falls back to the fp64
 // DMMA kernel when the factor is worse conditioned than that (eP > OZ_MAX_EXP) or N > 16384.
 //
@@ -19,20 +21,39 @@
 // Output: the per-row-block partial sums part_ssq [nb][ld] the DMMA kernel writes too.  The posterior MEAN does not go
 // through the slices: mu - mean = K* alpha is one fp64 dot product of length N per candidate (gpk_rowdot_kernel on the
 // fp64 K* that is built anyway, alpha = L^-T z once per fit), like george's own K* alpha; sum_i V_i z_i would put the
-// slices' 5e-12 error in front of |z| ~ 1e2 and cost the 1e-10 tolerance on the mean (measured: 1.1e-10 .. 1.9e-10).
+// slices' error in front of |z| ~ 1e2 and cost the 1e-10 tolerance on the mean (measured: 1.1e-10 .. 1.9e-10).
 #pragma once
 #include "gpk_gemm.cuh"
 
-constexpr int OZ_S = 8;                       // slices per operand
+constexpr int OZ_S = 7;                       // slices (balanced base-256 digits) per operand
+constexpr int OZ_PAIRS = OZ_S * (OZ_S + 1) / 2;   // slice pairs with s + t < OZ_S
 constexpr int OZ_TM = 128, OZ_TN = 64;        // tile: 128 rows of L^-1 x 64 candidates
 constexpr int OZ_KB = 64;                     // k-block: 64 int8 = one 64-byte swizzle row
 constexpr int OZ_UK = 32;                     // K of one kind::i8 MMA
 constexpr int OZ_NSTG = 2;
 constexpr int OZ_A_SLICE = OZ_TM * OZ_KB, OZ_B_SLICE = OZ_TN * OZ_KB;
-constexpr int OZ_STAGE = OZ_S * (OZ_A_SLICE + OZ_B_SLICE);               // 98304 bytes
+constexpr int OZ_STAGE = OZ_S * (OZ_A_SLICE + OZ_B_SLICE);               // 86016 bytes
 constexpr int OZ_THREADS = 192;
 constexpr int OZ_SMEM = OZ_NSTG * OZ_STAGE + 1024 + 256 + 4 * OZ_TN * 8;
 constexpr int OZ_MAX_EXP = 7;                 // row exponents above this (|L^-1| >= 64): use the fp64 kernel
+
+// Exponent e with |x| 2^-e inside the balanced digit interval [-128/255, 127/255) for every |x| <= amax: normally
+// frexp's exponent + 1 (|x| 2^-e in [1/4, 1/2)), one more when the largest mantissa is within 0.004 of 1.
+__host__ __device__ inline int oz_exponent(double amax) {
+    if (!(amax > 0.0)) return 0;
+    int ex;
+    const double m = frexp(amax, &ex);
+    return ex + 1 + (m * 128.0 >= 127.49 ? 1 : 0);
+}
+// next balanced base-256 digit of the remainder v (v in [-128/255, 127/255)): v <- 256 v - d with d = floor(256 v +
+// 128/255) in -128 .. 127; the new remainder lies in the same interval, so every digit fits an int8 and the S-digit
+// sum is within 0.502 * 256^-S of the value.  All operations are exact in fp64 (power-of-two scaling, integer part).
+__device__ __forceinline__ int oz_digit(double& v) {
+    v *= 256.0;
+    const double t = fmin(fmax(floor(v + 128.0 / 255.0), -128.0), 127.0);
+    v -= t;
+    return (int)t;
+}
 
 __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
@@ -74,7 +95,7 @@ __device__ __forceinline__ void oz_tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
 }
 
 // ---- operand split ------------------------------------------------------------------------------------------------
-// per-row exponent e[r] with |A[r][:]| / 2^e[r] < 1/2; emax receives the maximum over the rows (atomicMax)
+// per-row exponent e[r] = oz_exponent(max |A[r][:]|); emax receives the maximum over the rows (atomicMax)
 __global__ void gpk_oz_rowexp_kernel(const double* __restrict__ A, long ld, int cols, int* __restrict__ e, int* __restrict__ emax) {
     const long r = blockIdx.x;
     double m = 0.0;
@@ -84,14 +105,13 @@ __global__ void gpk_oz_rowexp_kernel(const double* __restrict__ A, long ld, int 
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]); __syncthreads(); }
     if (threadIdx.x == 0) {
-        int ex = 0;
-        if (sh[0] > 0.0) { frexp(sh[0], &ex); ex += 1; }
+        const int ex = oz_exponent(sh[0]);
         e[r] = ex;
         atomicMax(emax, ex);
     }
 }
-// q[s][row][col] (slices slice_stride bytes apart) = the s-th 7-bit digit of A[row][col] / 2^e; e = erow[row] or (erow == NULL) e0.
-// One thread per element; truncation towards zero keeps |q| <= 127 and the remainder's sign.
+// q[s][row][col] (slices slice_stride bytes apart) = the s-th balanced base-256 digit of A[row][col] / 2^e; e = erow[row]
+// or (erow == NULL) e0.  One thread per element.
 __global__ void gpk_oz_split_kernel(const double* __restrict__ A, long rows, long ld, const int* __restrict__ erow, int e0,
                                     int8_t* __restrict__ q, long slice_stride) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,12 +119,7 @@ __global__ void gpk_oz_split_kernel(const double* __restrict__ A, long rows, lon
     const long r = idx / ld;
     double v = ldexp(A[idx], -(erow ? erow[r] : e0));
 #pragma unroll
-    for (int s = 0; s < OZ_S; ++s) {
-        v *= 128.0;
-        const double t = trunc(v);
-        v -= t;
-        q[(long)s * slice_stride + idx] = (int8_t)(int)t;
-    }
+    for (int s = 0; s < OZ_S; ++s) q[(long)s * slice_stride + idx] = (int8_t)oz_digit(v);
 }
 
 // ---- the contraction ----------------------------------------------------------------------------------------------
@@ -192,7 +207,7 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
                     }
                 oz_commit(bar_empty + 8 * s);                        // the stage is free once these MMAs have read it
             }
-            oz_commit(bar_tmem);                                     // all eight accumulators are final
+            oz_commit(bar_tmem);                                     // all OZ_S accumulators are final
         }
     } else {
         // epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. + 31 = tile rows
@@ -210,7 +225,7 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
             for (int lvl = OZ_S - 1; lvl >= 0; --lvl) {              // least significant level first
                 uint32_t d[32];
                 oz_tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(lvl * OZ_TN + half * 32), d);
-                const double sc = ldexp(1.0, -7 * (lvl + 2));
+                const double sc = ldexp(1.0, -8 * (lvl + 2));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sc, v[j]);
             }
@@ -246,11 +261,11 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
 
 // ---------------------------------------------------------------------------------------
 // Two-pass variant (option "oztile" = 128): 128 x 128 tiles, levels 0..3 in a first pass over the contraction, levels
-// 4..7 in a second.  kind::i8 reads BOTH operands from shared memory at 128 B / clock / SM (measured: a 128 x 128 x 32
+// 4..6 in a second.  kind::i8 reads BOTH operands from shared memory at 128 B / clock / SM (measured: a 128 x 128 x 32
 // MMA takes 65.9 cycles = 8 KB / 128 B), so the 128 x 64 MMAs of gpk_oz_vargemm_kernel are operand-fetch bound (6 KB ->
 // 48 cycles for 33 cycles of arithmetic); 128 x 128 is balanced.  TMEM holds 4 accumulators of 128 columns per pass;
 // the fp64 partial result of pass 1 waits in an L2-resident scratch tile (one per SM, indexed by %smid: 1 CTA / SM).
-// 32-byte k-blocks (SWIZZLE_32B), 3 stages of 64 KB (pass 1 fills 4 + 4 slice tiles of a stage, pass 2 all 8 + 8).
+// 32-byte k-blocks (SWIZZLE_32B), 3 stages of 64 KB (pass 1 fills 4 + 4 slice tiles of a stage, pass 2 all 7 + 7).
 // ---------------------------------------------------------------------------------------
 constexpr int OZ2_KB = 32;
 constexpr int OZ2_T = 128;
@@ -313,7 +328,7 @@ gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_co
         if (lane == 0) {
             int it = 0;
             for (int pass = 0; pass < 2; ++pass) {
-                const int ns = pass == 0 ? 4 : 8;
+                const int ns = pass == 0 ? 4 : OZ_S;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % OZ2_NSTG;
                     if (it >= OZ2_NSTG) oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((it / OZ2_NSTG - 1) & 1));
@@ -349,7 +364,7 @@ gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_co
                                        idesc, (uint32_t)((kb | a) != 0));
                     } else {
 #pragma unroll
-                        for (int lvl = 4; lvl < 8; ++lvl)
+                        for (int lvl = 4; lvl < OZ_S; ++lvl)
 #pragma unroll
                             for (int a = 0; a <= lvl; ++a)
                                 oz_mma(tmem + (uint32_t)((lvl - 4) * OZ2_T), oz_desc32(st + a * OZ2_SL),
@@ -380,7 +395,7 @@ gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_co
             for (int lvl = 3; lvl >= 0; --lvl) {
                 uint32_t d[32];
                 oz_tmem_ld32(lane_base + (uint32_t)(lvl * OZ2_T + c0), d);
-                const double sf = ldexp(1.0, -7 * (lvl + 2));
+                const double sf = ldexp(1.0, -8 * (lvl + 2));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
             }
@@ -390,7 +405,7 @@ gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_co
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid == 64) mbar_arrive(bar_tempty);
-        // pass 2 result (levels 4..7) + scratch -> squares -> column sums
+        // pass 2 result (levels 4..6) + scratch -> squares -> column sums
         oz_mbar_wait(bar_tfull, 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -399,10 +414,10 @@ gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.0;
 #pragma unroll 1
-            for (int lvl = 7; lvl >= 4; --lvl) {
+            for (int lvl = OZ_S - 1; lvl >= 4; --lvl) {
                 uint32_t d[32];
                 oz_tmem_ld32(lane_base + (uint32_t)((lvl - 4) * OZ2_T + c0), d);
-                const double sf = ldexp(1.0, -7 * (lvl + 2));
+                const double sf = ldexp(1.0, -8 * (lvl + 2));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
             }
@@ -441,7 +456,7 @@ gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_co
 // ---------------------------------------------------------------------------------------
 // Covariance builder for the int8 path: gpk_cov_tma_kernel's tile loop (TMA-staged pre-scaled train operand, thread =
 // 2 train points x CC candidates), but the fp64 K* never reaches HBM: every value k = amp * prod f(q) leaves as its
-// OZ_S 7-bit digits (Kq[s][cand][j], two adjacent int8 per thread and slice), and the posterior mean's share
+// OZ_S balanced base-256 digits (Kq[s][cand][j], two adjacent int8 per thread and slice), and the posterior mean's share
 // sum_j k(c, j) alpha_j of this 128-column tile is reduced over the 64 threads of a candidate group and written to
 // part_mu[tile][cand] (summed in fixed order by gpk_finish_kernel: deterministic).  Replaces K* store (8 B / element)
 // + split kernel (8 B read, 8 B written) + mean dot (8 B read) by 8 B written per element.
@@ -532,10 +547,7 @@ gpk_cov_oz_kernel(const __grid_constant__ CUtensorMap mapX, const KSpec ks, int 
         int8_t* dst = Kq + ci * ldq + j0;
 #pragma unroll
         for (int s2 = 0; s2 < OZ_S; ++s2) {
-            r0 *= 128.0; r1 *= 128.0;
-            const double t0 = trunc(r0), t1 = trunc(r1);
-            r0 -= t0; r1 -= t1;
-            const int i0 = (int)t0, i1 = (int)t1;
+            const int i0 = oz_digit(r0), i1 = oz_digit(r1);
             *reinterpret_cast<uint16_t*>(dst + (long)s2 * slice_stride) = (uint16_t)((i0 & 0xFF) | ((i1 & 0xFF) << 8));
         }
         // mean share of this tile: reduce over the 64 threads (2 warps) of the candidate group, fixed order

@@ -910,7 +910,7 @@ def test_incremental_refit_through_the_model_classes():
 
 # --------------------------------------------------------------------------- int8 tensor-pipe contraction (option "ozaki")
 def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
-    """Option "ozaki": V = L^-1 K*^T as 36 exact int8 slice products (tcgen05 kind::i8) instead of fp64 DMMA.  Same
+    """Option "ozaki": V = L^-1 K*^T as 28 exact int8 slice products (tcgen05 kind::i8) instead of fp64 DMMA.  Same
     posterior moments / EI within the north_star tolerances against the oracle AND against the fp64 kernel; the handle
     must fall back to fp64 when the factor is too ill-conditioned for 8 slices (max |L^-1| >= 64)."""
     from robo_b200 import _lib

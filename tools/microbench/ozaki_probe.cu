@@ -1,14 +1,14 @@
 // ozaki_probe.cu — stand-alone prototype for VERDICT item 8: the variance contraction
 //     V = L^-1 K*^T ,  ssq_c = sum_i V_ic^2 ,  mu_c = sum_i V_ic z_i
 // on the int8 tensor pipe (tcgen05.mma kind::i8, TMEM accumulators) through an error-free (Ozaki) split of both
-// fp64 operands into S slices of 7 signed bits, instead of fp64 DMMA.
+// fp64 operands into S = 7 balanced base-256 digits (-128 .. 127), instead of fp64 DMMA.
 //
-//   P  (N x N, lower triangular, fp64)  ->  Pq[s][i][k] int8,  P[i][k]  ~ 2^eP[i] sum_s Pq[s][i][k] 2^(-7 (s+1))
-//   K* (M x N, fp64, 0 < k <= amp)      ->  Kq[t][c][k] int8,  K*[c][k] ~ 2^eK    sum_t Kq[t][c][k] 2^(-7 (t+1))
-//   V[i][c] = 2^(eP[i] + eK) sum_lvl 2^(-7 (lvl + 2)) sum_{s + t = lvl} <Pq[s][i][:], Kq[t][c][:]>      (lvl < S)
+//   P  (N x N, lower triangular, fp64)  ->  Pq[s][i][k] int8,  P[i][k]  ~ 2^eP[i] sum_s Pq[s][i][k] 2^(-8 (s+1))
+//   K* (M x N, fp64, 0 < k <= amp)      ->  Kq[t][c][k] int8,  K*[c][k] ~ 2^eK    sum_t Kq[t][c][k] 2^(-8 (t+1))
+//   V[i][c] = 2^(eP[i] + eK) sum_lvl 2^(-8 (lvl + 2)) sum_{s + t = lvl} <Pq[s][i][:], Kq[t][c][:]>      (lvl < S)
 // Every slice-pair product is an exact int32 GEMM; the pairs of one level share one TMEM accumulator
-// ((lvl + 1) * K * 127^2 < 2^31 for K <= 4096, S <= 8), so a 128 x 64 tile keeps S = 8 accumulators of 64 columns = all
-// 512 TMEM columns.  Per 64-byte k-block the CTA stages all 8 + 8 slices (96 KB) once and issues 36 pairs x 2 MMAs.
+// ((lvl + 1) * K * 128^2 < 2^31 for K <= 16384, S = 7), so a 128 x 64 tile keeps S = 7 accumulators of 64 columns = 448
+// of the 512 TMEM columns.  Per 64-byte k-block the CTA stages all 7 + 7 slices (84 KB) once and issues 28 pairs x 2 MMAs.
 //
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..5 = epilogue (TMEM -> fp64, scales,
 // column reductions).  Checked against an 80-bit CPU reference on real GP data (Matern-5/2, N = 1024) and timed on a
@@ -26,7 +26,7 @@
 
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { printf("{\"error\": \"%s -> %s (line %d)\"}\n", #call, cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
-constexpr int S = 8;                    // slices per operand
+constexpr int S = 7;                    // slices per operand
 constexpr int TM = 128, TN = 64;        // tile: 128 rows of P x 64 candidates
 constexpr int KBY = 64;                 // k-block in bytes (= int8 elements): one 64B-swizzle atom row
 constexpr int UMMA_K = 32;
@@ -105,8 +105,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
 
 // ---------------------------------------------------------------------------------------
 // operand split: one thread per element.  mode 0: per-row exponent from e[row]; mode 1: one exponent e[0] for all rows.
-// q[s][row][col] (ld = cols), truncation towards zero keeps |q| <= 127 and the remainder's sign.
+// q[s][row][col] (ld = cols), balanced base-256 digits.
 // ---------------------------------------------------------------------------------------
+// exponent e with |x| 2^-e in the balanced digit interval [-128/255, 127/255) for all |x| <= amax
+__host__ __device__ inline int oz_exponent(double amax) {
+    if (!(amax > 0.0)) return 0;
+    int ex;
+    const double m = frexp(amax, &ex);
+    return ex + 1 + (m * 128.0 >= 127.49 ? 1 : 0);
+}
 __global__ void oz_rowmax_kernel(const double* __restrict__ A, long rows, long cols, int* __restrict__ e) {
     const long r = blockIdx.x;
     double m = 0.0;
@@ -115,7 +122,7 @@ __global__ void oz_rowmax_kernel(const double* __restrict__ A, long rows, long c
     sh[threadIdx.x] = m;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]); __syncthreads(); }
-    if (threadIdx.x == 0) { int ex = 0; if (sh[0] > 0.0) { frexp(sh[0], &ex); ex += 1; } e[r] = ex; }     // |A| / 2^e < 1/2
+    if (threadIdx.x == 0) e[r] = oz_exponent(sh[0]);
 }
 __global__ void oz_split_kernel(const double* __restrict__ A, long rows, long cols, const int* __restrict__ e, int mode,
                                 int8_t* __restrict__ q) {
@@ -125,8 +132,8 @@ __global__ void oz_split_kernel(const double* __restrict__ A, long rows, long co
     double v = ldexp(A[idx], -(mode == 0 ? e[r] : e[0]));
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        v *= 128.0;
-        const double t = trunc(v);
+        v *= 256.0;
+        const double t = fmin(fmax(floor(v + 128.0 / 255.0), -128.0), 127.0);     // balanced digit, remainder stays in range
         v -= t;
         q[(long)s * rows * cols + idx] = (int8_t)(int)t;
     }
@@ -170,7 +177,7 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     const int crank = CL > 1 ? (int)cluster_rank() : 0;
     const int cid = (int)blockIdx.x / CL, cpr = g.ncb / CL;          // cluster id, clusters per row block
     int ib, cb;
-    if (CL == 1 && g.group > 0) oz_tile_of((int)blockIdx.x, g.nb, g.ncb, g.group, ib, cb);
+    if (g.group > 0) { int cc; oz_tile_of(cid, g.nb, cpr, g.group / CL, ib, cc); cb = cc * CL + crank; }   // groups of clusters
     else { ib = g.nb - 1 - cid / cpr; cb = (cid % cpr) * CL + crank; }
     const int nkb = (ib + 1) * TM / KBY;                             // lower triangle: columns < (ib + 1) * 128
     const uint16_t cmask = (uint16_t)((1u << CL) - 1);
@@ -261,7 +268,7 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
             for (int lvl = S - 1; lvl >= 0; --lvl) {                 // least significant level first
                 uint32_t d[32];
                 tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(lvl * TN + half * 32), d);
-                const double sc = ldexp(1.0, -7 * (lvl + 2));
+                const double sc = ldexp(1.0, -8 * (lvl + 2));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sc, v[j]);
             }
@@ -378,7 +385,7 @@ oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
         if (lane == 0) {
             int it = 0;
             for (int pass = 0; pass < 2; ++pass) {
-                const int ns = pass == 0 ? 4 : 8;
+                const int ns = pass == 0 ? 4 : S;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % NSTG2;
                     if (it >= NSTG2) mbar_wait(bar_empty + 8 * s, (uint32_t)((it / NSTG2 - 1) & 1));
@@ -414,7 +421,7 @@ oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
                                         idesc, (uint32_t)((kb | a) != 0));
                     } else {
 #pragma unroll
-                        for (int lvl = 4; lvl < 8; ++lvl)
+                        for (int lvl = 4; lvl < S; ++lvl)
 #pragma unroll
                             for (int a = 0; a <= lvl; ++a)
                                 umma_i8(tmem + (uint32_t)((lvl - 4) * T2), umma_desc32(st + a * SL2), umma_desc32(st + (8 + lvl - a) * SL2),
@@ -445,7 +452,7 @@ oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
             for (int lvl = 3; lvl >= 0; --lvl) {
                 uint32_t d[32];
                 tmem_ld32(lane_base + (uint32_t)(lvl * T2 + c0), d);
-                const double sf = ldexp(1.0, -7 * (lvl + 2));
+                const double sf = ldexp(1.0, -8 * (lvl + 2));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
             }
@@ -464,10 +471,10 @@ oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.0;
 #pragma unroll 1
-            for (int lvl = 7; lvl >= 4; --lvl) {
+            for (int lvl = S - 1; lvl >= 4; --lvl) {
                 uint32_t d[32];
                 tmem_ld32(lane_base + (uint32_t)((lvl - 4) * T2 + c0), d);
-                const double sf = ldexp(1.0, -7 * (lvl + 2));
+                const double sf = ldexp(1.0, -8 * (lvl + 2));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
             }
@@ -626,7 +633,7 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = f
     CKC(cudaMemcpy(dP, pr.P.data(), (size_t)N * N * 8, cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(dK, pr.Ks.data(), (size_t)M * N * 8, cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(dz, pr.z.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
-    int ek = 0; frexp(pr.amp, &ek); ek += 1;                    // 0 < K* <= amp: one exponent for the whole matrix
+    int ek = oz_exponent(pr.amp);                    // 0 < K* <= amp: one exponent for the whole matrix
     CKC(cudaMemcpy(deK, &ek, 4, cudaMemcpyHostToDevice));
     oz_rowmax_kernel<<<N, 256>>>(dP, N, N, deP);
     oz_split_kernel<<<(unsigned)(((size_t)N * N + 255) / 256), 256>>>(dP, N, N, deP, 0, dPq);
@@ -698,14 +705,18 @@ int main() {
     Problem big = synthetic_problem(4096, 16384);
     Result t = run_gpu(big, 4, 1), t2 = run_gpu(big, 4, 2), t4 = run_gpu(big, 4, 4), tt = run_gpu(big, 4, 1, true);
     Result tg = run_gpu(big, 4, 1, false, true), ttg = run_gpu(big, 4, 1, true, true);
+    Result tg2 = run_gpu(big, 4, 2, false, true), tg4 = run_gpu(big, 4, 4, false, true);
+    Result rg2 = run_gpu(pr, 1, 2, false, true), rg4 = run_gpu(pr, 1, 4, false, true);
+    double grp_cl_diff = 0;
+    for (int c = 0; c < pr.M; ++c) grp_cl_diff = std::max(grp_cl_diff, std::max(std::fabs(r.ssq[c] - rg2.ssq[c]), std::fabs(r.ssq[c] - rg4.ssq[c])));
     Result rg = run_gpu(pr, 1, 1, false, true), rtg = run_gpu(pr, 1, 1, true, true);
     double grp_diff = 0;
     for (int c = 0; c < pr.M; ++c) grp_diff = std::max(grp_diff, std::max(std::fabs(r.ssq[c] - rg.ssq[c]), std::fabs(rt.ssq[c] - rtg.ssq[c])));
     const double flops = 16384.0 * (4096.0 * 4096.0 + 2 * 4096.0);
     printf("{\"probe\": \"Ozaki int8 variance contraction, S=%d slices, tile %dx%d\", \"scaled_var_err_vs_80bit\": %.3e, "
            "\"mu_err\": %.3e, \"var_min\": %.3e, \"c2_chunk_ms_gemm\": %.4f, \"c2_chunk_ms_split_kstar\": %.4f, "
-           "\"fp64_equiv_tflops_gemm\": %.2f, \"fp64_equiv_tflops_incl_split\": %.2f, \"dmma_reference_tflops\": 35.2, \"cluster2_ms_gemm\": %.4f, \"a_sharing_order_ms_gemm\": %.4f, \"cluster_vs_plain_max_abs_diff\": %.3e, \"two_pass_128x128_ms_gemm\": %.4f, \"two_pass_scaled_var_err\": %.3e, \"two_pass_fp64_equiv_tflops\": %.2f, \"grouped_ms_gemm\": %.4f, \"two_pass_grouped_ms_gemm\": %.4f, \"grouped_max_abs_diff\": %.3e}\n",
+           "\"fp64_equiv_tflops_gemm\": %.2f, \"fp64_equiv_tflops_incl_split\": %.2f, \"dmma_reference_tflops\": 35.2, \"cluster2_ms_gemm\": %.4f, \"a_sharing_order_ms_gemm\": %.4f, \"cluster_vs_plain_max_abs_diff\": %.3e, \"two_pass_128x128_ms_gemm\": %.4f, \"two_pass_scaled_var_err\": %.3e, \"two_pass_fp64_equiv_tflops\": %.2f, \"grouped_ms_gemm\": %.4f, \"two_pass_grouped_ms_gemm\": %.4f, \"grouped_max_abs_diff\": %.3e, \"grouped_cluster2_ms_gemm\": %.4f, \"grouped_cluster4_ms_gemm\": %.4f, \"grouped_cluster_max_abs_diff\": %.3e}\n",
            S, TM, TN, worst_var, worst_mu, var_min, t.ms_gemm, t.ms_split_k, flops / (t.ms_gemm * 1e-3) / 1e12,
-           flops / ((t.ms_gemm + t.ms_split_k) * 1e-3) / 1e12, t2.ms_gemm, t4.ms_gemm, cl_diff, tt.ms_gemm, worst_var2, flops / (tt.ms_gemm * 1e-3) / 1e12, tg.ms_gemm, ttg.ms_gemm, grp_diff);
+           flops / ((t.ms_gemm + t.ms_split_k) * 1e-3) / 1e12, t2.ms_gemm, t4.ms_gemm, cl_diff, tt.ms_gemm, worst_var2, flops / (tt.ms_gemm * 1e-3) / 1e12, tg.ms_gemm, ttg.ms_gemm, grp_diff, tg2.ms_gemm, tg4.ms_gemm, grp_cl_diff);
     return 0;
 }

@@ -2,12 +2,14 @@
 """Numerical study for VERDICT item 8: could the variance contraction V = L^-1 K*^T run on the int8 tensor pipe
 (tcgen05 kind::i8, TMEM accumulators) through an Ozaki-style error-free split and still meet sigma^2 <= 1e-10?
 
-Emulation (exact): operand rows / columns are scaled by a power of two, cut into S slices of 7 signed bits
-(|q| <= 127, what an int8 MMA takes), every slice-pair product is an exact integer GEMM (emulated with fp64 BLAS on
-integer-valued matrices: K * 127^2 < 2^53), and the pair products are combined in fp64 with their scales, most
-significant first, keeping the pairs with s + t <= S + 1 (the usual triangle).  Reported: the posterior-variance error
-against an 80-bit reference, in the units of the parity tests (|dvar| / max(var, 1e-6 k**)), for the plain fp64 path
-and for S = 6..12; plus the int8 products per fp64 product that S implies.
+Emulation (exact): operand rows / columns are scaled by a power of two and cut into S int8 digits, every slice-pair
+product is an exact integer GEMM (emulated with fp64 BLAS on integer-valued matrices: K * 128^2 < 2^53), and the pair
+products are combined in fp64 with their scales, least significant level first, keeping the pairs with s + t < S (the
+usual triangle).  Two digit schemes: "base128" = 7-bit digits by truncation (|q| <= 127; the first version of the
+kernel, S = 8, 36 pairs) and "base256" = BALANCED base-256 digits (-128 .. 127, 8 bits per int8; what gpk_ozaki.cuh
+ships: S = 7, 28 pairs).  Reported: the posterior-variance error against an 80-bit reference, in the units of the
+parity tests (|dvar| / max(var, 1e-6 k**)), for the plain fp64 path and for both schemes over a range of S, plus the
+int8 products per fp64 product that S implies.
 
 CPU only (numpy); run: python tools/ozaki_study.py [N] [M]
 """
@@ -35,10 +37,28 @@ def split(A, S, axis, global_max=None):
     return Q, e
 
 
-def ozaki_matmul(P, Kt, S, amp=None):
+def split256(A, S, axis, global_max=None):
+    """A ~ sum_s Q_s * 2^(e - 8 (s+1)) with balanced digits -128 <= Q_s <= 127 (oz_exponent / oz_digit of gpk_ozaki.cuh):
+    remainders stay in [-128/255, 127/255), so S digits carry 8 S bits."""
+    mx = np.max(np.abs(A), axis=axis, keepdims=True) if global_max is None else np.full((1, 1), float(global_max))
+    m, ex = np.frexp(mx)
+    e = np.where(mx > 0, ex + 1 + (m * 128.0 >= 127.49), 0).astype(float)
+    r = A / np.exp2(e)
+    Q = []
+    for _ in range(S):
+        r = r * 256.0
+        q = np.clip(np.floor(r + 128.0 / 255.0), -128, 127)
+        r = r - q
+        Q.append(q)
+    return Q, e
+
+
+def ozaki_matmul(P, Kt, S, amp=None, base=128):
     """P (n x k) @ Kt (k x m) from S x S slices, pairs with s + t <= S - 1 (0-based)."""
-    QP, eP = split(P, S, axis=1)
-    QK, eK = split(Kt, S, axis=0, global_max=amp)
+    bits = 7.0 if base == 128 else 8.0
+    sp = split if base == 128 else split256
+    QP, eP = sp(P, S, axis=1)
+    QK, eK = sp(Kt, S, axis=0, global_max=amp)
     out = np.zeros((P.shape[0], Kt.shape[1]))
     pairs = 0
     for lvl in range(S - 1, -1, -1):                  # least significant level first, then upwards
@@ -47,7 +67,8 @@ def ozaki_matmul(P, Kt, S, amp=None):
             t = lvl - s
             acc += QP[s] @ QK[t]                      # exact: integers < 2^53
             pairs += 1
-        out += acc * np.exp2(-7.0 * (lvl + 2))
+        assert np.abs(acc).max() < 2.0 ** 31             # what the int32 TMEM accumulator of a level must hold
+        out += acc * np.exp2(-bits * (lvl + 2))
     return out * np.exp2(eP) * np.exp2(eK), pairs
 
 
@@ -77,11 +98,12 @@ def main():
         print("== %s: N=%d, M=%d, cond(K) ~ %.1e, max|P| = %.1e, var in [%.2e, %.2e]"
               % (label, N, M, np.linalg.cond(K), np.abs(P).max(), var_ref.min(), var_ref.max()))
         print("   fp64 (DMMA-equivalent) path: scaled variance error %.2e" % err64)
-        for S in range(6, 13):
-            V, pairs = ozaki_matmul(P, Ks.T, S, amp)
-            err = np.max(np.abs((amp - np.einsum("ij,ij->j", V, V)) - var_ref) / den)
-            print("   S = %2d slices/operand: %3d int8 GEMMs per fp64 GEMM, scaled variance error %.2e  %s"
-                  % (S, pairs, err, "<= 1e-10" if err <= 1e-10 else ""))
+        for base, rng in ((128, range(6, 11)), (256, range(5, 10))):
+            for S in rng:
+                V, pairs = ozaki_matmul(P, Ks.T, S, amp, base)
+                err = np.max(np.abs((amp - np.einsum("ij,ij->j", V, V)) - var_ref) / den)
+                print("   base%d S = %2d slices/operand: %3d int8 GEMMs per fp64 GEMM, scaled variance error %.2e  %s"
+                      % (base, S, pairs, err, "<= 1e-10" if err <= 1e-10 else ""))
 
 
 if __name__ == "__main__":
