@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <string>
 
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { printf("{\"error\": \"%s -> %s (line %d)\"}\n", #call, cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
@@ -312,6 +313,176 @@ oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     if (CL > 1) cluster_sync_all();                                  // no CTA leaves while peers may still signal / write it
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+
+// =======================================================================================
+// v7: CTA PAIR (tcgen05 cta_group::2).  kind::i8 reads both operands from shared memory (128 B / clock / SM), so the
+// 128 x 64 MMAs above are operand-fetch bound (6 KB -> 48 clocks for 33 clocks of arithmetic).  A pair of CTAs on one
+// TPC issues ONE MMA of M = 256 (two row blocks of L^-1, 128 rows in each CTA's shared memory and TMEM) x N candidates;
+// each CTA stages only HALF of the K* slice tiles (N / 2 candidate rows) and the pair's tensor cores share them:
+// 4 KB + N/2 x 32 B per CTA and MMA.  The leader CTA (rank 0) issues the MMAs and owns the "full" barriers (both CTAs'
+// TMA loads signal them: cp.async.bulk.tensor ... cta_group::2 with the barrier address mapped to rank 0); "empty" and
+// "accumulators final" arrive in both CTAs through the multicast commit.  `swap` selects which CTA stages which half
+// of the candidate rows (checked at run time against the single-CTA kernel).
+// =======================================================================================
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int NT>                                   // candidates per pair tile
+struct PairCfg {
+    static constexpr int BH = NT / 2;               // K* rows staged per CTA
+    static constexpr int BH_SLICE = BH * KBY;
+    static constexpr int STAGE = S * (A_SLICE + BH_SLICE);
+    static constexpr int NSTG = (3 * STAGE + 8192 <= 227 * 1024) ? 3 : 2;
+    static constexpr int SMEM = NSTG * STAGE + 1024 + 256 + 4 * NT * 2 * 8;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapKh, const OzArgs g, const int swap)
+{
+    using C = PairCfg<NT>;
+    extern __shared__ unsigned char raw[];
+    const uint32_t base = (s_u32(raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + C::NSTG * C::STAGE, bar_empty = bar_full + 8 * C::NSTG, bar_tmem = bar_empty + 8 * C::NSTG;
+    const uint32_t tmem_slot = bar_tmem + 8;
+    const uint32_t red = base + C::NSTG * C::STAGE + 256;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int crank = (int)cluster_rank();
+    int ibp, cb;
+    oz_tile_of((int)blockIdx.x / 2, g.nb / 2, g.ncb, g.group, ibp, cb);
+    const int ib = 2 * ibp + crank;
+    const int nkb = (2 * ibp + 2) * TM / KBY;                        // both CTAs run the longer of the two contractions
+                                                                     // (the upper triangle of L^-1 is stored as zeros)
+    if (tid == 0) {
+        for (int s = 0; s < C::NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                              // both CTAs' barriers and TMEM exist
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int crow = cb * NT + (crank ^ swap) * C::BH;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::NSTG;
+                if (kb >= C::NSTG) mbar_wait(bar_empty + 8 * s, (uint32_t)((kb / C::NSTG - 1) & 1));
+                const uint32_t st = base + s * C::STAGE;
+                const uint32_t lbar = map_to_rank(bar_full + 8 * s, 0);
+                if (crank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * C::STAGE);      // both CTAs' bytes land on this barrier
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    tma_2d_pair(st + q * A_SLICE, &mapP, kb * KBY, q * g.N + ib * TM, lbar);
+                    tma_2d_pair(st + S * A_SLICE + q * C::BH_SLICE, &mapKh, kb * KBY, q * g.Mc + crow, lbar);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc = umma_idesc(2 * TM, NT);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::NSTG;
+                mbar_wait(bar_full + 8 * s, (uint32_t)((kb / C::NSTG) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * C::STAGE;
+#pragma unroll
+                for (int lvl = 0; lvl < S; ++lvl)
+#pragma unroll
+                    for (int a = 0; a <= lvl; ++a) {
+                        const int b = lvl - a;
+#pragma unroll
+                        for (int k = 0; k < KBY / UMMA_K; ++k)
+                            umma_i8_pair(tmem + (uint32_t)(lvl * NT), umma_desc64(st + a * A_SLICE + k * UMMA_K),
+                                         umma_desc64(st + S * A_SLICE + b * C::BH_SLICE + k * UMMA_K), idesc,
+                                         (uint32_t)((kb | a | k) != 0));
+                    }
+                umma_commit_pair(bar_empty + 8 * s);                 // frees stage s in BOTH CTAs
+            }
+            umma_commit_pair(bar_tmem);                              // accumulators final, both CTAs' epilogues go
+        }
+    } else {
+        const int lg = warp & 3;
+        const int row = ib * TM + lg * 32 + lane;
+        mbar_wait(bar_tmem, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const double zr = g.z[row];
+        const double rs = ldexp(1.0, g.eP[row] + g.eK[0]);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+            for (int lvl = S - 1; lvl >= 0; --lvl) {
+                uint32_t d[32];
+                tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(lvl * NT + c0), d);
+                const double sc = ldexp(1.0, -8 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sc, v[j]);
+            }
+            double q2[32], qm[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const double x = v[j] * rs; q2[j] = x * x; qm[j] = x * zr; }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+                const bool up = (lane & w) != 0;
+#pragma unroll
+                for (int j = 0; j < w; ++j) {
+                    const double keep2 = up ? q2[j + w] : q2[j], send2 = up ? q2[j] : q2[j + w];
+                    const double keepm = up ? qm[j + w] : qm[j], sendm = up ? qm[j] : qm[j + w];
+                    q2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+                    qm[j] = keepm + __shfl_xor_sync(0xffffffffu, sendm, w);
+                }
+            }
+            const uint32_t slot = red + (uint32_t)(((lg * NT) + c0 + lane) * 16);
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(slot), "d"(q2[0]), "d"(qm[0]) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - 64;
+        if (et < NT) {
+            double s2 = 0.0, sm = 0.0;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+                double a, b;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(red + (uint32_t)((w4 * NT + et) * 16)));
+                s2 += a; sm += b;
+            }
+            g.part_ssq[(long)ib * g.Mc + cb * NT + et] = s2;
+            g.part_mu[(long)ib * g.Mc + cb * NT + et] = sm;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                              // the peer's shared memory / TMEM are no longer in use
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
 }
 
 // =======================================================================================
@@ -620,6 +791,22 @@ static void launch_oz(int grid, const CUtensorMap& mapP, const CUtensorMap& mapK
     CKC(cudaLaunchKernelEx(&cfg, oz_vargemm_kernel<CL, ORDER>, mapP, mapK, a));
 }
 
+template <int NT>
+static void launch_pair(int nb, int ncb, const CUtensorMap& mapP, const CUtensorMap& mapKh, const OzArgs& a, int swap) {
+    using C = PairCfg<NT>;
+    CKC(cudaFuncSetAttribute(oz_pair_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(nb * ncb); cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = 0;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CKC(cudaLaunchKernelEx(&cfg, oz_pair_kernel<NT>, mapP, mapKh, a, swap));
+}
+
+// cl: 1 / 2 = cluster size of the multicast variant, 4 = A-sharing issue order, 10 / 11 = CTA pair (cta_group::2), K* halves
+// in rank order / swapped
 static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = false, bool grouped = false) {
     const int N = pr.N, M = pr.M, nb = N / TM, ncb = M / TN;
     double *dP, *dK, *dz, *dpss, *dpmu, *dssq, *dmu;
@@ -641,6 +828,8 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = f
     CUtensorMap mapP, mapK, mapP32, mapK32;
     make_map(&mapP, dPq, (long)S * N, N, TM);
     make_map(&mapK, dKq, (long)S * M, N, TN);
+    CUtensorMap mapKh;
+    make_map(&mapKh, dKq, (long)S * M, N, TN / 2);
     make_map32(&mapP32, dPq, (long)S * N, N);
     make_map32(&mapK32, dKq, (long)S * M, N);
     double* dscr = nullptr;
@@ -656,6 +845,7 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = f
         oz_split_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(dK, M, N, deK, 1, dKq);
         CKC(cudaEventRecord(e1));
         if (two_pass) oz2_vargemm_kernel<<<nb * (M / T2), OZ_THREADS, OZ2_SMEM>>>(mapP32, mapK32, a2);
+        else if (cl >= 10) launch_pair<TN>(nb, ncb, mapP, mapKh, a, cl - 10);
         else if (cl == 1) launch_oz<1, 0>(nb * ncb, mapP, mapK, a);
         else if (cl == 2) launch_oz<2, 0>(nb * ncb, mapP, mapK, a);
         else launch_oz<1, 1>(nb * ncb, mapP, mapK, a);            // cl == 4 slot reused: A-sharing issue order
@@ -675,11 +865,30 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = f
     return res;
 }
 
-int main() {
+int main(int argc, char** argv) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
     g_encode = (EncodeFn)p;
+    if (argc > 1 && std::string(argv[1]) == "pair") {
+        // CTA-pair kernel alone (its own process: a protocol mistake would hang, not just miscompute)
+        Problem pr = gp_problem(1024, 256, 16);
+        Result r = run_gpu(pr, 1, 1, false, true), p0 = run_gpu(pr, 1, 10, false, true), p1 = run_gpu(pr, 1, 11, false, true);
+        double d0 = 0, d1 = 0;
+        for (int c = 0; c < pr.M; ++c) {
+            d0 = std::max(d0, std::fabs(r.ssq[c] - p0.ssq[c]) + std::fabs(r.mu[c] - p0.mu[c]));
+            d1 = std::max(d1, std::fabs(r.ssq[c] - p1.ssq[c]) + std::fabs(r.mu[c] - p1.mu[c]));
+        }
+        const int swap = d1 < d0 ? 1 : 0;
+        Problem big = synthetic_problem(4096, 16384);
+        Result t = run_gpu(big, 4, 1, false, true), tp = run_gpu(big, 4, 10 + swap, false, true);
+        double dbig = 0;
+        for (int c = 0; c < big.M; ++c) dbig = std::max(dbig, std::fabs(t.ssq[c] - tp.ssq[c]));
+        printf("{\"probe\": \"CTA pair (cta_group::2) 256x%d, S=%d\", \"max_abs_diff_halves_in_rank_order\": %.3e, "
+               "\"max_abs_diff_halves_swapped\": %.3e, \"swap\": %d, \"single_cta_ms_gemm\": %.4f, \"pair_ms_gemm\": %.4f, "
+               "\"c2_max_abs_diff\": %.3e}\n", TN, S, d0, d1, swap, t.ms_gemm, tp.ms_gemm, dbig);
+        return 0;
+    }
     // ---- accuracy on real GP data (N = 1024, D = 16, 256 candidates) against an 80-bit CPU contraction
     Problem pr = gp_problem(1024, 256, 16);
     Result r = run_gpu(pr, 1, 1), r2 = run_gpu(pr, 1, 2), r4 = run_gpu(pr, 1, 4), rt = run_gpu(pr, 1, 1, true);
