@@ -260,6 +260,171 @@ gpk_oz_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------
+// CTA-pair variant (option "ozpair" = 1): tcgen05 cta_group::2.  A pair of CTAs on one TPC issues ONE MMA of M = 256
+// (two row blocks of L^-1: 128 rows in each CTA's shared memory, 128 lanes in each CTA's TMEM) x 64 candidates; each CTA
+// stages only HALF of the K* slice tiles (32 candidate rows) and the pair's tensor cores share them, so the operand
+// fetch per CTA and MMA drops from 6 KB to 5 KB (40 clocks for 33 of arithmetic) and the L2 -> SM traffic per tile by
+// 17 %; 3 stages of 70 KB fit.  The leader CTA (cluster rank 0) issues the MMAs and owns the "full" barriers: both
+// CTAs' TMA loads (cp.async.bulk.tensor ... cta_group::2) complete on rank 0's barrier; "stage free" and "accumulators
+// final" arrive in both CTAs through the multicast commit.  Both CTAs run the longer of the two contractions (the
+// upper triangle of L^-1 is stored as zeros).  Needs an even number of row blocks.
+// ---------------------------------------------------------------------------------------
+constexpr int OZP_BH = OZ_TN / 2;                                   // K* rows staged per CTA
+constexpr int OZP_BH_SLICE = OZP_BH * OZ_KB;                        // 2048
+constexpr int OZP_STAGE = OZ_S * (OZ_A_SLICE + OZP_BH_SLICE);       // 71680
+constexpr int OZP_NSTG = 3;
+constexpr int OZP_SMEM = OZP_NSTG * OZP_STAGE + 1024 + 256 + 4 * OZ_TN * 8;
+constexpr int OZP_SWAP = 0;                                         // which CTA of the pair stages which half (probe-checked)
+
+__device__ __forceinline__ uint32_t oz_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t oz_map_to_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void oz_tma_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void oz_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void oz_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+gpk_oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapKh, const OzArgs g)
+{
+    extern __shared__ unsigned char oz_raw[];
+    const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + OZP_NSTG * OZP_STAGE, bar_empty = bar_full + 8 * OZP_NSTG, bar_tmem = bar_empty + 8 * OZP_NSTG;
+    const uint32_t tmem_slot = bar_tmem + 8;
+    const uint32_t red = base + OZP_NSTG * OZP_STAGE + 256;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int crank = (int)oz_cluster_rank();
+    int ibp, cb;
+    oz_tile_of((int)blockIdx.x / 2, g.nb / 2, g.ncb, g.group, ibp, cb);
+    const int ib = 2 * ibp + crank;
+    const int nkb = (2 * ibp + 2) * OZ_TM / OZ_KB;
+
+    if (tid == 0) {
+        for (int s = 0; s < OZP_NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tmem, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    oz_cluster_sync();                                               // both CTAs' barriers and TMEM exist
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int crow = cb * OZ_TN + (crank ^ OZP_SWAP) * OZP_BH;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % OZP_NSTG;
+                if (kb >= OZP_NSTG) oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((kb / OZP_NSTG - 1) & 1));
+                const uint32_t st = base + s * OZP_STAGE;
+                const uint32_t lbar = oz_map_to_rank(bar_full + 8 * s, 0);
+                if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * OZP_STAGE);       // both CTAs' bytes land here
+#pragma unroll
+                for (int q = 0; q < OZ_S; ++q) {
+                    oz_tma_pair(st + q * OZ_A_SLICE, &mapP, kb * OZ_KB, q * g.NP + ib * OZ_TM, lbar);
+                    oz_tma_pair(st + OZ_S * OZ_A_SLICE + q * OZP_BH_SLICE, &mapKh, kb * OZ_KB, q * g.rows + crow, lbar);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc = oz_idesc(2 * OZ_TM, OZ_TN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % OZP_NSTG;
+                oz_mbar_wait(bar_full + 8 * s, (uint32_t)((kb / OZP_NSTG) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * OZP_STAGE;
+#pragma unroll
+                for (int lvl = 0; lvl < OZ_S; ++lvl)
+#pragma unroll
+                    for (int a = 0; a <= lvl; ++a) {
+                        const int b = lvl - a;
+#pragma unroll
+                        for (int k = 0; k < OZ_KB / OZ_UK; ++k)
+                            oz_mma_pair(tmem + (uint32_t)(lvl * OZ_TN), oz_desc(st + a * OZ_A_SLICE + k * OZ_UK),
+                                        oz_desc(st + OZ_S * OZ_A_SLICE + b * OZP_BH_SLICE + k * OZ_UK), idesc,
+                                        (uint32_t)((kb | a | k) != 0));
+                    }
+                oz_commit_pair(bar_empty + 8 * s);                   // frees stage s in both CTAs
+            }
+            oz_commit_pair(bar_tmem);                                // accumulators final: both CTAs' epilogues go
+        }
+    } else {
+        const int lg = warp & 3;
+        const int row = ib * OZ_TM + lg * 32 + lane;
+        const double rs = ldexp(1.0, g.eP[row] + g.eK);
+        oz_mbar_wait(bar_tmem, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+            for (int lvl = OZ_S - 1; lvl >= 0; --lvl) {
+                uint32_t d[32];
+                oz_tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(lvl * OZ_TN + half * 32), d);
+                const double sc = ldexp(1.0, -8 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sc, v[j]);
+            }
+            double q2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const double x = v[j] * rs; q2[j] = x * x; }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+                const bool up = (lane & w) != 0;
+#pragma unroll
+                for (int j = 0; j < w; ++j) {
+                    const double keep2 = up ? q2[j + w] : q2[j], send2 = up ? q2[j] : q2[j + w];
+                    q2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+                }
+            }
+            sts64(red + (uint32_t)(((lg * OZ_TN) + half * 32 + lane) * 8), q2[0]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - 64;
+        if (et < OZ_TN) {
+            double s2 = 0.0;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) s2 += lds64(red + (uint32_t)((w4 * OZ_TN + et) * 8));
+            g.part_ssq[(long)ib * g.ldpart + cb * OZ_TN + et] = s2;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    oz_cluster_sync();                                               // the peer's shared memory and TMEM are no longer in use
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // Two-pass variant (option "oztile" = 128): 128 x 128 tiles, levels 0..3 in a first pass over the contraction, levels
 // 4..6 in a second.  kind::i8 reads BOTH operands from shared memory at 128 B / clock / SM (measured: a 128 x 128 x 32
 // MMA takes 65.9 cycles = 8 KB / 128 B), so the 128 x 64 MMAs of gpk_oz_vargemm_kernel are operand-fetch bound (6 KB ->

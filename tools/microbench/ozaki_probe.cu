@@ -485,6 +485,202 @@ oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
 }
 
+
+// =======================================================================================
+// v8: CTA pair AND two passes: M = 256 x N = 128 per pair.  Per CTA and MMA 4 KB (own 128 rows of an L^-1 slice) + 2 KB
+// (half of the 128 K* rows) of operand fetch for 66 clocks of arithmetic: tensor-bound, where the single-CTA 128 x 64
+// tile is fetch-bound (48 clocks for 33).  TMEM holds 128 columns per level, so the levels go in two passes over the
+// contraction: first the three least significant (4..6, all 7 slices), drained to fp64 in an L2-resident scratch tile,
+// then levels 0..3 (slices 0..3) added on top in the same least-significant-first order as the one-pass kernel.
+// =======================================================================================
+constexpr int P2_NT = 128;
+constexpr int P2_BH = P2_NT / 2;                    // 64 K* rows per CTA
+constexpr int P2_BH_SLICE = P2_BH * KBY;            // 4096
+constexpr int P2_STAGE = S * (A_SLICE + P2_BH_SLICE);   // 86016
+constexpr int P2_NSTG = 2;
+constexpr int P2_SMEM = P2_NSTG * P2_STAGE + 1024 + 256 + 4 * P2_NT * 2 * 8;
+constexpr int P2_LOW = 4;                           // levels P2_LOW .. S-1 in pass 0, 0 .. P2_LOW-1 in pass 1
+
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapKh, const OzArgs g,
+                double* __restrict__ scratch, const int swap)
+{
+    extern __shared__ unsigned char raw[];
+    const uint32_t base = (s_u32(raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + P2_NSTG * P2_STAGE, bar_empty = bar_full + 8 * P2_NSTG;
+    const uint32_t bar_tfull = bar_empty + 8 * P2_NSTG, bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
+    const uint32_t red = base + P2_NSTG * P2_STAGE + 256;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int crank = (int)cluster_rank();
+    int ibp, cb;
+    oz_tile_of((int)blockIdx.x / 2, g.nb / 2, g.ncb, g.group, ibp, cb);     // g.ncb = candidate blocks of 128 here
+    const int ib = 2 * ibp + crank;
+    const int nkb = (2 * ibp + 2) * TM / KBY;
+
+    if (tid == 0) {
+        for (int s = 0; s < P2_NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 2);                                   // one arrival per CTA of the pair (used on rank 0)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int crow = cb * P2_NT + (crank ^ swap) * P2_BH;
+            int it = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                const int ns = pass == 0 ? S : P2_LOW;              // slices needed: levels >= 4 touch all, levels < 4 only 0..3
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P2_NSTG;
+                    if (it >= P2_NSTG) mbar_wait(bar_empty + 8 * s, (uint32_t)((it / P2_NSTG - 1) & 1));
+                    const uint32_t st = base + s * P2_STAGE;
+                    const uint32_t lbar = map_to_rank(bar_full + 8 * s, 0);
+                    if (crank == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)(2 * ns * (A_SLICE + P2_BH_SLICE)));
+                    for (int q = 0; q < ns; ++q) {
+                        tma_2d_pair(st + q * A_SLICE, &mapP, kb * KBY, q * g.N + ib * TM, lbar);
+                        tma_2d_pair(st + S * A_SLICE + q * P2_BH_SLICE, &mapKh, kb * KBY, q * g.Mc + crow, lbar);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc = umma_idesc(2 * TM, P2_NT);
+            int it = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1) {                                     // both CTAs' epilogues have drained the low levels
+                    mbar_wait(bar_tempty, 0);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P2_NSTG;
+                    mbar_wait(bar_full + 8 * s, (uint32_t)((it / P2_NSTG) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * P2_STAGE;
+                    if (pass == 0) {
+#pragma unroll
+                        for (int lvl = P2_LOW; lvl < S; ++lvl)
+#pragma unroll
+                            for (int a = 0; a <= lvl; ++a)
+#pragma unroll
+                                for (int k = 0; k < KBY / UMMA_K; ++k)
+                                    umma_i8_pair(tmem + (uint32_t)((lvl - P2_LOW) * P2_NT), umma_desc64(st + a * A_SLICE + k * UMMA_K),
+                                                 umma_desc64(st + S * A_SLICE + (lvl - a) * P2_BH_SLICE + k * UMMA_K), idesc,
+                                                 (uint32_t)((kb | a | k) != 0));
+                    } else {
+#pragma unroll
+                        for (int lvl = 0; lvl < P2_LOW; ++lvl)
+#pragma unroll
+                            for (int a = 0; a <= lvl; ++a)
+#pragma unroll
+                                for (int k = 0; k < KBY / UMMA_K; ++k)
+                                    umma_i8_pair(tmem + (uint32_t)(lvl * P2_NT), umma_desc64(st + a * A_SLICE + k * UMMA_K),
+                                                 umma_desc64(st + S * A_SLICE + (lvl - a) * P2_BH_SLICE + k * UMMA_K), idesc,
+                                                 (uint32_t)((kb | a | k) != 0));
+                    }
+                    umma_commit_pair(bar_empty + 8 * s);
+                }
+                umma_commit_pair(bar_tfull);
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        const int rl = lg * 32 + lane, row = ib * TM + rl;
+        const double zr = g.z[row];
+        const double rs = ldexp(1.0, g.eP[row] + g.eK[0]);
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        double* sc = scratch + (size_t)(smid % 256) * TM * P2_NT;   // [column][row]: lanes = rows -> coalesced
+        const uint32_t lane_base = tmem + ((uint32_t)(lg * 32) << 16);
+        // pass 0: levels S-1 .. P2_LOW -> fp64 partial in scratch
+        mbar_wait(bar_tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < P2_NT; c0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+            for (int lvl = S - 1; lvl >= P2_LOW; --lvl) {
+                uint32_t d[32];
+                tmem_ld32(lane_base + (uint32_t)((lvl - P2_LOW) * P2_NT + c0), d);
+                const double sf = ldexp(1.0, -8 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc[(size_t)(c0 + j) * TM + rl] = v[j];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 64) mbar_arrive_remote(map_to_rank(bar_tempty, 0));
+        // pass 1: levels P2_LOW-1 .. 0 on top
+        mbar_wait(bar_tfull, 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < P2_NT; c0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = sc[(size_t)(c0 + j) * TM + rl];
+#pragma unroll 1
+            for (int lvl = P2_LOW - 1; lvl >= 0; --lvl) {
+                uint32_t d[32];
+                tmem_ld32(lane_base + (uint32_t)(lvl * P2_NT + c0), d);
+                const double sf = ldexp(1.0, -8 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
+            }
+            double q2[32], qm[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const double x = v[j] * rs; q2[j] = x * x; qm[j] = x * zr; }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+                const bool up = (lane & w) != 0;
+#pragma unroll
+                for (int j = 0; j < w; ++j) {
+                    const double keep2 = up ? q2[j + w] : q2[j], send2 = up ? q2[j] : q2[j + w];
+                    const double keepm = up ? qm[j + w] : qm[j], sendm = up ? qm[j] : qm[j + w];
+                    q2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+                    qm[j] = keepm + __shfl_xor_sync(0xffffffffu, sendm, w);
+                }
+            }
+            const uint32_t slot = red + (uint32_t)(((lg * P2_NT) + c0 + lane) * 16);
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(slot), "d"(q2[0]), "d"(qm[0]) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - 64;                                     // 0 .. 127 = column
+        double s2 = 0.0, sm = 0.0;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+            double a, b;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(red + (uint32_t)((w4 * P2_NT + et) * 16)));
+            s2 += a; sm += b;
+        }
+        g.part_ssq[(long)ib * g.Mc + cb * P2_NT + et] = s2;
+        g.part_mu[(long)ib * g.Mc + cb * P2_NT + et] = sm;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
 // =======================================================================================
 // v4: 128 x 128 tiles in TWO passes over the contraction (levels 0..3, then 4..7): the int8 MMA reads both operands
 // from shared memory at 128 B / clock / SM, so a 128 x 64 MMA (6 KB) is operand-fetch bound at 48 cycles instead of
@@ -805,6 +1001,20 @@ static void launch_pair(int nb, int ncb, const CUtensorMap& mapP, const CUtensor
     CKC(cudaLaunchKernelEx(&cfg, oz_pair_kernel<NT>, mapP, mapKh, a, swap));
 }
 
+static void launch_pair2(int nb, int ncb128, const CUtensorMap& mapP, const CUtensorMap& mapKh, OzArgs a, double* scratch, int swap, int group) {
+    CKC(cudaFuncSetAttribute(oz_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
+    a.ncb = ncb128; a.group = group;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(nb * ncb128); cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = P2_SMEM; cfg.stream = 0;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CKC(cudaLaunchKernelEx(&cfg, oz_pair2_kernel, mapP, mapKh, a, scratch, swap));
+}
+
+// cl: 20 / 21 = CTA pair + two passes (256 x 128), K* halves in rank order / swapped;
 // cl: 1 / 2 = cluster size of the multicast variant, 4 = A-sharing issue order, 10 / 11 = CTA pair (cta_group::2), K* halves
 // in rank order / swapped
 static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = false, bool grouped = false) {
@@ -845,6 +1055,7 @@ static Result run_gpu(const Problem& pr, int reps, int cl = 1, bool two_pass = f
         oz_split_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(dK, M, N, deK, 1, dKq);
         CKC(cudaEventRecord(e1));
         if (two_pass) oz2_vargemm_kernel<<<nb * (M / T2), OZ_THREADS, OZ2_SMEM>>>(mapP32, mapK32, a2);
+        else if (cl >= 20) launch_pair2(nb, M / P2_NT, mapP, mapK, a, dscr, cl - 20, grouped ? 16 : 8);
         else if (cl >= 10) launch_pair<TN>(nb, ncb, mapP, mapKh, a, cl - 10);
         else if (cl == 1) launch_oz<1, 0>(nb * ncb, mapP, mapK, a);
         else if (cl == 2) launch_oz<2, 0>(nb * ncb, mapP, mapK, a);
@@ -870,6 +1081,24 @@ int main(int argc, char** argv) {
     cudaDriverEntryPointQueryResult q;
     CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
     g_encode = (EncodeFn)p;
+    if (argc > 1 && std::string(argv[1]) == "pair2") {
+        Problem pr = gp_problem(1024, 256, 16);
+        Result r = run_gpu(pr, 1, 1, false, true), p0 = run_gpu(pr, 1, 20, false, true), p1 = run_gpu(pr, 1, 21, false, true);
+        double d0 = 0, d1 = 0;
+        for (int c = 0; c < pr.M; ++c) {
+            d0 = std::max(d0, std::fabs(r.ssq[c] - p0.ssq[c]) + std::fabs(r.mu[c] - p0.mu[c]));
+            d1 = std::max(d1, std::fabs(r.ssq[c] - p1.ssq[c]) + std::fabs(r.mu[c] - p1.mu[c]));
+        }
+        const int swap = d1 < d0 ? 1 : 0;
+        Problem big = synthetic_problem(4096, 16384);
+        Result t = run_gpu(big, 4, 1, false, true), tp = run_gpu(big, 4, 20 + swap, false, true);
+        double dbig = 0;
+        for (int c = 0; c < big.M; ++c) dbig = std::max(dbig, std::fabs(t.ssq[c] - tp.ssq[c]));
+        printf("{\"probe\": \"CTA pair (cta_group::2) 256x128 in two passes, S=%d\", \"max_abs_diff_halves_in_rank_order\": %.3e, "
+               "\"max_abs_diff_halves_swapped\": %.3e, \"swap\": %d, \"single_cta_ms_gemm\": %.4f, \"pair_two_pass_ms_gemm\": %.4f, "
+               "\"c2_max_abs_diff\": %.3e}\n", S, d0, d1, swap, t.ms_gemm, tp.ms_gemm, dbig);
+        return 0;
+    }
     if (argc > 1 && std::string(argv[1]) == "pair") {
         // CTA-pair kernel alone (its own process: a protocol mistake would hang, not just miscompute)
         Problem pr = gp_problem(1024, 256, 16);
