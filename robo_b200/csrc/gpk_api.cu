@@ -54,6 +54,7 @@ struct gpk_handle {
     DevBuf oz_scratch;
     CUtensorMap mapOzP32, mapOzK32, mapOzK32b;
     long oz_rows32 = 0, oz_rows32b = 0;
+    int oz_persist = 1;             // 1: one CTA (pair) per SM walks the tile list (gpk_oz_persist_kernel); 0: one CTA (pair) per tile
     int oz_pair = 0;                // 1: CTA pairs (tcgen05 cta_group::2, gpk_oz_pair_kernel) when the row-block count is even
     CUtensorMap mapOzKh, mapOzKh2;  // K* slices in 32-row boxes (the half tiles of a pair)
     int oz_fused = 1;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
@@ -355,6 +356,8 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 1)));
     CK(cudaFuncSetAttribute(gpk_oz_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
     CK(cudaFuncSetAttribute(gpk_oz_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_SMEM));
+    CK(cudaFuncSetAttribute(gpk_oz_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_PERSIST_SMEM));
+    CK(cudaFuncSetAttribute(gpk_oz_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_PERSIST_SMEM));
     CK(cudaFuncSetAttribute(gpk_oz2_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM));
     CK(cudaFuncSetAttribute(gpk_cov_oz_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_oz_smem_bytes(GPK_MAX_TERMS, 8)));
     CK(cudaFuncSetAttribute(gpk_cov_oz_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_oz_smem_bytes(GPK_MAX_TERMS, 4)));
@@ -925,18 +928,25 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             o.group = (int)std::min<long>(128, std::max<long>(4, ((long)64 << 20) / ((long)OZ_TN * NP * OZ_S)));
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart;
-            if (h->oz_pair && (h->nb % 2) == 0) {
+            const bool pair = h->oz_pair && (h->nb % 2) == 0;
+            const CUtensorMap& mk = pair ? (second ? h->mapOzKh2 : h->mapOzKh) : (second ? h->mapOzK2 : h->mapOzK);
+            const int tiles = pair ? (o.nb / 2) * o.ncb : o.nb * o.ncb;
+            const int sms = std::max(h->n_sm, 2);
+            if (pair) {
                 cudaLaunchConfig_t cfg;
                 memset(&cfg, 0, sizeof(cfg));
-                cfg.gridDim = dim3((unsigned)(o.nb * o.ncb)); cfg.blockDim = dim3(OZ_THREADS);
-                cfg.dynamicSmemBytes = OZP_SMEM; cfg.stream = h->stream;
+                cfg.gridDim = dim3((unsigned)(2 * (h->oz_persist ? std::min(tiles, sms / 2) : tiles))); cfg.blockDim = dim3(OZ_THREADS);
+                cfg.dynamicSmemBytes = h->oz_persist ? OZP_PERSIST_SMEM : OZP_SMEM; cfg.stream = h->stream;
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeClusterDimension;
                 attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
-                CK(cudaLaunchKernelEx(&cfg, gpk_oz_pair_kernel, h->mapOzP, second ? h->mapOzKh2 : h->mapOzKh, o));
-            } else
-                gpk_oz_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ_SMEM, h->stream>>>(h->mapOzP, second ? h->mapOzK2 : h->mapOzK, o);
+                if (h->oz_persist) CK(cudaLaunchKernelEx(&cfg, gpk_oz_persist_kernel<true>, h->mapOzP, mk, o));
+                else CK(cudaLaunchKernelEx(&cfg, gpk_oz_pair_kernel, h->mapOzP, mk, o));
+            } else if (h->oz_persist)
+                gpk_oz_persist_kernel<false><<<std::min(tiles, sms), OZ_THREADS, OZ_PERSIST_SMEM, h->stream>>>(h->mapOzP, mk, o);
+            else
+                gpk_oz_vargemm_kernel<<<tiles, OZ_THREADS, OZ_SMEM, h->stream>>>(h->mapOzP, mk, o);
             CKL();
             h->oz_launches += 1;
         } else if (h->persist && h->loader == LOADER_TMA_WS) {
@@ -1092,6 +1102,10 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
     if (!strcmp(key, "oztile")) {
         if (value != 64 && value != 128) BAD("oztile must be 64 (one pass, 128 x 64 tiles) or 128 (two passes, 128 x 128 tiles)");
         h->oz_tile = (int)value;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "ozpersist")) {
+        h->oz_persist = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "ozpair")) {

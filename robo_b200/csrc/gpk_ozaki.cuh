@@ -425,6 +425,192 @@ gpk_oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------
+// Persistent variants (option "ozpersist" = 1, the default): one CTA (or CTA pair) per SM walks the tile list
+// (tile t of unit u: t = u, u + units, ...; same L2-grouped, longest-first order), so
+//   * all CTAs of the contraction are resident from the start and the block scheduler can place the covariance
+//     builder of the NEXT chunk (low-priority side stream, FP64 ALU) into the SMs' spare registers / shared memory:
+//     with one CTA per tile the builder only ran in the tail of the grid (measured: no overlap at all);
+//   * barriers, TMEM allocation and the pipeline fill are paid once, and the TMA producer runs ahead into the next
+//     tile while the epilogue warps drain the accumulators (the MMA issuer waits for "TMEM drained" per tile).
+// PAIR: tcgen05 cta_group::2 as in gpk_oz_pair_kernel (M = 256, K* halves shared by the pair, 3 stages).
+// ---------------------------------------------------------------------------------------
+template <bool PAIR>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapK, const OzArgs g)
+{
+    constexpr int NSTG = PAIR ? OZP_NSTG : OZ_NSTG;
+    constexpr int STAGE = PAIR ? OZP_STAGE : OZ_STAGE;
+    constexpr int B_SLICE = PAIR ? OZP_BH_SLICE : OZ_B_SLICE;
+    extern __shared__ unsigned char oz_raw[];
+    const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + NSTG * STAGE, bar_empty = bar_full + 8 * NSTG;
+    const uint32_t bar_tfull = bar_empty + 8 * NSTG, bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
+    const uint32_t red = base + NSTG * STAGE + 256;                  // 2 x [4 lane groups][64 columns]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int crank = PAIR ? (int)oz_cluster_rank() : 0;
+    const int unit = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x, units = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+    const int rows_per_tile = PAIR ? 2 : 1;
+    const int nrow_tiles = g.nb / rows_per_tile, total = nrow_tiles * g.ncb;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, PAIR ? 2 : 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (PAIR) oz_cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = unit; t < total; t += units) {
+                int ibt, cb;
+                oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
+                const int ib = rows_per_tile * ibt + crank;
+                const int nkb = (rows_per_tile * ibt + rows_per_tile) * OZ_TM / OZ_KB;
+                const int crow = PAIR ? cb * OZ_TN + (crank ^ OZP_SWAP) * OZP_BH : cb * OZ_TN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % NSTG;
+                    if (it >= NSTG) oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((it / NSTG - 1) & 1));
+                    const uint32_t st = base + s * STAGE;
+                    if (PAIR) {
+                        const uint32_t lbar = oz_map_to_rank(bar_full + 8 * s, 0);
+                        if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * STAGE);
+#pragma unroll
+                        for (int q = 0; q < OZ_S; ++q) {
+                            oz_tma_pair(st + q * OZ_A_SLICE, &mapP, kb * OZ_KB, q * g.NP + ib * OZ_TM, lbar);
+                            oz_tma_pair(st + OZ_S * OZ_A_SLICE + q * B_SLICE, &mapK, kb * OZ_KB, q * g.rows + crow, lbar);
+                        }
+                    } else {
+                        mbar_arrive_expect_tx(bar_full + 8 * s, STAGE);
+#pragma unroll
+                        for (int q = 0; q < OZ_S; ++q) {
+                            tma_load_2d(st + q * OZ_A_SLICE, &mapP, kb * OZ_KB, q * g.NP + ib * OZ_TM, bar_full + 8 * s);
+                            tma_load_2d(st + OZ_S * OZ_A_SLICE + q * B_SLICE, &mapK, kb * OZ_KB, q * g.rows + crow, bar_full + 8 * s);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc = oz_idesc(PAIR ? 2 * OZ_TM : OZ_TM, OZ_TN);
+            int it = 0, tl = 0;
+            for (int t = unit; t < total; t += units, ++tl) {
+                int ibt, cb;
+                oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
+                const int nkb = (rows_per_tile * ibt + rows_per_tile) * OZ_TM / OZ_KB;
+                if (tl > 0) {                                        // the epilogue has drained the previous tile's accumulators
+                    oz_mbar_wait(bar_tempty, (uint32_t)((tl - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % NSTG;
+                    oz_mbar_wait(bar_full + 8 * s, (uint32_t)((it / NSTG) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * STAGE;
+#pragma unroll
+                    for (int lvl = 0; lvl < OZ_S; ++lvl)
+#pragma unroll
+                        for (int a = 0; a <= lvl; ++a) {
+                            const int b = lvl - a;
+#pragma unroll
+                            for (int k = 0; k < OZ_KB / OZ_UK; ++k) {
+                                const uint64_t da = oz_desc(st + a * OZ_A_SLICE + k * OZ_UK);
+                                const uint64_t db = oz_desc(st + OZ_S * OZ_A_SLICE + b * B_SLICE + k * OZ_UK);
+                                if (PAIR) oz_mma_pair(tmem + (uint32_t)(lvl * OZ_TN), da, db, idesc, (uint32_t)((kb | a | k) != 0));
+                                else oz_mma(tmem + (uint32_t)(lvl * OZ_TN), da, db, idesc, (uint32_t)((kb | a | k) != 0));
+                            }
+                        }
+                    if (PAIR) oz_commit_pair(bar_empty + 8 * s); else oz_commit(bar_empty + 8 * s);
+                }
+                if (PAIR) oz_commit_pair(bar_tfull); else oz_commit(bar_tfull);
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        int tl = 0;
+        for (int t = unit; t < total; t += units, ++tl) {
+            int ibt, cb;
+            oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
+            const int ib = rows_per_tile * ibt + crank;
+            const int row = ib * OZ_TM + lg * 32 + lane;
+            const double rs = ldexp(1.0, g.eP[row] + g.eK);
+            const uint32_t redt = red + (uint32_t)((tl & 1) * 4 * OZ_TN * 8);
+            oz_mbar_wait(bar_tfull, (uint32_t)(tl & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                double v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+                for (int lvl = OZ_S - 1; lvl >= 0; --lvl) {
+                    uint32_t d[32];
+                    oz_tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(lvl * OZ_TN + half * 32), d);
+                    const double sc = ldexp(1.0, -8 * (lvl + 2));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sc, v[j]);
+                }
+                if (half == 1) {                                     // TMEM is read out: hand it back before the reductions
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (tid == 64) {
+                        if (PAIR) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(oz_map_to_rank(bar_tempty, 0)) : "memory");
+                        else mbar_arrive(bar_tempty);
+                    }
+                }
+                double q2[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const double x = v[j] * rs; q2[j] = x * x; }
+#pragma unroll
+                for (int w = 16; w >= 1; w >>= 1) {
+                    const bool up = (lane & w) != 0;
+#pragma unroll
+                    for (int j = 0; j < w; ++j) {
+                        const double keep2 = up ? q2[j + w] : q2[j], send2 = up ? q2[j] : q2[j + w];
+                        q2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+                    }
+                }
+                sts64(redt + (uint32_t)(((lg * OZ_TN) + half * 32 + lane) * 8), q2[0]);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int et = tid - 64;
+            if (et < OZ_TN) {
+                double s2 = 0.0;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) s2 += lds64(redt + (uint32_t)((w4 * OZ_TN + et) * 8));
+                g.part_ssq[(long)ib * g.ldpart + cb * OZ_TN + et] = s2;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (PAIR) oz_cluster_sync();
+    if (warp == 1) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+    }
+}
+constexpr int OZ_PERSIST_SMEM = OZ_NSTG * OZ_STAGE + 1024 + 256 + 2 * 4 * OZ_TN * 8;
+constexpr int OZP_PERSIST_SMEM = OZP_NSTG * OZP_STAGE + 1024 + 256 + 2 * 4 * OZ_TN * 8;
+
+// ---------------------------------------------------------------------------------------
 // Two-pass variant (option "oztile" = 128): 128 x 128 tiles, levels 0..3 in a first pass over the contraction, levels
 // 4..6 in a second.  kind::i8 reads BOTH operands from shared memory at 128 B / clock / SM (measured: a 128 x 128 x 32
 // MMA takes 65.9 cycles = 8 KB / 128 B), so the 128 x 64 MMAs of gpk_oz_vargemm_kernel are operand-fetch bound (6 KB ->

@@ -918,13 +918,14 @@ def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
     X, y, Xs, theta, noise = O.synthetic_problem(N, D, M, seed_train=3)
     eta = float(np.min(y))
     res = {}
-    for oz in (0, 1, 2, 3, 4):                              # 2: separate split / mean kernels; 3: two-pass 128 x 128 tiles;
-                                                            # 4: CTA pairs (tcgen05 cta_group::2)
+    variants = (0, 1, 2, 3, 4, 5, 6)                        # 2: separate split / mean kernels; 3: two-pass 128 x 128 tiles;
+    for oz in variants:                                     # 4: CTA pairs (tcgen05 cta_group::2); 5, 6: one CTA (pair) per tile
         h, logdet, ll, diag_add, mean = _handle_for("matern52", theta, X, y, noise)
         h.set_option("ozaki", 1 if oz else 0)
         h.set_option("ozfused", 0 if oz == 2 else 1)
         h.set_option("oztile", 128 if oz == 3 else 64)
-        h.set_option("ozpair", 1 if oz == 4 else 0)
+        h.set_option("ozpair", 1 if oz in (4, 6) else 0)
+        h.set_option("ozpersist", 0 if oz in (5, 6) else 1)
         res[oz] = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
         if oz:                                              # chunking must stay invisible on the int8 path too
             h.set_option("chunk", 1024)
@@ -941,13 +942,14 @@ def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
     st = O.gp_fit(oracle_kernel("matern52", theta, D), X, y, noise=noise, normalize_input=False)
     mu_ref, var_ref = O.gp_predict_var_only_fast(st, Xs)
     amp = float(np.exp(theta[0]))
-    for oz in (0, 1, 2, 3, 4):
+    for oz in variants:
         assert_mean_close(res[oz]["mu"], mu_ref, y)
         assert_var_close(res[oz]["var"], var_ref, amp)
         assert_acq_close(res[oz]["values"], O.acq_ei(mu_ref, var_ref, eta), rtol=1e-8, atol=1e-13)
-    assert res[0]["best_idx"] == res[1]["best_idx"] == res[2]["best_idx"] == res[3]["best_idx"] == res[4]["best_idx"] == int(np.argmax(O.acq_ei(mu_ref, var_ref, eta)))
+    assert all(res[oz]["best_idx"] == int(np.argmax(O.acq_ei(mu_ref, var_ref, eta))) for oz in variants)
     np.testing.assert_array_equal(res[1]["var"], res[2]["var"])       # same digits either way
-    np.testing.assert_array_equal(res[1]["var"], res[4]["var"])       # same integers, same epilogue: the pair changes nothing
+    for oz in (4, 5, 6):                                              # same integers, same epilogue order: pairs and the
+        np.testing.assert_array_equal(res[1]["var"], res[oz]["var"])  # persistent tile walk change nothing
     # ill-conditioned factor (tiny noise, long length scales): row exponents of L^-1 exceed the 8-slice budget -> fp64
     theta_bad = theta + np.r_[0.0, np.full(D, np.log(4.0))]
     h, logdet, ll, diag_add, mean = _handle_for("matern52", theta_bad, X, y, 1e-8)
