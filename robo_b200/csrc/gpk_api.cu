@@ -356,6 +356,7 @@ int set_kernel_attrs(gpk_handle* h) {
     CK(cudaFuncSetAttribute(gpk_gemm_nt_kernel<EPI_STORE, LOADER_TMA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(LOADER_TMA, 1)));
     CK(cudaFuncSetAttribute(gpk_oz_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
     CK(cudaFuncSetAttribute(gpk_oz_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_SMEM));
+    CK(cudaFuncSetAttribute(gpk_oz_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZQ_SMEM));
     CK(cudaFuncSetAttribute(gpk_oz_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_PERSIST_SMEM));
     CK(cudaFuncSetAttribute(gpk_oz_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_PERSIST_SMEM));
     CK(cudaFuncSetAttribute(gpk_oz2_vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM));
@@ -791,14 +792,14 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         // (the tensor maps are re-encoded per call: a few microseconds, and they depend on the buffer, cap and NP)
         if ((rc = ensure(h, h->oz_Kq, (size_t)OZ_S * cap * NP))) return rc;
         if (h->overlap && (rc = ensure(h, h->oz_Kq2, (size_t)OZ_S * cap * NP))) return rc;
+        if ((rc = make_oz_map(h, &h->mapOzK, h->oz_Kq.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
+        if (h->overlap && (rc = make_oz_map(h, &h->mapOzK2, h->oz_Kq2.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
         if (h->oz_tile == 128) {
             if ((rc = ensure(h, h->oz_scratch, (size_t)OZ2_SCRATCH_SLOTS * OZ2_T * OZ2_T * 8))) return rc;
             if ((rc = make_oz_map(h, &h->mapOzP32, h->oz_Pq.p, (long)OZ_S * NP, NP, OZ2_T, OZ2_KB))) return rc;
             if ((rc = make_oz_map(h, &h->mapOzK32, h->oz_Kq.p, (long)OZ_S * cap, NP, OZ2_T, OZ2_KB))) return rc;
             if (h->overlap && (rc = make_oz_map(h, &h->mapOzK32b, h->oz_Kq2.p, (long)OZ_S * cap, NP, OZ2_T, OZ2_KB))) return rc;
         } else {
-            if ((rc = make_oz_map(h, &h->mapOzK, h->oz_Kq.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
-            if (h->overlap && (rc = make_oz_map(h, &h->mapOzK2, h->oz_Kq2.p, (long)OZ_S * cap, NP, OZ_TN))) return rc;
             if (h->oz_pair) {
                 if ((rc = make_oz_map(h, &h->mapOzKh, h->oz_Kq.p, (long)OZ_S * cap, NP, OZP_BH))) return rc;
                 if (h->overlap && (rc = make_oz_map(h, &h->mapOzKh2, h->oz_Kq2.p, (long)OZ_S * cap, NP, OZP_BH))) return rc;
@@ -919,7 +920,20 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             o.group = (int)std::min<long>(64, std::max<long>(2, ((long)64 << 20) / ((long)OZ2_T * NP * OZ_S)));
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart; o.scratch = ptr<double>(h->oz_scratch);
-            gpk_oz2_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ2_SMEM, h->stream>>>(h->mapOzP32, second ? h->mapOzK32b : h->mapOzK32, o);
+            if (h->oz_pair && (h->nb % 2) == 0) {
+                // CTA pair, 256 x 128 per pair in two passes; its K* half tile (64 rows x 64 B) is the box of mapOzK
+                const int tiles = (o.nb / 2) * o.ncb;
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3((unsigned)(2 * (h->oz_persist ? std::min(tiles, std::max(h->n_sm, 2) / 2) : tiles)));
+                cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = OZQ_SMEM; cfg.stream = h->stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                CK(cudaLaunchKernelEx(&cfg, gpk_oz_pair2_kernel, h->mapOzP, second ? h->mapOzK2 : h->mapOzK, o));
+            } else
+                gpk_oz2_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ2_SMEM, h->stream>>>(h->mapOzP32, second ? h->mapOzK32b : h->mapOzK32, o);
             CKL();
             h->oz_launches += 1;
         } else if (use_oz) {

@@ -645,6 +645,215 @@ struct Oz2Args {
     double* scratch;                    // [OZ2_SCRATCH_SLOTS][128][128]
 };
 
+// ---------------------------------------------------------------------------------------
+// CTA pair AND two passes (options "ozpair" = 1, "oztile" = 128): M = 256 x N = 128 per pair.  Measured (tools/microbench/
+// ozaki_probe.cu, 16384 candidates x N = 4096): 2.60 ms against 3.35 ms for the 128 x 64 single-CTA tile.  Why: a CTA
+// stages its own 128 rows of the L^-1 slices but only HALF (64 rows) of the K* slices for a 128 x 128 share of the
+// output, 132 KB of L2 -> SM traffic per 64-byte k-block instead of 168 KB (one pass, N = 64) or 176 KB (two passes, one
+// CTA), and the 256 x 128 x 32 MMA is not operand-fetch bound.  TMEM holds 128 columns per level, so the levels go in
+// two passes over the contraction: first the three least significant (4..6, all 7 slices), drained to fp64 in an
+// L2-resident scratch tile [column][row], then levels 0..3 (slices 0..3 only) on top, in the same least-significant-
+// first order as the one-pass kernels (bit-identical results).  Tile walk as in gpk_oz_persist_kernel: with
+// gridDim.x / 2 = number of pair tiles every pair does exactly one tile.
+// ---------------------------------------------------------------------------------------
+constexpr int OZQ_NT = 128;                                         // candidates per pair tile
+constexpr int OZQ_BH_SLICE = (OZQ_NT / 2) * OZ_KB;                  // 4096: 64 K* rows per CTA and slice
+constexpr int OZQ_STAGE = OZ_S * (OZ_A_SLICE + OZQ_BH_SLICE);       // 86016
+constexpr int OZQ_NSTG = 2;
+constexpr int OZQ_LOW = 4;                                          // levels OZQ_LOW .. S-1 in pass 0, 0 .. OZQ_LOW-1 in pass 1
+constexpr int OZQ_SMEM = OZQ_NSTG * OZQ_STAGE + 1024 + 256 + 2 * 4 * OZQ_NT * 8;
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapKh, const Oz2Args g)
+{
+    extern __shared__ unsigned char oz_raw[];
+    const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + OZQ_NSTG * OZQ_STAGE, bar_empty = bar_full + 8 * OZQ_NSTG;
+    const uint32_t bar_tfull = bar_empty + 8 * OZQ_NSTG, bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
+    const uint32_t red = base + OZQ_NSTG * OZQ_STAGE + 256;          // 2 x [4 lane groups][128 columns]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int crank = (int)oz_cluster_rank();
+    const int unit = (int)blockIdx.x / 2, units = (int)gridDim.x / 2;
+    const int nrow_tiles = g.nb / 2, total = nrow_tiles * g.ncb;
+
+    if (tid == 0) {
+        for (int s = 0; s < OZQ_NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 2);                                   // one arrival per CTA of the pair (waited on by rank 0)
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    oz_cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = unit; t < total; t += units) {
+                int ibt, cb;
+                oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
+                const int ib = 2 * ibt + crank;
+                const int nkb = (2 * ibt + 2) * OZ_TM / OZ_KB;
+                const int crow = cb * OZQ_NT + (crank ^ OZP_SWAP) * (OZQ_NT / 2);
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int ns = pass == 0 ? OZ_S : OZQ_LOW;       // levels >= 4 touch every slice, levels < 4 only slices 0..3
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const int s = it % OZQ_NSTG;
+                        if (it >= OZQ_NSTG) oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((it / OZQ_NSTG - 1) & 1));
+                        const uint32_t st = base + s * OZQ_STAGE;
+                        const uint32_t lbar = oz_map_to_rank(bar_full + 8 * s, 0);
+                        if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(2 * ns * (OZ_A_SLICE + OZQ_BH_SLICE)));
+                        for (int q = 0; q < ns; ++q) {
+                            oz_tma_pair(st + q * OZ_A_SLICE, &mapP, kb * OZ_KB, q * g.NP + ib * OZ_TM, lbar);
+                            oz_tma_pair(st + OZ_S * OZ_A_SLICE + q * OZQ_BH_SLICE, &mapKh, kb * OZ_KB, q * g.rows + crow, lbar);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc = oz_idesc(2 * OZ_TM, OZQ_NT);
+            int it = 0, n = 0;                                       // n = 2 * (tiles done) + pass
+            for (int t = unit; t < total; t += units) {
+                int ibt, cb;
+                oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
+                const int nkb = (2 * ibt + 2) * OZ_TM / OZ_KB;
+                for (int pass = 0; pass < 2; ++pass, ++n) {
+                    if (n > 0) {                                     // both CTAs' epilogues have drained the previous accumulators
+                        oz_mbar_wait(bar_tempty, (uint32_t)((n - 1) & 1));
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const int s = it % OZQ_NSTG;
+                        oz_mbar_wait(bar_full + 8 * s, (uint32_t)((it / OZQ_NSTG) & 1));
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t st = base + s * OZQ_STAGE;
+                        if (pass == 0) {
+#pragma unroll
+                            for (int lvl = OZQ_LOW; lvl < OZ_S; ++lvl)
+#pragma unroll
+                                for (int a = 0; a <= lvl; ++a)
+#pragma unroll
+                                    for (int k = 0; k < OZ_KB / OZ_UK; ++k)
+                                        oz_mma_pair(tmem + (uint32_t)((lvl - OZQ_LOW) * OZQ_NT), oz_desc(st + a * OZ_A_SLICE + k * OZ_UK),
+                                                    oz_desc(st + OZ_S * OZ_A_SLICE + (lvl - a) * OZQ_BH_SLICE + k * OZ_UK), idesc,
+                                                    (uint32_t)((kb | a | k) != 0));
+                        } else {
+#pragma unroll
+                            for (int lvl = 0; lvl < OZQ_LOW; ++lvl)
+#pragma unroll
+                                for (int a = 0; a <= lvl; ++a)
+#pragma unroll
+                                    for (int k = 0; k < OZ_KB / OZ_UK; ++k)
+                                        oz_mma_pair(tmem + (uint32_t)(lvl * OZQ_NT), oz_desc(st + a * OZ_A_SLICE + k * OZ_UK),
+                                                    oz_desc(st + OZ_S * OZ_A_SLICE + (lvl - a) * OZQ_BH_SLICE + k * OZ_UK), idesc,
+                                                    (uint32_t)((kb | a | k) != 0));
+                        }
+                        oz_commit_pair(bar_empty + 8 * s);
+                    }
+                    oz_commit_pair(bar_tfull);
+                }
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        const int rl = lg * 32 + lane;
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        double* sc = g.scratch + (size_t)(smid % OZ2_SCRATCH_SLOTS) * OZ_TM * OZQ_NT;      // [column][row]: lanes = rows
+        const uint32_t lane_base = tmem + ((uint32_t)(lg * 32) << 16);
+        const uint32_t tempty_leader = oz_map_to_rank(bar_tempty, 0);
+        int n = 0, tl = 0;
+        for (int t = unit; t < total; t += units, ++tl) {
+            int ibt, cb;
+            oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
+            const int ib = 2 * ibt + crank;
+            const int row = ib * OZ_TM + rl;
+            const double rs = ldexp(1.0, g.eP[row] + g.eK);
+            const uint32_t redt = red + (uint32_t)((tl & 1) * 4 * OZQ_NT * 8);
+            // pass 0: levels S-1 .. OZQ_LOW -> fp64 partial in the scratch tile
+            oz_mbar_wait(bar_tfull, (uint32_t)(n & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < OZQ_NT; c0 += 32) {
+                double v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.0;
+#pragma unroll 1
+                for (int lvl = OZ_S - 1; lvl >= OZQ_LOW; --lvl) {
+                    uint32_t d[32];
+                    oz_tmem_ld32(lane_base + (uint32_t)((lvl - OZQ_LOW) * OZQ_NT + c0), d);
+                    const double sf = ldexp(1.0, -8 * (lvl + 2));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sc[(size_t)(c0 + j) * OZ_TM + rl] = v[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (tid == 64) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(tempty_leader) : "memory");
+            ++n;
+            // pass 1: levels OZQ_LOW-1 .. 0 on top, squares, column sums
+            oz_mbar_wait(bar_tfull, (uint32_t)(n & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < OZQ_NT; c0 += 32) {
+                double v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = sc[(size_t)(c0 + j) * OZ_TM + rl];
+#pragma unroll 1
+                for (int lvl = OZQ_LOW - 1; lvl >= 0; --lvl) {
+                    uint32_t d[32];
+                    oz_tmem_ld32(lane_base + (uint32_t)(lvl * OZQ_NT + c0), d);
+                    const double sf = ldexp(1.0, -8 * (lvl + 2));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
+                }
+                if (c0 == OZQ_NT - 32) {                             // TMEM is read out: hand it back before the reductions
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (tid == 64) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(tempty_leader) : "memory");
+                }
+                double q2[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const double x = v[j] * rs; q2[j] = x * x; }
+#pragma unroll
+                for (int w = 16; w >= 1; w >>= 1) {
+                    const bool up = (lane & w) != 0;
+#pragma unroll
+                    for (int j = 0; j < w; ++j) {
+                        const double keep2 = up ? q2[j + w] : q2[j], send2 = up ? q2[j] : q2[j + w];
+                        q2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+                    }
+                }
+                sts64(redt + (uint32_t)((lg * OZQ_NT + c0 + lane) * 8), q2[0]);
+            }
+            ++n;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int et = tid - 64;                                 // 0 .. 127 = column of the tile
+            double s2 = 0.0;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) s2 += lds64(redt + (uint32_t)((w4 * OZQ_NT + et) * 8));
+            g.part_ssq[(long)ib * g.ldpart + cb * OZQ_NT + et] = s2;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    oz_cluster_sync();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 gpk_oz2_vargemm_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapK, const Oz2Args g)
 {

@@ -16,3 +16,10 @@ except Exception as e:
 PY
 done
 timeout 900 python -m pytest tests -x -q -m gpu > $out/r2f_pytest_default.log 2>&1; echo "pytest[default] exit $?"; tail -3 $out/r2f_pytest_default.log
+NCU="ncu --clock-control none"
+for k in "oz_persist gpk_oz_persist_kernelILb0E X=1" "oz_nonpersist gpk_oz_vargemm_kernel GPK_OZPERSIST=0"; do
+  set -- $k
+  env $3 timeout 600 $NCU --set full --import-source on --kernel-name-base mangled -k "regex:$2" -s 2 -c 1 -f -o $out/r02_$1 \
+      python tools/profile_driver.py 4096 16 32768 > $out/r02_$1.log 2>&1
+  tail -2 $out/r02_$1.log
+done
