@@ -293,6 +293,10 @@ int gpk_get_z(gpk_handle* h, double* z /* n */);
  * (option "ozaki"); out[12] = option "persist"; out[13] = int8 slice-pair products the int8 contraction spends per
  * fp64 product (28: 7 balanced base-256 digits per operand); out[14..15] reserved (zero). */
 int gpk_get_timings(gpk_handle* h, double* out16);
+/* diagnostics of the persistent int8 contraction (option "ozprof" = 1): per CTA of its last launch 8 clock64() sums:
+ * [0] MMA issuer loop, [1] of it waiting for staged operands, [2] waiting for the epilogue to drain TMEM, [3] TMA producer
+ * waiting for a free stage, [4] epilogue waiting for final accumulators, [5] epilogue draining TMEM, [6] tiles, [7] 0. */
+int gpk_get_oz_profile(gpk_handle* h, long long* out, int max_ctas, int* n_ctas);
 /* diagnostics of the blocked diagonal-block kernel (option "diagprof" = 1): clock64() stamps of the last
  * launched block: out[0] start, out[1] tiles loaded, out[2+2p] panel p factorised + solved, out[3+2p] panel p's
  * rank-16 update applied and panel p+1 published, out[33] end, out[34..41] finer stamps inside panel 3. */

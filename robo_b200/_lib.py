@@ -69,6 +69,7 @@ _SIGNATURES = {
     "gpk_get_z": [_vp, _dp],
     "gpk_get_timings": [_vp, _dp],
     "gpk_get_diag_profile": [_vp, C.POINTER(C.c_longlong)],
+    "gpk_get_oz_profile": [_vp, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int)],
 }
 
 _lib = None
@@ -413,6 +414,13 @@ class Handle(object):
         t = np.zeros(64, dtype=np.int64)
         self._check(self.lib.gpk_get_diag_profile(self._h, t.ctypes.data_as(C.POINTER(C.c_longlong))))
         return t
+
+    def oz_profile(self, max_ctas=16384):
+        """(n_ctas, 8) clock64() sums of the last persistent int8 contraction (option "ozprof")."""
+        buf = (C.c_longlong * (8 * max_ctas))()
+        n = C.c_int(0)
+        self._check(self.lib.gpk_get_oz_profile(self._h, buf, int(max_ctas), C.byref(n)))
+        return np.frombuffer(buf, dtype=np.int64, count=8 * n.value).reshape(n.value, 8).copy()
 
     def timings(self):
         t = np.zeros(16)

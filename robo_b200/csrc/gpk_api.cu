@@ -54,6 +54,9 @@ struct gpk_handle {
     DevBuf oz_scratch;
     CUtensorMap mapOzP32, mapOzK32, mapOzK32b;
     long oz_rows32 = 0, oz_rows32b = 0;
+    int oz_prof = 0;                // 1: gpk_oz_persist_kernel accumulates clock64() wait sums per CTA (gpk_get_oz_profile)
+    DevBuf oz_profbuf;
+    int oz_prof_ctas = 0;
     int oz_persist = 1;             // 1: one CTA (pair) per SM walks the tile list (gpk_oz_persist_kernel); 0: one CTA (pair) per tile
     int oz_pair = 0;                // 1: CTA pairs (tcgen05 cta_group::2, gpk_oz_pair_kernel) when the row-block count is even
     CUtensorMap mapOzKh, mapOzKh2;  // K* slices in 32-row boxes (the half tiles of a pair)
@@ -942,14 +945,25 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             o.group = (int)std::min<long>(128, std::max<long>(4, ((long)64 << 20) / ((long)OZ_TN * NP * OZ_S)));
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart;
+            o.prof = nullptr;
             const bool pair = h->oz_pair && (h->nb % 2) == 0;
             const CUtensorMap& mk = pair ? (second ? h->mapOzKh2 : h->mapOzKh) : (second ? h->mapOzK2 : h->mapOzK);
             const int tiles = pair ? (o.nb / 2) * o.ncb : o.nb * o.ncb;
             const int sms = std::max(h->n_sm, 2);
+            // "ozpersist" 1: one CTA (pair) per SM walks the tile list; 2: the same kernel, one tile per CTA (pair); 0: the
+            // one-tile kernels
+            const int units = h->oz_persist == 1 ? std::min(tiles, pair ? sms / 2 : sms) : tiles;
+            if (h->oz_prof && h->oz_persist) {
+                const int ctas = pair ? 2 * units : units;
+                if ((rc = ensure(h, h->oz_profbuf, (size_t)ctas * 64))) return rc;
+                CK(cudaMemsetAsync(h->oz_profbuf.p, 0, (size_t)ctas * 64, h->stream));
+                o.prof = ptr<long long>(h->oz_profbuf);
+                h->oz_prof_ctas = ctas;
+            }
             if (pair) {
                 cudaLaunchConfig_t cfg;
                 memset(&cfg, 0, sizeof(cfg));
-                cfg.gridDim = dim3((unsigned)(2 * (h->oz_persist ? std::min(tiles, sms / 2) : tiles))); cfg.blockDim = dim3(OZ_THREADS);
+                cfg.gridDim = dim3((unsigned)(2 * units)); cfg.blockDim = dim3(OZ_THREADS);
                 cfg.dynamicSmemBytes = h->oz_persist ? OZP_PERSIST_SMEM : OZP_SMEM; cfg.stream = h->stream;
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -958,7 +972,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
                 if (h->oz_persist) CK(cudaLaunchKernelEx(&cfg, gpk_oz_persist_kernel<true>, h->mapOzP, mk, o));
                 else CK(cudaLaunchKernelEx(&cfg, gpk_oz_pair_kernel, h->mapOzP, mk, o));
             } else if (h->oz_persist)
-                gpk_oz_persist_kernel<false><<<std::min(tiles, sms), OZ_THREADS, OZ_PERSIST_SMEM, h->stream>>>(h->mapOzP, mk, o);
+                gpk_oz_persist_kernel<false><<<units, OZ_THREADS, OZ_PERSIST_SMEM, h->stream>>>(h->mapOzP, mk, o);
             else
                 gpk_oz_vargemm_kernel<<<tiles, OZ_THREADS, OZ_SMEM, h->stream>>>(h->mapOzP, mk, o);
             CKL();
@@ -1119,7 +1133,12 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         return GPK_OK;
     }
     if (!strcmp(key, "ozpersist")) {
+        if (value < 0 || value > 2) BAD("ozpersist must be 0, 1 or 2");
         h->oz_persist = (int)value;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "ozprof")) {
+        h->oz_prof = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "ozpair")) {
@@ -2418,6 +2437,18 @@ int gpk_get_z(gpk_handle* h, double* z) {
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(z, ptr<double>(h->Kbuf) + (long)h->NP * h->NP, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return GPK_OK;
+}
+
+int gpk_get_oz_profile(gpk_handle* h, long long* out, int max_ctas, int* n_ctas) {
+    if (!h || !out || !n_ctas) return GPK_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    const int n = std::min(h->oz_prof_ctas, max_ctas);
+    *n_ctas = n;
+    if (n > 0) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(out, h->oz_profbuf.p, (size_t)n * 64, cudaMemcpyDeviceToHost));
+    }
     return GPK_OK;
 }
 

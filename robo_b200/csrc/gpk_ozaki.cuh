@@ -141,6 +141,7 @@ struct OzArgs {
     int NP, rows;                       // L^-1 is NP x NP; the K* slices have `rows` rows each
     const int* eP; int eK;
     double* part_ssq; long ldpart;
+    long long* prof;                    // option "ozprof": per CTA 8 clock64() sums (gpk_oz_persist_kernel), else nullptr
 };
 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
@@ -478,6 +479,7 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
+            long long w_empty = 0;
             for (int t = unit; t < total; t += units) {
                 int ibt, cb;
                 oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
@@ -486,7 +488,11 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
                 const int crow = PAIR ? cb * OZ_TN + (crank ^ OZP_SWAP) * OZP_BH : cb * OZ_TN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % NSTG;
-                    if (it >= NSTG) oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((it / NSTG - 1) & 1));
+                    if (it >= NSTG) {
+                        const long long c0 = g.prof ? clock64() : 0;
+                        oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((it / NSTG - 1) & 1));
+                        if (g.prof) w_empty += clock64() - c0;
+                    }
                     const uint32_t st = base + s * STAGE;
                     if (PAIR) {
                         const uint32_t lbar = oz_map_to_rank(bar_full + 8 * s, 0);
@@ -506,22 +512,31 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
                     }
                 }
             }
+            if (g.prof) g.prof[(long)blockIdx.x * 8 + 3] = w_empty;
         }
     } else if (warp == 1) {
         if (lane == 0 && crank == 0) {
             const uint32_t idesc = oz_idesc(PAIR ? 2 * OZ_TM : OZ_TM, OZ_TN);
             int it = 0, tl = 0;
+            long long w_full = 0, w_tempty = 0;
+            const long long c_start = g.prof ? clock64() : 0;
             for (int t = unit; t < total; t += units, ++tl) {
                 int ibt, cb;
                 oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
                 const int nkb = (rows_per_tile * ibt + rows_per_tile) * OZ_TM / OZ_KB;
                 if (tl > 0) {                                        // the epilogue has drained the previous tile's accumulators
+                    const long long c0 = g.prof ? clock64() : 0;
                     oz_mbar_wait(bar_tempty, (uint32_t)((tl - 1) & 1));
+                    if (g.prof) w_tempty += clock64() - c0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % NSTG;
-                    oz_mbar_wait(bar_full + 8 * s, (uint32_t)((it / NSTG) & 1));
+                    {
+                        const long long c0 = g.prof ? clock64() : 0;
+                        oz_mbar_wait(bar_full + 8 * s, (uint32_t)((it / NSTG) & 1));
+                        if (g.prof) w_full += clock64() - c0;
+                    }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = base + s * STAGE;
 #pragma unroll
@@ -541,10 +556,17 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
                 }
                 if (PAIR) oz_commit_pair(bar_tfull); else oz_commit(bar_tfull);
             }
+            if (g.prof) {
+                g.prof[(long)blockIdx.x * 8 + 0] = clock64() - c_start;
+                g.prof[(long)blockIdx.x * 8 + 1] = w_full;
+                g.prof[(long)blockIdx.x * 8 + 2] = w_tempty;
+                g.prof[(long)blockIdx.x * 8 + 6] = tl;
+            }
         }
     } else {
         const int lg = warp & 3;
         int tl = 0;
+        long long w_tfull = 0, w_drain = 0;
         for (int t = unit; t < total; t += units, ++tl) {
             int ibt, cb;
             oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
@@ -552,7 +574,9 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
             const int row = ib * OZ_TM + lg * 32 + lane;
             const double rs = ldexp(1.0, g.eP[row] + g.eK);
             const uint32_t redt = red + (uint32_t)((tl & 1) * 4 * OZ_TN * 8);
+            long long c1 = g.prof ? clock64() : 0;
             oz_mbar_wait(bar_tfull, (uint32_t)(tl & 1));
+            if (g.prof) { const long long c2 = clock64(); w_tfull += c2 - c1; c1 = c2; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -573,6 +597,7 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
                     if (tid == 64) {
                         if (PAIR) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(oz_map_to_rank(bar_tempty, 0)) : "memory");
                         else mbar_arrive(bar_tempty);
+                        if (g.prof) w_drain += clock64() - c1;
                     }
                 }
                 double q2[32];
@@ -597,6 +622,10 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
                 for (int w4 = 0; w4 < 4; ++w4) s2 += lds64(redt + (uint32_t)((w4 * OZ_TN + et) * 8));
                 g.part_ssq[(long)ib * g.ldpart + cb * OZ_TN + et] = s2;
             }
+        }
+        if (g.prof && tid == 64) {
+            g.prof[(long)blockIdx.x * 8 + 4] = w_tfull;
+            g.prof[(long)blockIdx.x * 8 + 5] = w_drain;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
