@@ -54,10 +54,13 @@ struct gpk_handle {
     DevBuf oz_scratch;
     CUtensorMap mapOzP32, mapOzK32, mapOzK32b;
     long oz_rows32 = 0, oz_rows32b = 0;
+    int oz_pdl = 1;                 // 1: look-ahead K* builder = small resident grid that triggers the dependent launch of the
+                                    //    contraction behind it on the SAME stream (real overlap); 0: side stream (tail overlap only)
+    int cov_ctas = 2;               // CTAs per SM of that resident builder grid
     int oz_prof = 0;                // 1: gpk_oz_persist_kernel accumulates clock64() wait sums per CTA (gpk_get_oz_profile)
     DevBuf oz_profbuf;
     int oz_prof_ctas = 0;
-    int oz_persist = 1;             // 1: one CTA (pair) per SM walks the tile list (gpk_oz_persist_kernel); 0: one CTA (pair) per tile
+    int oz_persist = 0;             // 1: one CTA (pair) per SM walks the tile list (gpk_oz_persist_kernel); 0: one CTA (pair) per tile
     int oz_pair = 0;                // 1: CTA pairs (tcgen05 cta_group::2, gpk_oz_pair_kernel) when the row-block count is even
     CUtensorMap mapOzKh, mapOzKh2;  // K* slices in 32-row boxes (the half tiles of a pair)
     int oz_fused = 1;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
@@ -322,6 +325,33 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// int8 contraction launch: optional CTA pair (cluster of 2) and optional programmatic dependency on the kernel launched
+// just before it on the stream (the resident look-ahead K* builder, which triggers at its start)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_oz(void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t stream, bool pair, bool dependent, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(OZ_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pair) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (dependent) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -842,7 +872,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         h->ev_g1.push_back(e2);
     }
     h->last_nchunks = nchunks;
-    auto launch_cov = [&](int ci, cudaStream_t st, bool small) -> int {
+    auto launch_cov = [&](int ci, cudaStream_t st, bool small, bool resident = false) -> int {
         const long base = (long)ci * cap;
         const long mc = std::min(cap, m - base);
         const long mcp = round_up(mc, BM);
@@ -860,13 +890,20 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             int mrc = make_cov_map(h, &map, (void*)train_operand(h), h->spec.n_terms, NP);
             if (mrc) return mrc;
             double* pmu = (pipelined && (ci & 1)) ? ptr<double>(h->oz_pmu2) : ptr<double>(h->part_mu);
-            const unsigned gx = (unsigned)(NP / 128);
-            if (small)
-                gpk_cov_oz_kernel<4><<<dim3(gx, (unsigned)(mcp / 16)), 256, cov_oz_smem_bytes(h->spec.n_terms, 4), st>>>(
-                    map, h->spec, h->n, dX + base * h->d, h->d, mc, lo, up, ptr<double>(h->alpha), oz_eK, qdst, NP, cap * NP, pmu, cap);
-            else
-                gpk_cov_oz_kernel<8><<<dim3(gx, (unsigned)(mcp / 32)), 256, cov_oz_smem_bytes(h->spec.n_terms, 8), st>>>(
-                    map, h->spec, h->n, dX + base * h->d, h->d, mc, lo, up, ptr<double>(h->alpha), oz_eK, qdst, NP, cap * NP, pmu, cap);
+            const int gx = (int)(NP / 128);
+            if (small) {
+                const int gy = (int)(mcp / 16);
+                const long items = (long)gx * gy;
+                const unsigned grid = resident ? (unsigned)std::min<long>(items, (long)std::max(h->n_sm, 1) * h->cov_ctas) : (unsigned)items;
+                gpk_cov_oz_kernel<4><<<grid, 256, cov_oz_smem_bytes(h->spec.n_terms, 4), st>>>(
+                    map, h->spec, h->n, dX + base * h->d, h->d, mc, lo, up, ptr<double>(h->alpha), oz_eK, qdst, NP, cap * NP, pmu, cap,
+                    gx, gy, resident ? 1 : 0);
+            } else {
+                const int gy = (int)(mcp / 32);
+                gpk_cov_oz_kernel<8><<<(unsigned)((long)gx * gy), 256, cov_oz_smem_bytes(h->spec.n_terms, 8), st>>>(
+                    map, h->spec, h->n, dX + base * h->d, h->d, mc, lo, up, ptr<double>(h->alpha), oz_eK, qdst, NP, cap * NP, pmu, cap,
+                    gx, gy, 0);
+            }
             CKL();
             return GPK_OK;
         }
@@ -881,7 +918,14 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         CKL();
         return GPK_OK;
     };
-    if (pipelined) {
+    // int8 path with the fused builder: everything on ONE stream.  The builder of chunk i+1 is a small resident grid
+    // (cov_ctas CTAs per SM) that triggers its dependents at once; the contraction of chunk i behind it is launched with
+    // the programmatic-stream-serialization attribute, so it starts while the builder runs and the two share the SMs
+    // (FP64 ALU + tensor pipe).  With two streams the block scheduler only placed the builder in the contraction's tail.
+    const bool chained = pipelined && oz_fused && h->oz_pdl;
+    if (chained) {
+        if ((rc = launch_cov(0, h->stream, false))) return rc;
+    } else if (pipelined) {
         CK(cudaEventRecord(h->ev_order, h->stream));          // side stream starts after all prior work
         CK(cudaStreamWaitEvent(h->side_stream, h->ev_order, 0));
         if ((rc = launch_cov(0, h->side_stream, false))) return rc;
@@ -893,7 +937,15 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         const long mcp = round_up(mc, BM);
         const bool last = ci == nchunks - 1;
         if (last) CK(cudaEventRecord(h->ev[8], h->stream));
-        if (pipelined) {
+        bool dependent = false;                                 // the contraction below is the dependent of a resident builder
+        if (chained) {
+            if (last) CK(cudaEventRecord(h->ev[10], h->stream));
+            CK(cudaEventRecord(h->ev_g0[ci], h->stream));       // nothing may sit between the builder and its dependent
+            if (ci + 1 < nchunks) {
+                if ((rc = launch_cov(ci + 1, h->stream, true, true))) return rc;
+                dependent = true;
+            }
+        } else if (pipelined) {
             CK(cudaStreamWaitEvent(h->stream, h->ev_cov[ci], 0));
             if (ci + 1 < nchunks) {
                 if (ci >= 1) CK(cudaStreamWaitEvent(h->side_stream, h->ev_gemm[ci - 1], 0));   // buffer (ci+1)&1 is free
@@ -915,8 +967,10 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         a.part_mu = ptr<double>(h->part_mu);
         a.part_ssq = ptr<double>(h->part_ssq);
         a.ldpart = cap;
-        if (last) CK(cudaEventRecord(h->ev[10], h->stream));
-        CK(cudaEventRecord(h->ev_g0[ci], h->stream));
+        if (!chained) {
+            if (last) CK(cudaEventRecord(h->ev[10], h->stream));
+            CK(cudaEventRecord(h->ev_g0[ci], h->stream));
+        }
         if (use_oz && h->oz_tile == 128) {
             Oz2Args o;
             o.nb = h->nb; o.ncb = (int)(mcp / OZ2_T); o.NP = (int)NP; o.rows = (int)cap;
@@ -926,17 +980,11 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             if (h->oz_pair && (h->nb % 2) == 0) {
                 // CTA pair, 256 x 128 per pair in two passes; its K* half tile (64 rows x 64 B) is the box of mapOzK
                 const int tiles = (o.nb / 2) * o.ncb;
-                cudaLaunchConfig_t cfg;
-                memset(&cfg, 0, sizeof(cfg));
-                cfg.gridDim = dim3((unsigned)(2 * (h->oz_persist ? std::min(tiles, std::max(h->n_sm, 2) / 2) : tiles)));
-                cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = OZQ_SMEM; cfg.stream = h->stream;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                CK(cudaLaunchKernelEx(&cfg, gpk_oz_pair2_kernel, h->mapOzP, second ? h->mapOzK2 : h->mapOzK, o));
+                const unsigned grid = (unsigned)(2 * (h->oz_persist == 1 ? std::min(tiles, std::max(h->n_sm, 2) / 2) : tiles));
+                CK(launch_oz(gpk_oz_pair2_kernel, grid, (size_t)OZQ_SMEM, h->stream, true, dependent, h->mapOzP, second ? h->mapOzK2 : h->mapOzK, o));
             } else
-                gpk_oz2_vargemm_kernel<<<o.nb * o.ncb, OZ_THREADS, OZ2_SMEM, h->stream>>>(h->mapOzP32, second ? h->mapOzK32b : h->mapOzK32, o);
+                CK(launch_oz(gpk_oz2_vargemm_kernel, (unsigned)(o.nb * o.ncb), (size_t)OZ2_SMEM, h->stream, false, dependent,
+                             h->mapOzP32, second ? h->mapOzK32b : h->mapOzK32, o));
             CKL();
             h->oz_launches += 1;
         } else if (use_oz) {
@@ -960,21 +1008,14 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
                 o.prof = ptr<long long>(h->oz_profbuf);
                 h->oz_prof_ctas = ctas;
             }
-            if (pair) {
-                cudaLaunchConfig_t cfg;
-                memset(&cfg, 0, sizeof(cfg));
-                cfg.gridDim = dim3((unsigned)(2 * units)); cfg.blockDim = dim3(OZ_THREADS);
-                cfg.dynamicSmemBytes = h->oz_persist ? OZP_PERSIST_SMEM : OZP_SMEM; cfg.stream = h->stream;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                if (h->oz_persist) CK(cudaLaunchKernelEx(&cfg, gpk_oz_persist_kernel<true>, h->mapOzP, mk, o));
-                else CK(cudaLaunchKernelEx(&cfg, gpk_oz_pair_kernel, h->mapOzP, mk, o));
-            } else if (h->oz_persist)
-                gpk_oz_persist_kernel<false><<<units, OZ_THREADS, OZ_PERSIST_SMEM, h->stream>>>(h->mapOzP, mk, o);
+            if (pair && h->oz_persist)
+                CK(launch_oz(gpk_oz_persist_kernel<true>, (unsigned)(2 * units), (size_t)OZP_PERSIST_SMEM, h->stream, true, dependent, h->mapOzP, mk, o));
+            else if (pair)
+                CK(launch_oz(gpk_oz_pair_kernel, (unsigned)(2 * units), (size_t)OZP_SMEM, h->stream, true, dependent, h->mapOzP, mk, o));
+            else if (h->oz_persist)
+                CK(launch_oz(gpk_oz_persist_kernel<false>, (unsigned)units, (size_t)OZ_PERSIST_SMEM, h->stream, false, dependent, h->mapOzP, mk, o));
             else
-                gpk_oz_vargemm_kernel<<<tiles, OZ_THREADS, OZ_SMEM, h->stream>>>(h->mapOzP, mk, o);
+                CK(launch_oz(gpk_oz_vargemm_kernel, (unsigned)tiles, (size_t)OZ_SMEM, h->stream, false, dependent, h->mapOzP, mk, o));
             CKL();
             h->oz_launches += 1;
         } else if (h->persist && h->loader == LOADER_TMA_WS) {
@@ -990,7 +1031,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
         } else if ((rc = launch_gemm<EPI_COLREDUCE>(h, h->mapP, second ? h->mapKs2 : h->mapKs, a, h->nb * a.mcb))) return rc;
         CK(cudaEventRecord(h->ev_g1[ci], h->stream));
         if (last) CK(cudaEventRecord(h->ev[11], h->stream));
-        if (pipelined && !oz_fused) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
+        if (pipelined && !chained && !oz_fused) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
         h->launches_var += 1;
         h->last_chunk_rows = mcp;
         FinishArgs f;
@@ -1015,7 +1056,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             CKL();
         }
         // fused int8 builder: it also writes this parity's mean partials, which the finish kernel above still reads
-        if (pipelined && oz_fused) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
+        if (pipelined && !chained && oz_fused) CK(cudaEventRecord(h->ev_gemm[ci], h->stream));
         if (last) CK(cudaEventRecord(h->ev[12], h->stream));
     }
     CK(cudaEventRecord(h->ev[7], h->stream));
@@ -1135,6 +1176,15 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
     if (!strcmp(key, "ozpersist")) {
         if (value < 0 || value > 2) BAD("ozpersist must be 0, 1 or 2");
         h->oz_persist = (int)value;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "ozpdl")) {
+        h->oz_pdl = (int)value;
+        return GPK_OK;
+    }
+    if (!strcmp(key, "covctas")) {
+        if (value < 1 || value > 8) BAD("covctas must be 1..8");
+        h->cov_ctas = (int)value;
         return GPK_OK;
     }
     if (!strcmp(key, "ozprof")) {

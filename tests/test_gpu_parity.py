@@ -918,15 +918,18 @@ def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
     X, y, Xs, theta, noise = O.synthetic_problem(N, D, M, seed_train=3)
     eta = float(np.min(y))
     res = {}
-    variants = (0, 1, 2, 3, 4, 5, 6, 7, 8)                  # 2: separate split / mean kernels; 3: two-pass 128 x 128 tiles;
+    variants = (0, 1, 2, 3, 4, 5, 6, 7, 8, 9)                # 2: separate split / mean kernels; 3: two-pass 128 x 128 tiles;
     for oz in variants:                                     # 4: CTA pairs (tcgen05 cta_group::2); 5, 6: one CTA (pair) per tile;
                                                             # 7, 8: CTA pairs, 256 x 128 in two passes (persistent / per tile)
+                                                            # 9: look-ahead K* builder on the side stream instead of the
+                                                            #    resident grid + programmatic dependent launch
         h, logdet, ll, diag_add, mean = _handle_for("matern52", theta, X, y, noise)
         h.set_option("ozaki", 1 if oz else 0)
         h.set_option("ozfused", 0 if oz == 2 else 1)
         h.set_option("oztile", 128 if oz in (3, 7, 8) else 64)
         h.set_option("ozpair", 1 if oz in (4, 6, 7, 8) else 0)
-        h.set_option("ozpersist", 0 if oz in (5, 6, 8) else 1)
+        h.set_option("ozpersist", 0 if oz in (5, 6, 8, 9) else 1)
+        h.set_option("ozpdl", 0 if oz == 9 else 1)
         res[oz] = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
         if oz:                                              # chunking must stay invisible on the int8 path too
             h.set_option("chunk", 1024)
@@ -949,7 +952,7 @@ def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
         assert_acq_close(res[oz]["values"], O.acq_ei(mu_ref, var_ref, eta), rtol=1e-8, atol=1e-13)
     assert all(res[oz]["best_idx"] == int(np.argmax(O.acq_ei(mu_ref, var_ref, eta))) for oz in variants)
     np.testing.assert_array_equal(res[1]["var"], res[2]["var"])       # same digits either way
-    for oz in (4, 5, 6, 7, 8):                                        # same integers, same epilogue order: pairs and the
+    for oz in (4, 5, 6, 7, 8, 9):                                     # same integers, same epilogue order: pairs and the
         np.testing.assert_array_equal(res[1]["var"], res[oz]["var"])  # persistent tile walk change nothing
     # ill-conditioned factor (tiny noise, long length scales): row exponents of L^-1 exceed the 8-slice budget -> fp64
     theta_bad = theta + np.r_[0.0, np.full(D, np.log(4.0))]
