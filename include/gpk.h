@@ -278,6 +278,9 @@ int gpk_measure_fp64_peaks(gpk_handle* h, double* dmma_tflops, double* dfma_tflo
 /* int8 tensor-pipe issue-rate peak in TOP/s (tcgen05.mma kind::i8, 128 x 128 x 32, operands in shared memory,
  * accumulator in TMEM): the roofline denominator of the option-"ozaki" contraction. */
 int gpk_measure_int8_peak(gpk_handle* h, double* tops);
+/* the same kernel launched back to back for `seconds` (<= 10); reports the rate of the second half, i.e. at the SM clock
+ * the board's power limit allows for this pipe: the denominator for a kernel timed inside a long step. */
+int gpk_measure_int8_peak_sustained(gpk_handle* h, double seconds, double* tops);
 
 /* ---- introspection (tests / debugging) ----------------------------------------------- */
 int gpk_get_factor(gpk_handle* h, double* L /* n x n row-major, lower */);

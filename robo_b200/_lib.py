@@ -64,6 +64,7 @@ _SIGNATURES = {
     "gpk_nll_grad": [_vp, C.c_double, _dp],
     "gpk_measure_fp64_peaks": [_vp, _dp, _dp],
     "gpk_measure_int8_peak": [_vp, _dp],
+    "gpk_measure_int8_peak_sustained": [_vp, C.c_double, _dp],
     "gpk_get_factor": [_vp, _dp],
     "gpk_get_linv": [_vp, _dp],
     "gpk_get_z": [_vp, _dp],
@@ -392,6 +393,12 @@ class Handle(object):
         """-> int8 tensor-pipe issue-rate peak in TOP/s (tcgen05 kind::i8) measured on this GPU."""
         a = C.c_double()
         self._check(self.lib.gpk_measure_int8_peak(self._h, C.byref(a)))
+        return a.value
+
+    def measure_int8_peak_sustained(self, seconds=0.4):
+        """-> the same issue rate held for `seconds` (second half timed): what the power limit leaves of the burst figure."""
+        a = C.c_double()
+        self._check(self.lib.gpk_measure_int8_peak_sustained(self._h, float(seconds), C.byref(a)))
         return a.value
 
     # -- introspection ----------------------------------------------------------------

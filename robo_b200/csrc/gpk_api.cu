@@ -2453,6 +2453,38 @@ int gpk_measure_int8_peak(gpk_handle* h, double* tops) {
     return GPK_OK;
 }
 
+int gpk_measure_int8_peak_sustained(gpk_handle* h, double seconds, double* tops) {
+    if (!h || !tops || !(seconds > 0.0) || seconds > 10.0) return GPK_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    // back-to-back launches of the issue-rate kernel for `seconds`; the rate of the SECOND half is reported: by then the
+    // SM clock has settled where the board's power limit puts it (the int8 pipe at full rate runs into sw_power_cap)
+    const int blocks = std::max(h->n_sm, 1), iters = 8000, smem = 2 * 8192 + 1024 + 64;
+    const double ops = 2.0 * 128 * 128 * 32 * 2.0 * iters * blocks;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float ms1 = 0.f;
+    CK(cudaEventRecord(e0, h->stream));
+    gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters);
+    CKL();
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms1, e0, e1));
+    const int n_half = std::max(1, (int)(0.5 * seconds * 1e3 / std::max(ms1, 1e-3f)));
+    for (int i = 0; i < n_half; ++i) gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters);
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < n_half; ++i) gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters);
+    CKL();
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tops = ops * n_half / (ms * 1e-3) / 1e12;
+    return GPK_OK;
+}
+
 int gpk_get_factor(gpk_handle* h, double* L) {
     int rc = require(h, true, true, true);
     if (rc) return rc;
