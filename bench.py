@@ -49,7 +49,10 @@ N_TRAIN, DIM = 4096, 16
 METRIC = "EI evals/sec (GP N=4096, D=16, fp64)"
 FP64_PEAK_TFLOPS = 37.0      # SURVEY.md section 8d "P64": B200 FP64 / FP64-tensor datasheet (296 TF per 8-GPU HGX)
 VARGEMM_NCU_CSV = os.path.join("profiles", "r02_vargemm_fp64_ncu_full_raw.csv")
-OZ_NCU_CSV = os.path.join("profiles", "r02_oz_vargemm_ncu_full_raw.csv")
+OZ_NCU_CSV = os.path.join("profiles", "r02_oz_pair2_ncu_full_raw.csv")
+OZ_KERNELS = {1: "gpk_oz_vargemm_kernel (128 x 64 tile per CTA, one pass)", 2: "gpk_oz_pair_kernel (CTA pair, 256 x 64, one pass)",
+              3: "gpk_oz2_vargemm_kernel (128 x 128 per CTA, two passes)",
+              4: "gpk_oz_pair2_kernel (CTA pair, tcgen05 cta_group::2: 256 x 128 per pair, two passes)"}
 
 
 def train_problem(n=N_TRAIN, d=DIM):
@@ -560,11 +563,13 @@ def run_ours(args, rank, world, local_rank):
         # triangle of L^-1 in 128-row blocks = pairs (N^2 + 128 N) int8 multiply-adds x 2 per candidate row
         pairs = float(tim.get("ozaki_slice_pairs") or 28.0)
         int8_ops = float(last_rows) * pairs * (N_TRAIN ** 2 + 128 * N_TRAIN)
-        oz_traffic = ncu_dram_bytes(OZ_NCU_CSV, "gpk_oz") if last_rows == 16384 else None
+        oz_traffic = (ncu_dram_bytes(OZ_NCU_CSV, "gpk_oz_pair2")
+                      if last_rows == 16384 and int(tim.get("ozaki_kernel_variant", 0)) == 4 else None)
         int8_achieved = int8_ops / (gemm_ms * 1e-3) / 1e12
         roofline = dict(fp64_block, bound="tensor",
-                        kernel="gpk_oz_vargemm_kernel (L^-1 K*^T as %d int8 slice-pair products, tcgen05.mma kind::i8, TMEM "
-                               "accumulators, TMA-staged swizzled slices)" % int(pairs),
+                        kernel="%s%s: L^-1 K*^T as %d int8 slice-pair products, tcgen05.mma kind::i8, TMEM accumulators, TMA-staged "
+                               "swizzled slices" % (OZ_KERNELS.get(int(tim.get("ozaki_kernel_variant", 0)) & 7, "int8 contraction"),
+                                                    ", persistent tile walk" if int(tim.get("ozaki_kernel_variant", 0)) & 8 else "", int(pairs)),
                         achieved=int8_achieved, peak=int8_peak_sustained, unit="TFLOP/s", frac=int8_achieved / int8_peak_sustained,
                         peak_burst=int8_peak, frac_of_burst_peak=int8_achieved / int8_peak,
                         ops="int8 multiply-accumulate counted as 2 ops (TOP/s)",

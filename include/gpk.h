@@ -294,7 +294,8 @@ int gpk_get_z(gpk_handle* h, double* z /* n */);
  * out[9] = total kernel launches so far,
  * out[10] = of those, launches of the int8 (Ozaki) contraction; out[11] = largest row exponent of L^-1 seen by it
  * (option "ozaki"); out[12] = option "persist"; out[13] = int8 slice-pair products the int8 contraction spends per
- * fp64 product (28: 7 balanced base-256 digits per operand); out[14..15] reserved (zero). */
+ * fp64 product (28: 7 balanced base-256 digits per operand); out[14] = which int8 kernel ran last (1 one pass, 2 one pass on
+ * CTA pairs, 3 two passes, 4 two passes on CTA pairs = the default; + 8: persistent tile walk); out[15] reserved (zero). */
 int gpk_get_timings(gpk_handle* h, double* out16);
 /* diagnostics of the persistent int8 contraction (option "ozprof" = 1): per CTA of its last launch 8 clock64() sums:
  * [0] MMA issuer loop, [1] of it waiting for staged operands, [2] waiting for the epilogue to drain TMEM, [3] TMA producer

@@ -434,7 +434,7 @@ class Handle(object):
         self._check(self.lib.gpk_get_timings(self._h, _as_dp(t)))
         keys = ["fit_ms", "kbuild_ms", "potrf_ms", "linv_ms", "score_ms", "kstar_ms", "vargemm_ms", "finish_ms",
                 "launches_vargemm", "launches_total", "launches_ozaki", "ozaki_max_row_exponent", "persist",
-                "ozaki_slice_pairs"]
+                "ozaki_slice_pairs", "ozaki_kernel_variant"]
         return dict(zip(keys, t.tolist()))
 
 

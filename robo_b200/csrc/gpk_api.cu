@@ -50,18 +50,21 @@ struct gpk_handle {
     // variance contraction on the int8 tensor pipe (gpk_ozaki.cuh); 0 = fp64 DMMA kernels
     int ozaki = 1;
     DevBuf oz_Pq, oz_Kq, oz_Kq2, oz_eP, oz_emax, oz_mu, oz_mu2, oz_pmu2;
-    int oz_tile = 64;               // 64: one pass, 128 x 64 tiles (gpk_oz_vargemm_kernel); 128: two passes, 128 x 128 tiles
+    int oz_tile = 128;              // 128: two passes, 128 candidates per tile (with oz_pair: 256 x 128 per CTA pair, gpk_oz_pair2_kernel:
+                                    // the default; an odd row-block count falls back to the one-pass single-CTA kernel); 64: one pass
     DevBuf oz_scratch;
     CUtensorMap mapOzP32, mapOzK32, mapOzK32b;
     long oz_rows32 = 0, oz_rows32b = 0;
-    int oz_pdl = 1;                 // 1: look-ahead K* builder = small resident grid that triggers the dependent launch of the
+    int oz_pdl = 0;                 // 1: look-ahead K* builder = small resident grid that triggers the dependent launch of the
                                     //    contraction behind it on the SAME stream (real overlap); 0: side stream (tail overlap only)
     int cov_ctas = 2;               // CTAs per SM of that resident builder grid
+    int oz_last_variant = 0;        // contraction kernel of the last int8 launch: 1 one pass, 2 one pass CTA pair, 3 two passes, 4 two passes
+                                    // CTA pair; + 8 when the persistent tile walk ran
     int oz_prof = 0;                // 1: gpk_oz_persist_kernel accumulates clock64() wait sums per CTA (gpk_get_oz_profile)
     DevBuf oz_profbuf;
     int oz_prof_ctas = 0;
     int oz_persist = 0;             // 1: one CTA (pair) per SM walks the tile list (gpk_oz_persist_kernel); 0: one CTA (pair) per tile
-    int oz_pair = 0;                // 1: CTA pairs (tcgen05 cta_group::2, gpk_oz_pair_kernel) when the row-block count is even
+    int oz_pair = 1;                // 1: CTA pairs (tcgen05 cta_group::2) when the row-block count is even
     CUtensorMap mapOzKh, mapOzKh2;  // K* slices in 32-row boxes (the half tiles of a pair)
     int oz_fused = 1;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
     long oz_linv_serial = -1;       // linv_serial the slices of L^-1 were made for
@@ -971,13 +974,15 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             if (last) CK(cudaEventRecord(h->ev[10], h->stream));
             CK(cudaEventRecord(h->ev_g0[ci], h->stream));
         }
-        if (use_oz && h->oz_tile == 128) {
+        const bool oz_pair_ok = h->oz_pair && (h->nb % 2) == 0;
+        if (use_oz && h->oz_tile == 128 && (oz_pair_ok || !h->oz_pair)) {
             Oz2Args o;
             o.nb = h->nb; o.ncb = (int)(mcp / OZ2_T); o.NP = (int)NP; o.rows = (int)cap;
             o.group = (int)std::min<long>(64, std::max<long>(2, ((long)64 << 20) / ((long)OZ2_T * NP * OZ_S)));
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart; o.scratch = ptr<double>(h->oz_scratch);
-            if (h->oz_pair && (h->nb % 2) == 0) {
+            h->oz_last_variant = oz_pair_ok ? 4 + (h->oz_persist == 1 ? 8 : 0) : 3;
+            if (oz_pair_ok) {
                 // CTA pair, 256 x 128 per pair in two passes; its K* half tile (64 rows x 64 B) is the box of mapOzK
                 const int tiles = (o.nb / 2) * o.ncb;
                 const unsigned grid = (unsigned)(2 * (h->oz_persist == 1 ? std::min(tiles, std::max(h->n_sm, 2) / 2) : tiles));
@@ -994,13 +999,14 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart;
             o.prof = nullptr;
-            const bool pair = h->oz_pair && (h->nb % 2) == 0;
+            const bool pair = oz_pair_ok && h->oz_tile != 128;
             const CUtensorMap& mk = pair ? (second ? h->mapOzKh2 : h->mapOzKh) : (second ? h->mapOzK2 : h->mapOzK);
             const int tiles = pair ? (o.nb / 2) * o.ncb : o.nb * o.ncb;
             const int sms = std::max(h->n_sm, 2);
             // "ozpersist" 1: one CTA (pair) per SM walks the tile list; 2: the same kernel, one tile per CTA (pair); 0: the
             // one-tile kernels
             const int units = h->oz_persist == 1 ? std::min(tiles, pair ? sms / 2 : sms) : tiles;
+            h->oz_last_variant = (pair ? 2 : 1) + (h->oz_persist == 1 ? 8 : 0);
             if (h->oz_prof && h->oz_persist) {
                 const int ctas = pair ? 2 * units : units;
                 if ((rc = ensure(h, h->oz_profbuf, (size_t)ctas * 64))) return rc;
@@ -2575,6 +2581,7 @@ int gpk_get_timings(gpk_handle* h, double* out /* 16 */) {
     out[11] = (double)h->oz_emax_host;
     out[12] = (double)h->persist;
     out[13] = (double)OZ_PAIRS;
+    out[14] = (double)h->oz_last_variant;
     return GPK_OK;
 }
 

@@ -6,7 +6,7 @@
 //   P  = L^-1 :  P[i][k]  ~ 2^eP[i] sum_s Pq[s][i][k] 2^(-8 (s+1))     per-row exponent, S = 7 balanced base-256 digits
 //   K*        :  K*[c][k] ~ 2^eK    sum_t Kq[t][c][k] 2^(-8 (t+1))     one exponent (0 < k <= amp)
 //   V[i][c] = 2^(eP[i] + eK) sum_lvl 2^(-8 (lvl + 2)) sum_{s + t = lvl} <Pq[s][i][:], Kq[t][c][:]>      (lvl < S)
-// Digits are BALANCED (-128 .. 127, oz_digit below), so every int8 carries 8 bits: 7 slices hold 56 bits of each
+// Digits are BALANCED (-128 .. 127, oz_digits below), so every int8 carries 8 bits: 7 slices hold 56 bits of each
 // operand relative to its row maximum and the triangle s + t < 7 has 28 slice pairs.  (The first version cut 7-bit
 // truncated digits: 8 slices, 36 pairs, for a LARGER error — tools/ozaki_study.py prints both.)  The pairs of one
 // level share one int32 accumulator ((lvl + 1) K 128^2 < 2^31 for K <= 16384), so a 128 x 64 tile keeps 7 accumulators
@@ -45,15 +45,17 @@ __host__ __device__ inline int oz_exponent(double amax) {
     const double m = frexp(amax, &ex);
     return ex + 1 + (m * 128.0 >= 127.49 ? 1 : 0);
 }
-// next balanced base-256 digit of the remainder v (v in [-128/255, 127/255)): v <- 256 v - d with d = floor(256 v +
-// 128/255) in -128 .. 127; the new remainder lies in the same interval, so every digit fits an int8 and the S-digit
-// sum is within 0.502 * 256^-S of the value.  All operations are exact in fp64 (power-of-two scaling, integer part).
-__device__ __forceinline__ int oz_digit(double& v) {
-    v *= 256.0;
-    const double t = fmin(fmax(floor(v + 128.0 / 255.0), -128.0), 127.0);
-    v -= t;
-    return (int)t;
+// The OZ_S balanced base-256 digits of v (|v| < 127.49 / 256, i.e. already scaled by 2^-e), most significant first in
+// the bytes 6 .. 0 of the result, each digit d as the int8 bit pattern: v ~ sum_s d_s 256^-(s+1), |error| <= 2^-57.
+// Integer arithmetic: X = rint(v 2^56) (exact power-of-two scaling, one F2I), then with B = 0x80 in every byte the
+// bytes b of X + B are the digits + 128 (sum (b_j - 128) 256^j = X, and 0 <= X + B < 2^56 because |X| < 0.997 2^55), so
+// XOR 0x80 turns each byte into the two's-complement digit.  One conversion and three integer instructions replace
+// seven rounds of scale / floor / clamp / subtract in fp64.
+__device__ __forceinline__ unsigned long long oz_digits(double v) {
+    const long long X = __double2ll_rn(v * 72057594037927936.0);             // 2^56
+    return (unsigned long long)(X + 0x0080808080808080LL) ^ 0x0080808080808080ULL;
 }
+__device__ __forceinline__ int oz_digit_of(unsigned long long y, int s) { return (int)((y >> (8 * (OZ_S - 1 - s))) & 0xFFull); }
 
 __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
@@ -119,7 +121,9 @@ __global__ void gpk_oz_split_kernel(const double* __restrict__ A, long rows, lon
     const long r = idx / ld;
     double v = ldexp(A[idx], -(erow ? erow[r] : e0));
 #pragma unroll
-    for (int s = 0; s < OZ_S; ++s) q[(long)s * slice_stride + idx] = (int8_t)oz_digit(v);
+    const unsigned long long y = oz_digits(v);
+#pragma unroll
+    for (int s = 0; s < OZ_S; ++s) q[(long)s * slice_stride + idx] = (int8_t)oz_digit_of(y, s);
 }
 
 // ---- the contraction ----------------------------------------------------------------------------------------------
@@ -1144,13 +1148,11 @@ gpk_cov_oz_kernel(const __grid_constant__ CUtensorMap mapX, const KSpec ks, int 
             const double k0 = (cv && v0) ? ks.amp * pr[c][0] : 0.0;
             const double k1 = (cv && v1) ? ks.amp * pr[c][1] : 0.0;
             // digits: two adjacent int8 per slice
-            double r0 = k0 * sc, r1 = k1 * sc;
+            const unsigned long long y0 = oz_digits(k0 * sc), y1 = oz_digits(k1 * sc);
             int8_t* dst = Kq + ci * ldq + j0;
 #pragma unroll
-            for (int s2 = 0; s2 < OZ_S; ++s2) {
-                const int i0 = oz_digit(r0), i1 = oz_digit(r1);
-                *reinterpret_cast<uint16_t*>(dst + (long)s2 * slice_stride) = (uint16_t)((i0 & 0xFF) | ((i1 & 0xFF) << 8));
-            }
+            for (int s2 = 0; s2 < OZ_S; ++s2)
+                *reinterpret_cast<uint16_t*>(dst + (long)s2 * slice_stride) = (uint16_t)(oz_digit_of(y0, s2) | (oz_digit_of(y1, s2) << 8));
             // mean share of this tile: reduce over the 64 threads (2 warps) of the candidate group, fixed order
             double pm = fma(k0, a0, k1 * a1);
 #pragma unroll

@@ -954,6 +954,16 @@ def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
     np.testing.assert_array_equal(res[1]["var"], res[2]["var"])       # same digits either way
     for oz in (4, 5, 6, 7, 8, 9):                                     # same integers, same epilogue order: pairs and the
         np.testing.assert_array_equal(res[1]["var"], res[oz]["var"])  # persistent tile walk change nothing
+    # odd number of 128-row blocks (N = 1100 -> 9): the default CTA-pair kernel does not apply, the one-pass kernel runs
+    Xo, yo, Xso, theta_o, noise_o = O.synthetic_problem(1100, D, 2500, seed_train=5)
+    h, logdet, ll, diag_add, mean = _handle_for("matern52", theta_o, Xo, yo, noise_o)
+    r = h.acq(Xso, _lib.ACQ_EI, float(np.min(yo)), 0.0, want_values=True, want_moments=True)
+    assert h.timings()["launches_ozaki"] >= 1
+    h.close()
+    st = O.gp_fit(oracle_kernel("matern52", theta_o, D), Xo, yo, noise=noise_o, normalize_input=False)
+    mu_ref, var_ref = O.gp_predict_var_only_fast(st, Xso)
+    assert_mean_close(r["mu"], mu_ref, yo)
+    assert_var_close(r["var"], var_ref, float(np.exp(theta_o[0])))
     # ill-conditioned factor (tiny noise, long length scales): row exponents of L^-1 exceed the 8-slice budget -> fp64
     theta_bad = theta + np.r_[0.0, np.full(D, np.log(4.0))]
     h, logdet, ll, diag_add, mean = _handle_for("matern52", theta_bad, X, y, 1e-8)

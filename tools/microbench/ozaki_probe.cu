@@ -132,12 +132,11 @@ __global__ void oz_split_kernel(const double* __restrict__ A, long rows, long co
     const long r = idx / cols;
     double v = ldexp(A[idx], -(mode == 0 ? e[r] : e[0]));
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        v *= 256.0;
-        const double t = fmin(fmax(floor(v + 128.0 / 255.0), -128.0), 127.0);     // balanced digit, remainder stays in range
-        v -= t;
-        q[(long)s * rows * cols + idx] = (int8_t)(int)t;
-    }
+    // balanced base-256 digits by integer arithmetic: X = rint(v 2^56); the bytes of X + 0x80..80 are the digits + 128
+    const long long X = __double2ll_rn(v * 72057594037927936.0);
+    const unsigned long long y = (unsigned long long)(X + 0x0080808080808080LL) ^ 0x0080808080808080ULL;
+#pragma unroll
+    for (int s = 0; s < S; ++s) q[(long)s * rows * cols + idx] = (int8_t)((y >> (8 * (S - 1 - s))) & 0xFFull);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -45,7 +45,14 @@ def split256(A, S, axis, global_max=None):
     e = np.where(mx > 0, ex + 1 + (m * 128.0 >= 127.49), 0).astype(float)
     r = A / np.exp2(e)
     Q = []
-    for _ in range(S):
+    if S <= 7:
+        # the kernel's way (oz_digits): X = rint(v 256^S), the bytes of X + 0x80..80 are the digits + 128
+        X = np.rint(r * 256.0 ** S).astype(np.int64)
+        Y = X + sum(128 << (8 * j) for j in range(S))
+        for s_ in range(S):
+            Q.append((((Y >> (8 * (S - 1 - s_))) & 0xFF) - 128).astype(np.float64))
+        return Q, e
+    for _ in range(S):                                   # more than 56 bits: same digits by floating-point peeling
         r = r * 256.0
         q = np.clip(np.floor(r + 128.0 / 255.0), -128, 127)
         r = r - q

@@ -18,7 +18,8 @@ cap() {  # name regex skip [env]
       python tools/profile_driver.py 4096 16 32768 > $out/${tag}_$1.log 2>&1
   tail -2 $out/${tag}_$1.log
 }
-cap oz_vargemm        'gpk_oz_vargemm_kernel'   2      X=1           # int8 variance contraction (default scoring kernel)
+cap oz_pair2          'gpk_oz_pair2_kernel'     2      X=1           # int8 variance contraction, CTA pair x two passes (default scoring kernel)
+cap oz_vargemm        'gpk_oz_vargemm_kernel'   2      'GPK_OZPAIR=0 GPK_OZTILE=64'   # one-pass single-CTA int8 contraction
 cap cov_oz            'gpk_cov_oz_kernelILi4E'  1      X=1           # fused covariance builder + int8 digits (look-ahead chunk)
 cap cov_kbuild        'gpk_cov_tma_kernelILi8E' 2      X=1           # third fit's K build (tri = 1)
 cap cov_kstar_fp64    'gpk_cov_tma_kernelILi4E' 1      GPK_OZAKI=0   # fp64 K* of a look-ahead chunk
