@@ -957,6 +957,7 @@ def test_ozaki_int8_contraction_matches_fp64_contraction_and_oracle():
     # odd number of 128-row blocks (N = 1100 -> 9): the default CTA-pair kernel does not apply, the one-pass kernel runs
     Xo, yo, Xso, theta_o, noise_o = O.synthetic_problem(1100, D, 2500, seed_train=5)
     h, logdet, ll, diag_add, mean = _handle_for("matern52", theta_o, Xo, yo, noise_o)
+    h.set_option("ozaki", 1)
     r = h.acq(Xso, _lib.ACQ_EI, float(np.min(yo)), 0.0, want_values=True, want_moments=True)
     assert h.timings()["launches_ozaki"] >= 1
     h.close()
