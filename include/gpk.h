@@ -69,14 +69,25 @@ const char* gpk_version(void);
  *               N = 4096) is captured once per layout into a CUDA graph and replayed per fit [default]; 0 = enqueue
  *               every call directly
  *   "ozaki"     1 = variance contraction on the int8 tensor pipe (tcgen05 kind::i8, TMEM accumulators) through an
- *               error-free 8 x 8 slice split of L^-1 and K* (gpk_ozaki.cuh); used while max |L^-1| < 64, otherwise the
- *               fp64 kernel runs [default; batches of >= 2048 candidates]; 0 = always fp64 DMMA.  The posterior mean
- *               never goes through the slices (fp64 K* alpha)
- *   "oztile"    64 = int8 contraction in one pass, 128 x 64 tiles, 8 accumulators of 64 TMEM columns [default]; 128 = two
- *               passes over the contraction (levels 0..3, then 4..7), 128 x 128 tiles, 4 accumulators of 128 columns
- *               (kind::i8 reads both operands from shared memory: the wider MMA halves the operand bytes per product)
+ *               error-free split of L^-1 and K* into 7 balanced base-256 digits each, 28 digit-pair products
+ *               (gpk_ozaki.cuh); used while max |L^-1| < 64 and N <= 16384, otherwise the fp64 kernel runs [default;
+ *               batches of >= 2048 candidates]; 0 = always fp64 DMMA.  The posterior mean never goes through the digits
+ *               (fp64 K* alpha)
+ *   "oztile"    128 = two passes over the contraction (levels 4..6, then 0..3), 128 candidates per tile [default];
+ *               64 = one pass, 64 candidates per tile, 7 accumulators of 64 TMEM columns
+ *   "ozpair"    1 = CTA pairs (tcgen05 cta_group::2, cluster of 2): 256 rows of L^-1 per pair, each CTA stages half of the
+ *               K* slice tiles [default, with "oztile" 128: gpk_oz_pair2_kernel; needs an even number of 128-row blocks,
+ *               otherwise the one-pass single-CTA kernel runs]; 0 = one CTA per tile
+ *   "ozpersist" 0 = one CTA (pair) per tile [default]; 1 = one CTA (pair) per SM walks the tile list; 2 = the persistent
+ *               kernel launched with one tile per CTA (profiling aid).  Measured: 3.3 ms alone, 4.0 - 4.3 ms inside a
+ *               scoring step (profiles/r02_int8_variants_bench.txt)
+ *   "ozpdl"     1 = the look-ahead K* builder runs as a small resident grid ("covctas" CTAs per SM) that triggers a
+ *               programmatic dependent launch of the contraction behind it on the same stream (the two really co-run);
+ *               0 = builder on the side stream (the block scheduler places it in the contraction's tail) [default: the
+ *               co-running contraction loses more than the builder costs]
  *   "ozfused"   1 = with "ozaki": the covariance builder writes the int8 digits and the mean partials itself, no fp64
- *               K* in HBM [default: 3.35 vs 3.16 M EI/s at N = 4096]; 0 = fp64 K* + split kernel + mean dot
+ *               K* in HBM [default]; 0 = fp64 K* + split kernel + mean dot
+ *   "ozprof"    1 = the persistent int8 kernel accumulates clock64() sums per role (gpk_get_oz_profile)
  *   "persist"   1 = persistent fp64 variance contraction (one CTA per SM, dynamic tile counter); 0 = one CTA per tile
  *               [default: the persistent variant measured 2 % slower at N = 4096 and equal at N = 1024]
  *   "depth2"    1 = trailing updates of two consecutive panels in one K = 256 contraction (odd steps; even steps update

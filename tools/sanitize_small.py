@@ -39,18 +39,23 @@ for loader, diag in ((2, 4), (1, 3), (0, 2)):
 Xb = rng.rand(2304, D)
 hs = []
 for opts in ({"ozaki": 1, "ozfused": 1}, {"ozaki": 1, "ozfused": 0}, {"ozaki": 0, "persist": 1},
-             {"ozaki": 0, "chainsplit": 1, "graph": 1, "depth2": 1}):
+             {"ozaki": 0, "chainsplit": 1, "graph": 1, "depth2": 1},
+             # int8 contraction variants: one pass / CTA pair / two passes / persistent walk / resident builder + dependent launch
+             {"ozaki": 1, "oztile": 64, "ozpair": 0}, {"ozaki": 1, "oztile": 64, "ozpair": 1}, {"ozaki": 1, "oztile": 128, "ozpair": 0},
+             {"ozaki": 1, "oztile": 64, "ozpair": 0, "ozpersist": 1}, {"ozaki": 1, "oztile": 64, "ozpair": 1, "ozpersist": 1},
+             {"ozaki": 1, "ozpersist": 1}, {"ozaki": 1, "ozpdl": 1}):
     h = _lib.Handle(0)
     for k, v in opts.items():
         h.set_option(k, v)
     h.set_option("chunk", 1024)
-    h.set_data(X, y)
+    Xt, yt = (X, y) if len(hs) < 4 else (X[:250], y[:250])       # 250 rows = 2 row blocks: the CTA-pair kernels apply
+    h.set_data(Xt, yt)
     h.set_kernel(f["family"], f["log_amp"], f["axis"], f["group"], f["log_metric"])
     for _ in range(2):
-        ll = h.fit(1e-3 + 1.25e-12, float(y.mean()))
+        ll = h.fit(1e-3 + 1.25e-12, float(yt.mean()))
     r = h.acq(Xb, _lib.ACQ_EI, float(y.min()), 0.0, want_values=True, want_moments=True)
     t = h.timings()
-    print(opts, "fit", ll, "best", r["best_idx"], "oz launches", t["launches_ozaki"])
+    print(opts, "fit", ll, "best", r["best_idx"], "oz launches", t["launches_ozaki"], "variant", t["ozaki_kernel_variant"])
     mu, cov = h.posterior_cov(Xs[:100])
     hs.append(h)
 rm = _lib.acq_multi(hs[:3], Xs[:300], 0, _lib.ACQ_EI, [float(y.min())] * 3, 0.0, want_argmax=True)
