@@ -981,11 +981,18 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             o.group = (int)std::min<long>(64, std::max<long>(2, ((long)64 << 20) / ((long)OZ2_T * NP * OZ_S)));
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart; o.scratch = ptr<double>(h->oz_scratch);
+            o.prof = nullptr;
             h->oz_last_variant = oz_pair_ok ? 4 + (h->oz_persist == 1 ? 8 : 0) : 3;
             if (oz_pair_ok) {
                 // CTA pair, 256 x 128 per pair in two passes; its K* half tile (64 rows x 64 B) is the box of mapOzK
                 const int tiles = (o.nb / 2) * o.ncb;
                 const unsigned grid = (unsigned)(2 * (h->oz_persist == 1 ? std::min(tiles, std::max(h->n_sm, 2) / 2) : tiles));
+                if (h->oz_prof) {
+                    if ((rc = ensure(h, h->oz_profbuf, (size_t)grid * 64))) return rc;
+                    CK(cudaMemsetAsync(h->oz_profbuf.p, 0, (size_t)grid * 64, h->stream));
+                    o.prof = ptr<long long>(h->oz_profbuf);
+                    h->oz_prof_ctas = (int)grid;
+                }
                 CK(launch_oz(gpk_oz_pair2_kernel, grid, (size_t)OZQ_SMEM, h->stream, true, dependent, h->mapOzP, second ? h->mapOzK2 : h->mapOzK, o));
             } else
                 CK(launch_oz(gpk_oz2_vargemm_kernel, (unsigned)(o.nb * o.ncb), (size_t)OZ2_SMEM, h->stream, false, dependent,

@@ -319,6 +319,9 @@ gpk_oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
     const uint32_t red = base + OZP_NSTG * OZP_STAGE + 256;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = (int)oz_cluster_rank();
+    // each CTA of the pair publishes the (identical) TMEM base address in its own word: the collective cta_group::2
+    // allocation writes through both CTAs' shared memory, and two words keep compute-sanitizer's racecheck quiet
+    const uint32_t tmem_slot_own = tmem_slot + 8u * (uint32_t)crank;
     int ibp, cb;
     oz_tile_of((int)blockIdx.x / 2, g.nb / 2, g.ncb, g.group, ibp, cb);
     const int ib = 2 * ibp + crank;
@@ -331,7 +334,7 @@ gpk_oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
         fence_proxy_async();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_own), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -339,7 +342,7 @@ gpk_oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
     oz_cluster_sync();                                               // both CTAs' barriers and TMEM exist
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot_own) : "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -453,6 +456,7 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     const uint32_t red = base + NSTG * STAGE + 256;                  // 2 x [4 lane groups][64 columns]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = PAIR ? (int)oz_cluster_rank() : 0;
+    const uint32_t tmem_slot_own = tmem_slot + 8u * (uint32_t)crank;     // see gpk_oz_pair_kernel
     const int unit = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x, units = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
     const int rows_per_tile = PAIR ? 2 : 1;
     const int nrow_tiles = g.nb / rows_per_tile, total = nrow_tiles * g.ncb;
@@ -466,10 +470,10 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     }
     if (warp == 1) {
         if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_own), "r"(512u) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_own), "r"(512u) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
@@ -478,7 +482,7 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     if (PAIR) oz_cluster_sync();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot_own) : "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -676,6 +680,7 @@ struct Oz2Args {
     const int* eP; int eK;
     double* part_ssq; long ldpart;
     double* scratch;                    // [OZ2_SCRATCH_SLOTS][128][128]
+    long long* prof;                    // option "ozprof" (gpk_oz_pair2_kernel): per CTA 8 clock64() sums, else nullptr
 };
 
 // ---------------------------------------------------------------------------------------
@@ -706,6 +711,7 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
     const uint32_t red = base + OZQ_NSTG * OZQ_STAGE + 256;          // 2 x [4 lane groups][128 columns]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = (int)oz_cluster_rank();
+    const uint32_t tmem_slot_own = tmem_slot + 8u * (uint32_t)crank;     // see gpk_oz_pair_kernel
     const int unit = (int)blockIdx.x / 2, units = (int)gridDim.x / 2;
     const int nrow_tiles = g.nb / 2, total = nrow_tiles * g.ncb;
 
@@ -717,7 +723,7 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
         fence_proxy_async();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_own), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -725,11 +731,12 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
     oz_cluster_sync();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot_own) : "memory");
 
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
+            long long w_empty = 0;
             for (int t = unit; t < total; t += units) {
                 int ibt, cb;
                 oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
@@ -740,7 +747,11 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
                     const int ns = pass == 0 ? OZ_S : OZQ_LOW;       // levels >= 4 touch every slice, levels < 4 only slices 0..3
                     for (int kb = 0; kb < nkb; ++kb, ++it) {
                         const int s = it % OZQ_NSTG;
-                        if (it >= OZQ_NSTG) oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((it / OZQ_NSTG - 1) & 1));
+                        if (it >= OZQ_NSTG) {
+                            const long long c0 = g.prof ? clock64() : 0;
+                            oz_mbar_wait(bar_empty + 8 * s, (uint32_t)((it / OZQ_NSTG - 1) & 1));
+                            if (g.prof) w_empty += clock64() - c0;
+                        }
                         const uint32_t st = base + s * OZQ_STAGE;
                         const uint32_t lbar = oz_map_to_rank(bar_full + 8 * s, 0);
                         if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(2 * ns * (OZ_A_SLICE + OZQ_BH_SLICE)));
@@ -751,23 +762,32 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
                     }
                 }
             }
+            if (g.prof) g.prof[(long)blockIdx.x * 8 + 3] = w_empty;
         }
     } else if (warp == 1) {
         if (lane == 0 && crank == 0) {
             const uint32_t idesc = oz_idesc(2 * OZ_TM, OZQ_NT);
             int it = 0, n = 0;                                       // n = 2 * (tiles done) + pass
+            long long w_full = 0, w_tempty = 0;
+            const long long c_start = g.prof ? clock64() : 0;
             for (int t = unit; t < total; t += units) {
                 int ibt, cb;
                 oz_tile_of(t, nrow_tiles, g.ncb, g.group, ibt, cb);
                 const int nkb = (2 * ibt + 2) * OZ_TM / OZ_KB;
                 for (int pass = 0; pass < 2; ++pass, ++n) {
                     if (n > 0) {                                     // both CTAs' epilogues have drained the previous accumulators
+                        const long long c0 = g.prof ? clock64() : 0;
                         oz_mbar_wait(bar_tempty, (uint32_t)((n - 1) & 1));
+                        if (g.prof) w_tempty += clock64() - c0;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     for (int kb = 0; kb < nkb; ++kb, ++it) {
                         const int s = it % OZQ_NSTG;
-                        oz_mbar_wait(bar_full + 8 * s, (uint32_t)((it / OZQ_NSTG) & 1));
+                        {
+                            const long long c0 = g.prof ? clock64() : 0;
+                            oz_mbar_wait(bar_full + 8 * s, (uint32_t)((it / OZQ_NSTG) & 1));
+                            if (g.prof) w_full += clock64() - c0;
+                        }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t st = base + s * OZQ_STAGE;
                         if (pass == 0) {
@@ -795,6 +815,12 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
                     }
                     oz_commit_pair(bar_tfull);
                 }
+            }
+            if (g.prof) {
+                g.prof[(long)blockIdx.x * 8 + 0] = clock64() - c_start;
+                g.prof[(long)blockIdx.x * 8 + 1] = w_full;
+                g.prof[(long)blockIdx.x * 8 + 2] = w_tempty;
+                g.prof[(long)blockIdx.x * 8 + 6] = n / 2;
             }
         }
     } else {

@@ -20,8 +20,9 @@ y = np.sinc(X * 10 - 5).sum(axis=1) + 0.01 * rng.randn(N)
 Xs = np.random.RandomState(4321).rand(M, D)
 theta = np.concatenate(([0.0], np.full(D, np.log(D / 4.0))))
 out = {}
-for label, opts in (("persistent", {"ozpersist": 1}), ("same_kernel_one_tile_per_cta", {"ozpersist": 2}),
-                    ("persistent_pair", {"ozpersist": 1, "ozpair": 1}), ("pair_one_tile_per_pair", {"ozpersist": 2, "ozpair": 1})):
+for label, opts in (("default_cta_pair_two_passes", {}), ("cta_pair_two_passes_persistent", {"ozpersist": 1}),
+                    ("persistent", {"ozpersist": 1, "ozpair": 0, "oztile": 64}), ("same_kernel_one_tile_per_cta", {"ozpersist": 2, "ozpair": 0, "oztile": 64}),
+                    ("persistent_pair", {"ozpersist": 1, "ozpair": 1, "oztile": 64}), ("pair_one_tile_per_pair", {"ozpersist": 2, "ozpair": 1, "oztile": 64})):
     h = _lib.Handle(0)
     h.set_option("ozprof", 1)
     for k, v in opts.items():

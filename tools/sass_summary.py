@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """SASS evidence per kernel of robo_b200/libgpk.so (runs without a GPU): for every kernel the count of the instructions
-that prove what it is made of — DMMA (fp64 tensor pipe), DFMA/DADD/DMUL (fp64 vector pipe), UTMALDG (TMA loads),
+that prove what it is made of — DMMA (fp64 tensor pipe), UTCIMMA (tcgen05.mma kind::i8; .2CTA = cta_group::2), LDTM (tcgen05.ld),
+UTCBAR (tcgen05.commit), DFMA/DADD/DMUL (fp64 vector pipe), UTMALDG (TMA loads),
 SYNCS (mbarrier), LDS/STS, LDG/STG, MUFU, BAR, plus registers from the ELF.  Output: profiles/<tag>_sass_summary.txt
     python tools/sass_summary.py r02"""
 import collections
@@ -11,7 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "robo_b200", "libgpk.so")
-KEYS = ["DMMA", "DFMA", "DADD", "DMUL", "UTMALDG", "SYNCS", "LDS", "STS", "LDG", "STG", "MUFU", "BAR", "LDGSTS", "ATOM", "RED"]
+KEYS = ["DMMA", "UTCIMMA", "UTCIMMA.2CTA", "LDTM", "UTCBAR", "DFMA", "DADD", "DMUL", "UTMALDG", "SYNCS", "LDS", "STS", "LDG", "STG", "MUFU", "BAR",
+        "LDGSTS", "ATOM", "RED"]
 
 
 def main():
@@ -48,9 +50,14 @@ def main():
             for k in KEYS:
                 if op == k or op.startswith(k + "."):
                     counts[name][k] += 1
-    demangle = subprocess.run(["c++filt"] + list(counts), stdout=subprocess.PIPE, text=True).stdout.splitlines()
+    try:
+        demangle = subprocess.run(["c++filt"] + list(counts), stdout=subprocess.PIPE, text=True).stdout.splitlines()
+    except OSError:
+        demangle = []
+    if len(demangle) != len(counts):
+        demangle = list(counts)                          # no c++filt on this box: keep the mangled names
     out = ["# SASS summary of robo_b200/libgpk.so (%s), cuobjdump -sass; one line per kernel" % arch,
-           "# %-70s %6s %5s %6s " % ("kernel", "instr", "regs", "smem") + " ".join("%7s" % k for k in KEYS)]
+           "# %-70s %6s %5s %6s " % ("kernel", "instr", "regs", "smem") + " ".join("%7s" % k[-7:] for k in KEYS)]
     tot = collections.Counter()
     for (mangled, c), nice in zip(counts.items(), demangle):
         nice = re.sub(r"\(.*", "", nice).replace("void ", "")
