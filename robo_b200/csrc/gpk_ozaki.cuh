@@ -319,9 +319,9 @@ gpk_oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
     const uint32_t red = base + OZP_NSTG * OZP_STAGE + 256;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = (int)oz_cluster_rank();
-    // each CTA of the pair publishes the (identical) TMEM base address in its own word: the collective cta_group::2
-    // allocation writes through both CTAs' shared memory, and two words keep compute-sanitizer's racecheck quiet
-    const uint32_t tmem_slot_own = tmem_slot + 8u * (uint32_t)crank;
+    // Both CTAs of the pair pass the SAME shared-memory offset to the collective cta_group::2 allocation (a per-rank offset
+    // was tried to silence compute-sanitizer and faults with "misaligned address"): racecheck reports the two CTAs'
+    // writes of the identical TMEM base address through the pair as a hazard on this word (profiles/r02_sanitizer_racecheck.txt)
     int ibp, cb;
     oz_tile_of((int)blockIdx.x / 2, g.nb / 2, g.ncb, g.group, ibp, cb);
     const int ib = 2 * ibp + crank;
@@ -334,7 +334,7 @@ gpk_oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
         fence_proxy_async();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_own), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -342,7 +342,7 @@ gpk_oz_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_consta
     oz_cluster_sync();                                               // both CTAs' barriers and TMEM exist
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot_own) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -456,7 +456,6 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     const uint32_t red = base + NSTG * STAGE + 256;                  // 2 x [4 lane groups][64 columns]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = PAIR ? (int)oz_cluster_rank() : 0;
-    const uint32_t tmem_slot_own = tmem_slot + 8u * (uint32_t)crank;     // see gpk_oz_pair_kernel
     const int unit = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x, units = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
     const int rows_per_tile = PAIR ? 2 : 1;
     const int nrow_tiles = g.nb / rows_per_tile, total = nrow_tiles * g.ncb;
@@ -470,10 +469,10 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     }
     if (warp == 1) {
         if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_own), "r"(512u) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_own), "r"(512u) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
@@ -482,7 +481,7 @@ gpk_oz_persist_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_con
     if (PAIR) oz_cluster_sync();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot_own) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -711,7 +710,6 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
     const uint32_t red = base + OZQ_NSTG * OZQ_STAGE + 256;          // 2 x [4 lane groups][128 columns]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = (int)oz_cluster_rank();
-    const uint32_t tmem_slot_own = tmem_slot + 8u * (uint32_t)crank;     // see gpk_oz_pair_kernel
     const int unit = (int)blockIdx.x / 2, units = (int)gridDim.x / 2;
     const int nrow_tiles = g.nb / 2, total = nrow_tiles * g.ncb;
 
@@ -723,7 +721,7 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
         fence_proxy_async();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_own), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -731,7 +729,7 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
     oz_cluster_sync();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot_own) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {
         if (lane == 0) {
