@@ -96,6 +96,58 @@ __device__ __forceinline__ void oz_tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// The same load without the wait, and one wait for two loads: the drains of the pair kernel read two levels per round trip
+// to TMEM instead of one (the wait costs a full TMEM latency and there is one epilogue warp per scheduler to hide it).
+// The "+r" operands tie every destination register to the wait, so no consumer can be scheduled above it.
+__device__ __forceinline__ void oz_tmem_ld32_issue(uint32_t addr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(addr));
+}
+#define OZ_REGS32(v) "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), \
+                     "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), \
+                     "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), \
+                     "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+__device__ __forceinline__ void oz_tmem_ld_wait(uint32_t (&a)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : OZ_REGS32(a) :: "memory");
+}
+__device__ __forceinline__ void oz_tmem_ld_wait(uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : OZ_REGS32(a) :: "memory");
+    asm volatile("" : OZ_REGS32(b) :: "memory");
+}
+// exact int32 -> fp64 without the quarter-rate I2F.F64: 2^52 + 2^31 + d as bit pattern, minus the constant
+__device__ __forceinline__ double oz_i2d(uint32_t d) {
+    return __hiloint2double(0x43300000, (int)(d ^ 0x80000000u)) - 4503601774854144.0;
+}
+// v[j] += scale(lvl) * accumulator(lvl)[j] for the levels hi, hi - 1, ..., lo (least significant first), two levels per wait;
+// `col(lvl)` = TMEM column of level lvl's first column of this 32-column chunk
+template <int HI, int LO, int LVL_COLS, int LVL_BASE>
+__device__ __forceinline__ void oz_drain_levels(uint32_t lane_base, int c0, double (&v)[32]) {
+    uint32_t da[32], db[32];
+#pragma unroll
+    for (int lvl = HI; lvl >= LO; lvl -= 2) {
+        oz_tmem_ld32_issue(lane_base + (uint32_t)((lvl - LVL_BASE) * LVL_COLS + c0), da);
+        if (lvl - 1 >= LO) {
+            oz_tmem_ld32_issue(lane_base + (uint32_t)((lvl - 1 - LVL_BASE) * LVL_COLS + c0), db);
+            oz_tmem_ld_wait(da, db);
+        } else
+            oz_tmem_ld_wait(da);
+        const double sa = ldexp(1.0, -8 * (lvl + 2));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fma(oz_i2d(da[j]), sa, v[j]);
+        if (lvl - 1 >= LO) {
+            const double sb = ldexp(1.0, -8 * (lvl + 1));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fma(oz_i2d(db[j]), sb, v[j]);
+        }
+    }
+}
+
 // ---- operand split ------------------------------------------------------------------------------------------------
 // per-row exponent e[r] = oz_exponent(max |A[r][:]|); emax receives the maximum over the rows (atomicMax)
 __global__ void gpk_oz_rowexp_kernel(const double* __restrict__ A, long ld, int cols, int* __restrict__ e, int* __restrict__ emax) {
@@ -845,14 +897,7 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
                 double v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.0;
-#pragma unroll 1
-                for (int lvl = OZ_S - 1; lvl >= OZQ_LOW; --lvl) {
-                    uint32_t d[32];
-                    oz_tmem_ld32(lane_base + (uint32_t)((lvl - OZQ_LOW) * OZQ_NT + c0), d);
-                    const double sf = ldexp(1.0, -8 * (lvl + 2));
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
-                }
+                oz_drain_levels<OZ_S - 1, OZQ_LOW, OZQ_NT, OZQ_LOW>(lane_base, c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sc[(size_t)(c0 + j) * OZ_TM + rl] = v[j];
             }
@@ -868,14 +913,7 @@ gpk_oz_pair2_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
                 double v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = sc[(size_t)(c0 + j) * OZ_TM + rl];
-#pragma unroll 1
-                for (int lvl = OZQ_LOW - 1; lvl >= 0; --lvl) {
-                    uint32_t d[32];
-                    oz_tmem_ld32(lane_base + (uint32_t)(lvl * OZQ_NT + c0), d);
-                    const double sf = ldexp(1.0, -8 * (lvl + 2));
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fma((double)(int)d[j], sf, v[j]);
-                }
+                oz_drain_levels<OZQ_LOW - 1, 0, OZQ_NT, 0>(lane_base, c0, v);
                 if (c0 == OZQ_NT - 32) {                             // TMEM is read out: hand it back before the reductions
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     asm volatile("bar.sync 2, 128;" ::: "memory");
