@@ -553,6 +553,31 @@ def test_edge_shapes(N, D, M):
     assert abs(model.gp.log_likelihood(y) - ll_ref) <= 1e-10 * max(1.0, abs(ll_ref))
 
 
+@pytest.mark.parametrize("N,D,M", [(100, 3, 2048), (129, 2, 2049), (256, 16, 2177), (640, 5, 4099), (384, 8, 2500)])
+def test_int8_scoring_edge_shapes(N, D, M):
+    """Ragged sizes on the default large-batch path (int8 tensor-pipe contraction): one, two (CTA pair), three (odd: one-pass
+    kernel) and five row blocks, candidate counts that are not multiples of the 128 / 64-candidate tiles."""
+    from robo_b200 import _lib
+    rng = np.random.RandomState(N * 7 + D)
+    X, Xs = rng.rand(N, D), rng.rand(M, D)
+    y = np.sin(X.sum(axis=1)) + 0.5
+    theta = np.concatenate(([0.2], rng.uniform(-0.5, 0.5, D)))
+    h, logdet, ll, diag_add, mean = _handle_for("matern52", theta, X, y, 1e-3)
+    h.set_option("ozaki", 1)
+    eta = float(np.min(y))
+    r = h.acq(Xs, _lib.ACQ_EI, eta, 0.0, want_values=True, want_moments=True)
+    t = h.timings()
+    h.close()
+    assert t["launches_ozaki"] >= 1, t
+    st = O.gp_fit(oracle_kernel("matern52", theta, D), X, y, noise=1e-3, normalize_input=False)
+    mu_ref, var_ref = O.gp_predict_var_only_fast(st, Xs)
+    assert_mean_close(r["mu"], mu_ref, np.append(y, [0.0, 1.0]))
+    assert_var_close(r["var"], var_ref, float(np.exp(theta[0])))
+    ei_ref = O.acq_ei(mu_ref, var_ref, eta)
+    assert_acq_close(r["values"], ei_ref, rtol=1e-8, atol=1e-13)
+    assert r["best_idx"] == int(np.argmax(ei_ref))
+
+
 def test_bad_arguments_raise_value_errors():
     from robo_b200 import _lib
     h = _lib.Handle(0)
