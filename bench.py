@@ -530,7 +530,8 @@ def run_ours(args, rank, world, local_rank):
     dmma_peak, dfma_peak = h.measure_fp64_peaks()
     used_int8 = tim.get("launches_ozaki", 0) > 0
     int8_peak = h.measure_int8_peak() if used_int8 else None
-    int8_peak_sustained = h.measure_int8_peak_sustained(0.5) if used_int8 else None
+    int8_peak_sustained = h.measure_int8_peak_sustained(0.5, True) if used_int8 else None
+    int8_peak_sustained_const = h.measure_int8_peak_sustained(0.5, False) if used_int8 else None
     # ---- CPU baselines on this box's host cores (bounded sample; rank 0, N = 1 only) ----
     cpu, cpu_opt = None, None
     if world == 1 and not args.no_cpu_baseline:
@@ -572,13 +573,15 @@ def run_ours(args, rank, world, local_rank):
                                                     ", persistent tile walk" if int(tim.get("ozaki_kernel_variant", 0)) & 8 else "", int(pairs)),
                         achieved=int8_achieved, peak=int8_peak_sustained, unit="TFLOP/s", frac=int8_achieved / int8_peak_sustained,
                         peak_burst=int8_peak, frac_of_burst_peak=int8_achieved / int8_peak,
+                        peak_sustained_constant_operands=int8_peak_sustained_const,
                         ops="int8 multiply-accumulate counted as 2 ops (TOP/s)",
                         peak_source="measured live on this GPU: tcgen05.mma kind::i8 128x128x32 issue rate from shared memory, "
-                                    "launched back to back for 0.5 s, second half timed (gpk_measure_int8_peak_sustained): the "
-                                    "contraction is timed inside a long step and the int8 pipe runs into sw_power_cap, so the "
-                                    "sustained figure is the denominator (as MEASURED_PEAKS.json does for bf16: 1376 sustained / "
-                                    "1667 burst); peak_burst = one 0.3 ms launch (gpk_measure_int8_peak); nominal dense int8 = "
-                                    "4500 TOP/s",
+                                    "pseudo-random operand bytes, launched back to back for 0.5 s, second half timed "
+                                    "(gpk_measure_int8_peak_sustained): the contraction is timed inside a long step and the int8 pipe "
+                                    "runs into sw_power_cap, so the sustained figure is the denominator (as MEASURED_PEAKS.json does "
+                                    "for bf16: 1376 sustained / 1667 burst); peak_sustained_constant_operands = the same with a "
+                                    "constant operand pattern (no switching activity); peak_burst = one 0.3 ms launch "
+                                    "(gpk_measure_int8_peak); nominal dense int8 = 4500 TOP/s",
                         traffic=oz_traffic,
                         traffic_source="read at run time from the committed capture %s (ncu --set full, one 16384-candidate "
                                        "launch); algorithmic minimum = %d slices x (L^-1 lower triangle 8.4 MB + K* 67 MB) "

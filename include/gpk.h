@@ -290,8 +290,10 @@ int gpk_measure_fp64_peaks(gpk_handle* h, double* dmma_tflops, double* dfma_tflo
  * accumulator in TMEM): the roofline denominator of the option-"ozaki" contraction. */
 int gpk_measure_int8_peak(gpk_handle* h, double* tops);
 /* the same kernel launched back to back for `seconds` (<= 10); reports the rate of the second half, i.e. at the SM clock
- * the board's power limit allows for this pipe: the denominator for a kernel timed inside a long step. */
-int gpk_measure_int8_peak_sustained(gpk_handle* h, double seconds, double* tops);
+ * the board's power limit allows for this pipe: the denominator for a kernel timed inside a long step.
+ * random_operands = 0: constant operand pattern (no switching activity: does not reach the power limit); 1: pseudo-random
+ * bytes, the statistics of real digit slices. */
+int gpk_measure_int8_peak_sustained(gpk_handle* h, double seconds, int random_operands, double* tops);
 
 /* ---- introspection (tests / debugging) ----------------------------------------------- */
 int gpk_get_factor(gpk_handle* h, double* L /* n x n row-major, lower */);

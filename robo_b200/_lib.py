@@ -64,7 +64,7 @@ _SIGNATURES = {
     "gpk_nll_grad": [_vp, C.c_double, _dp],
     "gpk_measure_fp64_peaks": [_vp, _dp, _dp],
     "gpk_measure_int8_peak": [_vp, _dp],
-    "gpk_measure_int8_peak_sustained": [_vp, C.c_double, _dp],
+    "gpk_measure_int8_peak_sustained": [_vp, C.c_double, C.c_int, _dp],
     "gpk_get_factor": [_vp, _dp],
     "gpk_get_linv": [_vp, _dp],
     "gpk_get_z": [_vp, _dp],
@@ -395,10 +395,11 @@ class Handle(object):
         self._check(self.lib.gpk_measure_int8_peak(self._h, C.byref(a)))
         return a.value
 
-    def measure_int8_peak_sustained(self, seconds=0.4):
-        """-> the same issue rate held for `seconds` (second half timed): what the power limit leaves of the burst figure."""
+    def measure_int8_peak_sustained(self, seconds=0.4, random_operands=True):
+        """-> the same issue rate held for `seconds` (second half timed): what the power limit leaves of the burst figure.
+        random_operands: pseudo-random operand bytes (switching activity of real digit slices) instead of a constant pattern."""
         a = C.c_double()
-        self._check(self.lib.gpk_measure_int8_peak_sustained(self._h, float(seconds), C.byref(a)))
+        self._check(self.lib.gpk_measure_int8_peak_sustained(self._h, float(seconds), 1 if random_operands else 0, C.byref(a)))
         return a.value
 
     # -- introspection ----------------------------------------------------------------

@@ -2453,7 +2453,7 @@ int gpk_measure_int8_peak(gpk_handle* h, double* tops) {
     for (int rep = 0; rep < 3; ++rep) {
         float ms = 0.f;
         CK(cudaEventRecord(e0, h->stream));
-        gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters);
+        gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters, 0);
         CKL();
         CK(cudaEventRecord(e1, h->stream));
         CK(cudaEventSynchronize(e1));
@@ -2466,7 +2466,7 @@ int gpk_measure_int8_peak(gpk_handle* h, double* tops) {
     return GPK_OK;
 }
 
-int gpk_measure_int8_peak_sustained(gpk_handle* h, double seconds, double* tops) {
+int gpk_measure_int8_peak_sustained(gpk_handle* h, double seconds, int random_operands, double* tops) {
     if (!h || !tops || !(seconds > 0.0) || seconds > 10.0) return GPK_BAD_ARG;
     CK(cudaSetDevice(h->device));
     // back-to-back launches of the issue-rate kernel for `seconds`; the rate of the SECOND half is reported: by then the
@@ -2478,15 +2478,15 @@ int gpk_measure_int8_peak_sustained(gpk_handle* h, double seconds, double* tops)
     CK(cudaEventCreate(&e1));
     float ms1 = 0.f;
     CK(cudaEventRecord(e0, h->stream));
-    gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters);
+    gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters, random_operands);
     CKL();
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&ms1, e0, e1));
     const int n_half = std::max(1, (int)(0.5 * seconds * 1e3 / std::max(ms1, 1e-3f)));
-    for (int i = 0; i < n_half; ++i) gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters);
+    for (int i = 0; i < n_half; ++i) gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters, random_operands);
     CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < n_half; ++i) gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters);
+    for (int i = 0; i < n_half; ++i) gpk_peak_i8_kernel<<<blocks, 128, smem, h->stream>>>(iters, random_operands);
     CKL();
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));

@@ -1240,13 +1240,19 @@ inline size_t cov_oz_smem_bytes(int n_terms, int cc) { return (size_t)n_terms * 
 // TMEM accumulator; no loads in the loop.  tools/microbench/i8_umma_probe.cu checks the same instruction against a
 // CPU integer GEMM.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) gpk_peak_i8_kernel(int iters)
+__global__ void __launch_bounds__(128, 1) gpk_peak_i8_kernel(int iters, int random_operands)
 {
     extern __shared__ unsigned char pk_raw[];
     const uint32_t base = (smem_u32(pk_raw) + 1023u) & ~1023u;            // A: 128 x 64 B, B: 128 x 64 B (64B swizzle atoms)
     const uint32_t bar = base + 2 * 8192, slot = bar + 8;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int e = tid; e < 4096; e += 128) asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + 4u * e), "r"(0x01010101u * (e & 3)) : "memory");
+    // operands: a constant pattern (no switching activity in the datapath) or pseudo-random bytes (the statistics of real
+    // digit slices: this is what decides how far the power limit lets the pipe run in a long measurement)
+    for (int e = tid; e < 4096; e += 128) {
+        uint32_t w = 0x01010101u * (e & 3);
+        if (random_operands) { w = (uint32_t)e * 2654435761u + blockIdx.x * 40503u; w ^= w >> 15; w *= 2246822519u; w ^= w >> 13; }
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + 4u * e), "r"(w) : "memory");
+    }
     if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "r"(128u) : "memory");
