@@ -608,8 +608,11 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": "common candidate list of %d rows, contiguous shards x%d (gpk_shard_bounds), fit state "
                                   "replicated, one 16-byte ncclAllGather + device merge per step inside libgpk.so"
                                   % (M_total, world),
-                   "l2": "working set per step (L^-1 134 MB + K* chunk %d MB) exceeds the 126 MB L2; no flush needed"
-                         % (rows * N_TRAIN * 8 // 2 ** 20)},
+                   "l2": ("working set per step (int8 digit slices: L^-1 %d MB + K* %d MB per chunk, %d chunks per step) exceeds "
+                          "the 126 MB L2; no flush needed"
+                          % (7 * N_TRAIN * N_TRAIN // 2 ** 20, 7 * rows * N_TRAIN // 2 ** 20, (M + rows - 1) // rows)) if used_int8 else
+                         ("working set per step (L^-1 134 MB + K* chunk %d MB) exceeds the 126 MB L2; no flush needed"
+                          % (rows * N_TRAIN * 8 // 2 ** 20))},
         "fit_ms": float(np.median(fit_ms[1:])), "fit_breakdown_ms": {k: t_fit[k] for k in ("kbuild_ms", "potrf_ms", "linv_ms")},
         "loglik": ll, "fit_append_8rows_ms": append_ms,
         "argmax_check": argmax_check,
