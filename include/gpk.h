@@ -78,9 +78,10 @@ const char* gpk_version(void);
  *   "ozpair"    1 = CTA pairs (tcgen05 cta_group::2, cluster of 2): 256 rows of L^-1 per pair, each CTA stages half of the
  *               K* slice tiles [default, with "oztile" 128: gpk_oz_pair2_kernel; needs an even number of 128-row blocks,
  *               otherwise the one-pass single-CTA kernel runs]; 0 = one CTA per tile
- *   "ozpersist" 0 = one CTA (pair) per tile [default]; 1 = one CTA (pair) per SM walks the tile list; 2 = the persistent
- *               kernel launched with one tile per CTA (profiling aid).  Measured: 3.3 ms alone, 4.0 - 4.3 ms inside a
- *               scoring step (profiles/r02_int8_variants_bench.txt)
+ *   "ozpersist" 0 = one CTA (pair) per tile; 1 = one CTA (pair) per SM walks the tile list; 2 = the persistent kernel
+ *               launched with one tile per CTA (profiling aid); 3 = automatic [default]: persistent for N <= 1024, where
+ *               tiles are short (configs[2] maximisation 23.6 -> 22.1 ms), one tile per CTA above (N = 4096: the
+ *               persistent walk measured 3.5 % slower inside a scoring step, profiles/r02_int8_variants_bench.txt)
  *   "ozpdl"     1 = the look-ahead K* builder runs as a small resident grid ("covctas" CTAs per SM) that triggers a
  *               programmatic dependent launch of the contraction behind it on the same stream (the two really co-run);
  *               0 = builder on the side stream (the block scheduler places it in the contraction's tail) [default: the

@@ -63,7 +63,9 @@ struct gpk_handle {
     int oz_prof = 0;                // 1: gpk_oz_persist_kernel accumulates clock64() wait sums per CTA (gpk_get_oz_profile)
     DevBuf oz_profbuf;
     int oz_prof_ctas = 0;
-    int oz_persist = 0;             // 1: one CTA (pair) per SM walks the tile list (gpk_oz_persist_kernel); 0: one CTA (pair) per tile
+    int oz_persist = 3;             // 1: one CTA (pair) per SM walks the tile list; 0: one CTA (pair) per tile; 2: the persistent kernel with one
+                                    // tile per CTA (profiling); 3 = automatic [default]: persistent for N <= 1024 (short tiles: -7 % on a
+                                    // configs[2] maximisation), one tile per CTA above (N = 4096: the persistent walk is 3.5 % slower)
     int oz_pair = 1;                // 1: CTA pairs (tcgen05 cta_group::2) when the row-block count is even
     CUtensorMap mapOzKh, mapOzKh2;  // K* slices in 32-row boxes (the half tiles of a pair)
     int oz_fused = 1;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
@@ -975,6 +977,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             CK(cudaEventRecord(h->ev_g0[ci], h->stream));
         }
         const bool oz_pair_ok = h->oz_pair && (h->nb % 2) == 0;
+        const int oz_persist = h->oz_persist == 3 ? (h->nb <= 8 ? 1 : 0) : h->oz_persist;
         if (use_oz && h->oz_tile == 128 && (oz_pair_ok || !h->oz_pair)) {
             Oz2Args o;
             o.nb = h->nb; o.ncb = (int)(mcp / OZ2_T); o.NP = (int)NP; o.rows = (int)cap;
@@ -982,11 +985,11 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             o.eP = ptr<int>(h->oz_eP); o.eK = oz_eK;
             o.part_ssq = a.part_ssq; o.ldpart = a.ldpart; o.scratch = ptr<double>(h->oz_scratch);
             o.prof = nullptr;
-            h->oz_last_variant = oz_pair_ok ? 4 + (h->oz_persist == 1 ? 8 : 0) : 3;
+            h->oz_last_variant = oz_pair_ok ? 4 + (oz_persist == 1 ? 8 : 0) : 3;
             if (oz_pair_ok) {
                 // CTA pair, 256 x 128 per pair in two passes; its K* half tile (64 rows x 64 B) is the box of mapOzK
                 const int tiles = (o.nb / 2) * o.ncb;
-                const unsigned grid = (unsigned)(2 * (h->oz_persist == 1 ? std::min(tiles, std::max(h->n_sm, 2) / 2) : tiles));
+                const unsigned grid = (unsigned)(2 * (oz_persist == 1 ? std::min(tiles, std::max(h->n_sm, 2) / 2) : tiles));
                 if (h->oz_prof) {
                     if ((rc = ensure(h, h->oz_profbuf, (size_t)grid * 64))) return rc;
                     CK(cudaMemsetAsync(h->oz_profbuf.p, 0, (size_t)grid * 64, h->stream));
@@ -1012,20 +1015,20 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             const int sms = std::max(h->n_sm, 2);
             // "ozpersist" 1: one CTA (pair) per SM walks the tile list; 2: the same kernel, one tile per CTA (pair); 0: the
             // one-tile kernels
-            const int units = h->oz_persist == 1 ? std::min(tiles, pair ? sms / 2 : sms) : tiles;
-            h->oz_last_variant = (pair ? 2 : 1) + (h->oz_persist == 1 ? 8 : 0);
-            if (h->oz_prof && h->oz_persist) {
+            const int units = oz_persist == 1 ? std::min(tiles, pair ? sms / 2 : sms) : tiles;
+            h->oz_last_variant = (pair ? 2 : 1) + (oz_persist == 1 ? 8 : 0);
+            if (h->oz_prof && oz_persist) {
                 const int ctas = pair ? 2 * units : units;
                 if ((rc = ensure(h, h->oz_profbuf, (size_t)ctas * 64))) return rc;
                 CK(cudaMemsetAsync(h->oz_profbuf.p, 0, (size_t)ctas * 64, h->stream));
                 o.prof = ptr<long long>(h->oz_profbuf);
                 h->oz_prof_ctas = ctas;
             }
-            if (pair && h->oz_persist)
+            if (pair && oz_persist)
                 CK(launch_oz(gpk_oz_persist_kernel<true>, (unsigned)(2 * units), (size_t)OZP_PERSIST_SMEM, h->stream, true, dependent, h->mapOzP, mk, o));
             else if (pair)
                 CK(launch_oz(gpk_oz_pair_kernel, (unsigned)(2 * units), (size_t)OZP_SMEM, h->stream, true, dependent, h->mapOzP, mk, o));
-            else if (h->oz_persist)
+            else if (oz_persist)
                 CK(launch_oz(gpk_oz_persist_kernel<false>, (unsigned)units, (size_t)OZ_PERSIST_SMEM, h->stream, false, dependent, h->mapOzP, mk, o));
             else
                 CK(launch_oz(gpk_oz_vargemm_kernel, (unsigned)tiles, (size_t)OZ_SMEM, h->stream, false, dependent, h->mapOzP, mk, o));
@@ -1187,7 +1190,7 @@ int gpk_set_option(gpk_handle* h, const char* key, long value) {
         return GPK_OK;
     }
     if (!strcmp(key, "ozpersist")) {
-        if (value < 0 || value > 2) BAD("ozpersist must be 0, 1 or 2");
+        if (value < 0 || value > 3) BAD("ozpersist must be 0, 1, 2 or 3");
         h->oz_persist = (int)value;
         return GPK_OK;
     }
