@@ -79,9 +79,10 @@ const char* gpk_version(void);
  *               K* slice tiles [default, with "oztile" 128: gpk_oz_pair2_kernel; needs an even number of 128-row blocks,
  *               otherwise the one-pass single-CTA kernel runs]; 0 = one CTA per tile
  *   "ozpersist" 0 = one CTA (pair) per tile; 1 = one CTA (pair) per SM walks the tile list; 2 = the persistent kernel
- *               launched with one tile per CTA (profiling aid); 3 = automatic [default]: persistent for N <= 1024, where
- *               tiles are short (configs[2] maximisation 23.6 -> 22.1 ms), one tile per CTA above (N = 4096: the
- *               persistent walk measured 3.5 % slower inside a scoring step, profiles/r02_int8_variants_bench.txt)
+ *               launched with one tile per CTA (profiling aid); 3 = automatic [default]: persistent for N <= 3072, where a
+ *               scoring pass is 7 - 13 % shorter (the resident grid lets the next chunk's K* builder run beside it;
+ *               profiles/r02_persistent_walk_by_n.json, configs[2] maximisation 23.6 -> 22.1 ms), one tile per CTA above
+ *               (N = 4096, D = 16, sustained: 3.5 % slower, profiles/r02_int8_variants_bench.txt)
  *   "ozpdl"     1 = the look-ahead K* builder runs as a small resident grid ("covctas" CTAs per SM) that triggers a
  *               programmatic dependent launch of the contraction behind it on the same stream (the two really co-run);
  *               0 = builder on the side stream (the block scheduler places it in the contraction's tail) [default: the

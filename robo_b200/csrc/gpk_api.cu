@@ -64,8 +64,8 @@ struct gpk_handle {
     DevBuf oz_profbuf;
     int oz_prof_ctas = 0;
     int oz_persist = 3;             // 1: one CTA (pair) per SM walks the tile list; 0: one CTA (pair) per tile; 2: the persistent kernel with one
-                                    // tile per CTA (profiling); 3 = automatic [default]: persistent for N <= 1024 (short tiles: -7 % on a
-                                    // configs[2] maximisation), one tile per CTA above (N = 4096: the persistent walk is 3.5 % slower)
+                                    // tile per CTA (profiling); 3 = automatic [default]: persistent for N <= 3072 (a scoring pass is 7 - 13 %
+                                    // shorter, profiles/r02_persistent_walk_by_n.json), one tile per CTA above (N = 4096, sustained: 3.5 % slower)
     int oz_pair = 1;                // 1: CTA pairs (tcgen05 cta_group::2) when the row-block count is even
     CUtensorMap mapOzKh, mapOzKh2;  // K* slices in 32-row boxes (the half tiles of a pair)
     int oz_fused = 1;               // 1: K* leaves the covariance builder as int8 digits (gpk_cov_oz_kernel); 0: fp64 K* + split + dot
@@ -977,7 +977,7 @@ int score_dev(gpk_handle* h, const double* dX, long m, int kind, double eta, dou
             CK(cudaEventRecord(h->ev_g0[ci], h->stream));
         }
         const bool oz_pair_ok = h->oz_pair && (h->nb % 2) == 0;
-        const int oz_persist = h->oz_persist == 3 ? (h->nb <= 8 ? 1 : 0) : h->oz_persist;
+        const int oz_persist = h->oz_persist == 3 ? (h->nb <= 24 ? 1 : 0) : h->oz_persist;
         if (use_oz && h->oz_tile == 128 && (oz_pair_ok || !h->oz_pair)) {
             Oz2Args o;
             o.nb = h->nb; o.ncb = (int)(mcp / OZ2_T); o.NP = (int)NP; o.rows = (int)cap;
